@@ -1,0 +1,165 @@
+/* stb200.h — C ABI of libstb200.so: the sm_100a kernels of the SimpleTuner diffusion training step.
+ *
+ * Plain pointers, sizes and element strides only; every pointer is a CUDA device pointer unless
+ * noted, every tensor is bf16 unless noted, `stream` is a cudaStream_t.  All functions return 0 on
+ * success and a negative code on failure; stb_last_error() returns the message of the last failure
+ * on the calling thread.  There is no CPU fallback: without an sm_100 device every launch fails.
+ *
+ * The reference (bghira/SimpleTuner) has no FFI for this path — its seams are Python-level
+ * (SURVEY.md §8b).  Each entry point below names the reference call site it replaces; the Python
+ * host layer (simpletuner_b200/) binds these through ctypes and mirrors the reference's module /
+ * processor interfaces on top.  INTEGRATION.md shows the reference-side binding.
+ */
+#ifndef STB200_H
+#define STB200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STB_OK 0
+#define STB_ERR_ARG (-1)
+#define STB_ERR_CUDA (-2)
+#define STB_ERR_UNSUPPORTED (-3)
+
+const char* stb_last_error(void);
+int stb_version(void);
+/* number of kernel launches issued by this library since load / last reset (bench gpu_launches) */
+long long stb_launch_count(void);
+void stb_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Linear layers.  Replaces nn.Linear / PEFT lora.Linear / torch.cat+Linear call sites:
+ *   flux/transformer.py:127-129,146-148 (q/k/v + added projections), :218-221 (out projections),
+ *   :460-464 (single-block proj_mlp / GELU / cat / proj_out / gate / residual),
+ *   :581-586 (FeedForward + gate + residual), :1001,1064,1506 (embedders, proj_out),
+ *   common.py:1094-1117 (LoRA: y = x W^T + b + s (x A^T) B^T as an extra K-segment).
+ *
+ *   D[b, s, n] = epi( sum_seg  A_seg[b, s, :K_seg] . W_seg[n, :K_seg]  + bias[n] )
+ *
+ * A_seg: [num_batches, rows_per_batch, K] with element strides (a_batch_stride, a_row_stride, 1).
+ * W_seg: [N, K] with row stride w_row_stride (K contiguous) — nn.Linear weight layout.
+ * Alignment: base pointers 16 B; strides multiples of 8 elements.
+ * ------------------------------------------------------------------------------------------- */
+enum stb_gemm_epilogue {
+  STB_EPI_STORE = 0,     /* D = acc + bias                                                     */
+  STB_EPI_GELU = 1,      /* D = gelu_tanh(acc + bias); aux (optional, written) = acc + bias    */
+  STB_EPI_GATE_RES = 2,  /* D = res + gate[b, n] * (acc + bias); nan_to_num optional           */
+  STB_EPI_MUL_DGELU = 3, /* D = acc * gelu_tanh'(aux[b, s, n])      (aux read)                 */
+  STB_EPI_ADD_RES = 4    /* D = acc + bias + res                                               */
+};
+
+typedef struct {
+  const void* a;
+  long long a_batch_stride, a_row_stride;
+  const void* w;
+  long long w_row_stride;
+  int K;
+} stb_gemm_seg;
+
+typedef struct {
+  int num_batches, rows_per_batch, N, nseg;
+  stb_gemm_seg seg[3];
+  void* d;
+  long long d_batch_stride, d_row_stride;
+  const void* bias; /* [N] or NULL */
+  int epi;
+  int nan_to_num;   /* STB_EPI_GATE_RES: nan->0, +-inf->+-65504 (flux/transformer.py:467,601) */
+  const void* gate; /* [num_batches, N] with batch stride */
+  long long gate_batch_stride;
+  const void* res;
+  long long res_batch_stride, res_row_stride;
+  void* aux;
+  long long aux_batch_stride, aux_row_stride;
+  int tile_mt, tile_bn; /* 0 = pick automatically; else MT in {1,2}, BN in {64,128,256} */
+} stb_gemm_args;
+
+int stb_gemm_bf16(const stb_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention.  Replaces F.scaled_dot_product_attention (non-causal, no mask, dropout 0) at
+ * flux/transformer.py:200-207 and its autograd backward.  q/k/v/o are [B, S, H, HD] views given by
+ * element strides (batch, token, head; HD contiguous).  lse: fp32 [B, H, Sq].  HD in {64, 128}.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, H, Sq, Sk, HD;
+  float scale;
+  const void *q, *k, *v;
+  long long q_b, q_s, q_h, k_b, k_s, k_h, v_b, v_s, v_h;
+  void* o;
+  long long o_b, o_s, o_h;
+  float* lse;
+} stb_attn_fwd_args;
+int stb_attn_fwd(const stb_attn_fwd_args* args, void* stream);
+
+typedef struct {
+  int B, H, Sq, Sk, HD;
+  float scale;
+  const void *q, *k, *v, *o, *d_o;
+  long long q_b, q_s, q_h, k_b, k_s, k_h, v_b, v_s, v_h, o_b, o_s, o_h, do_b, do_s, do_h;
+  const float* lse;  /* [B, H, Sq] from the forward */
+  float* delta;      /* [B, H, Sq] fp32 scratch: rowsum(dO * O) */
+  float* dq_accum;   /* [B, Sq, H, HD] fp32 scratch (zeroed by the call) */
+  void *dq, *dk, *dv;
+  long long dq_b, dq_s, dq_h, dk_b, dk_s, dk_h, dv_b, dv_s, dv_h;
+} stb_attn_bwd_args;
+int stb_attn_bwd(const stb_attn_bwd_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * adaLN modulation: out = LayerNorm(x, eps, no affine) * (1 + scale[b]) + shift[b]
+ * Replaces diffusers AdaLayerNormZero/ZeroSingle/Continuous + the norm2 modulation, as called at
+ * flux/transformer.py:386-412, 577-580, 589-593.  Backward is w.r.t. x only (+ optional residual
+ * gradient `add`), the modulation linears being frozen under LoRA training.
+ * ------------------------------------------------------------------------------------------- */
+int stb_ln_modulate_fwd(const void* x, long long x_b, long long x_s, const void* shift, const void* scale,
+                        long long mod_b, void* out, long long o_b, long long o_s, int B, int S, int D,
+                        float eps, void* stream);
+int stb_ln_modulate_bwd(const void* dy, long long dy_b, long long dy_s, const void* x, long long x_b,
+                        long long x_s, const void* scale, long long mod_b, const void* add, long long add_b,
+                        long long add_s, void* dx, long long dx_b, long long dx_s, int B, int S, int D,
+                        float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-head RMSNorm (fp32 variance, learned weight) + rotary embedding on q and k.
+ * Replaces attn.norm_q/norm_k/norm_added_q/norm_added_k + _apply_rotary_emb_anyshape
+ * (flux/transformer.py:73-98, 138-141, 159-162, 189-190).  src is the projection output
+ * [B, S, ...] holding q at column 0 and k at column k_off (head stride HD); rows s < s_split use
+ * the *_added weights (text stream), the rest the image-stream weights.  cos/sin: fp32 [S, HD] or NULL.
+ * ------------------------------------------------------------------------------------------- */
+int stb_qk_rmsnorm_rope_fwd(const void* src, long long src_b, long long src_s, int k_off, const void* wq,
+                            const void* wk, const void* wq_added, const void* wk_added, int s_split,
+                            const float* cos_t, const float* sin_t, void* q_out, void* k_out,
+                            long long dst_b, long long dst_s, int B, int S, int H, int HD, float eps,
+                            void* stream);
+int stb_qk_rmsnorm_rope_bwd(const void* dq, const void* dk, long long d_b, long long d_s, const void* src,
+                            long long src_b, long long src_s, int k_off, const void* wq, const void* wk,
+                            const void* wq_added, const void* wk_added, int s_split, const float* cos_t,
+                            const float* sin_t, void* dsrc, long long ds_b, long long ds_s, int B, int S,
+                            int H, int HD, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Flow-matching batch prep and loss (Flux 2x2 patchify folded into the index math).
+ *   stb_flow_prep_pack : noisy = (1 - sigma) * latents + sigma * noise  (common.py:4975-4992),
+ *                        written unpacked (optional) and packed (flux/__init__.py:25-30).
+ *   stb_flow_mse_loss  : mean_b mean_chw (pred.float() - (noise - latents).float())^2
+ *                        (common.py:4610-4611, 6286, 6426-6429) with pred in packed layout
+ *                        (unpack_latents, flux/__init__.py:33-44); optional d loss/d pred (packed).
+ * latents/noise: bf16 [B, C, Hh, Ww] contiguous; sigmas fp32 [B]; loss_out fp32 [1] (zeroed here).
+ * ------------------------------------------------------------------------------------------- */
+int stb_flow_prep_pack(const void* latents, const void* noise, const float* sigmas, void* noisy,
+                       void* packed, int B, int C, int Hh, int Ww, void* stream);
+int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* noise, float* loss_out,
+                      void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LoRA weight gradients: out[r, n] += alpha * sum_m L[m, r] * Rm[m, n]   (fp32 out, R in 16..64)
+ *   dA = s * (dY B)^T X   (L = dY B [M, r], Rm = X  [M, K])
+ *   dB^T = s * (X A^T)^T dY (L = X A^T [M, r], Rm = dY [M, N])
+ * Autograd of peft lora.Linear (reference common.py:1094-1117).
+ * ------------------------------------------------------------------------------------------- */
+int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, long long r_b, long long r_s,
+                  float* out, int B, int S, int R, int N, float alpha, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STB200_H */

@@ -1,0 +1,517 @@
+// simpletuner_b200 — C-ABI entry points (include/stb200.h): argument checking, TMA tensor-map
+// construction and kernel launches.  No torch types here; the Python host passes raw pointers.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/stb200.h"
+#include "attn_bwd.cuh"
+#include "attn_fwd.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define STB_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess) return fail(STB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define STB_LAUNCH_CHECK(name)                                                                  \
+  do {                                                                                          \
+    cudaError_t e_ = cudaGetLastError();                                                        \
+    if (e_ != cudaSuccess) return fail(STB_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                         \
+  } while (0)
+
+// ---------------------------------------------------------------- device / driver helpers
+int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return v;
+  }();
+  return n;
+}
+
+int check_device() {
+  static int ok = [] {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+  }();
+  if (!ok) return fail(STB_ERR_UNSUPPORTED, "libstb200 needs an sm_100 (B200) device; there is no CPU or other-arch fallback");
+  return 0;
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  int rank;
+  unsigned long long dims[4];
+  unsigned long long strides[3];
+  unsigned box[4];
+  bool operator==(const MapKey& o) const { return std::memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(&k);
+    size_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey); ++i) h = (h ^ p[i]) * 1099511628211ull;
+    return h;
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// bf16 tensor map, SWIZZLE_128B, dims/strides innermost-first (strides in BYTES for dims 1..rank-1)
+int make_map(CUtensorMap* out, const void* ptr, int rank, const unsigned long long* dims,
+             const unsigned long long* strides_bytes, const unsigned* box) {
+  MapKey key;
+  std::memset(&key, 0, sizeof key);
+  key.ptr = ptr;
+  key.rank = rank;
+  for (int i = 0; i < rank; ++i) key.dims[i] = dims[i], key.box[i] = box[i];
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  auto fn = encode_fn();
+  if (!fn) return fail(STB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail(STB_ERR_ARG, "tensor base pointer must be 16-byte aligned");
+  for (int i = 0; i + 1 < rank; ++i)
+    if (strides_bytes[i] & 15) return fail(STB_ERR_ARG, "tensor stride %d (%llu bytes) must be a multiple of 16 bytes", i, strides_bytes[i]);
+  cuuint64_t gdim[4];
+  cuuint64_t gstr[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) gdim[i] = dims[i], bx[i] = box[i], es[i] = 1;
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(STB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    if (g_maps.size() > 65536) g_maps.clear();
+    g_maps.emplace(key, *out);
+  }
+  return 0;
+}
+
+// fp32 map without swizzle (dq accumulator reduce-add)
+int make_map_f32(CUtensorMap* out, const void* ptr, int rank, const unsigned long long* dims,
+                 const unsigned long long* strides_bytes, const unsigned* box) {
+  auto fn = encode_fn();
+  if (!fn) return fail(STB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[4];
+  cuuint64_t gstr[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) gdim[i] = dims[i], bx[i] = box[i], es[i] = 1;
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(STB_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed with CUresult %d", int(r));
+  return 0;
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  STB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return 0;
+}
+
+// ---------------------------------------------------------------- GEMM
+template <int MT, int BN>
+int launch_gemm(const stb_gemm_args* a, cudaStream_t st) {
+  using Cfg = stb::GemmCfg<MT, BN>;
+  stb::GemmMaps maps;
+  std::memset(&maps, 0, sizeof maps);
+  stb::GemmParams p;
+  std::memset(&p, 0, sizeof p);
+  for (int s = 0; s < a->nseg; ++s) {
+    const stb_gemm_seg& g = a->seg[s];
+    if (g.K <= 0 || (g.K & 7)) return fail(STB_ERR_ARG, "segment %d: K=%d must be a positive multiple of 8", s, g.K);
+    unsigned long long ad[3] = {(unsigned long long)g.K, (unsigned long long)a->rows_per_batch,
+                                (unsigned long long)a->num_batches};
+    unsigned long long as[2] = {(unsigned long long)g.a_row_stride * 2ull, (unsigned long long)g.a_batch_stride * 2ull};
+    if (a->num_batches == 1) as[1] = as[0] * (unsigned long long)a->rows_per_batch;
+    unsigned ab[3] = {64, 128, 1};
+    if (int r = make_map(&maps.a[s], g.a, 3, ad, as, ab)) return r;
+    unsigned long long wd[2] = {(unsigned long long)g.K, (unsigned long long)a->N};
+    unsigned long long ws[1] = {(unsigned long long)g.w_row_stride * 2ull};
+    unsigned wb[2] = {64, (unsigned)BN};
+    if (int r = make_map(&maps.w[s], g.w, 2, wd, ws, wb)) return r;
+    p.kblocks[s] = (g.K + 63) / 64;
+    int rem = g.K - (p.kblocks[s] - 1) * 64;
+    p.kmmas_last[s] = (rem + 15) / 16;
+  }
+  p.rows_per_batch = a->rows_per_batch;
+  p.num_batches = a->num_batches;
+  p.N = a->N;
+  p.nseg = a->nseg;
+  p.epi = a->epi;
+  p.nan_to_num = a->nan_to_num;
+  p.D = static_cast<__nv_bfloat16*>(a->d);
+  p.d_batch_stride = a->d_batch_stride;
+  p.d_row_stride = a->d_row_stride;
+  p.bias = static_cast<const __nv_bfloat16*>(a->bias);
+  p.gate = static_cast<const __nv_bfloat16*>(a->gate);
+  p.gate_batch_stride = a->gate_batch_stride;
+  p.res = static_cast<const __nv_bfloat16*>(a->res);
+  p.res_batch_stride = a->res_batch_stride;
+  p.res_row_stride = a->res_row_stride;
+  p.aux = static_cast<__nv_bfloat16*>(a->aux);
+  p.aux_batch_stride = a->aux_batch_stride;
+  p.aux_row_stride = a->aux_row_stride;
+
+  auto kernel = stb::gemm_bf16_tn_kernel<MT, BN>;
+  static bool configured = false;
+  if (!configured) {
+    if (int r = set_smem(kernel, Cfg::SMEM_BYTES)) return r;
+    configured = true;
+  }
+  const int tiles_m = ((a->rows_per_batch + Cfg::BM - 1) / Cfg::BM) * a->num_batches;
+  const int tiles_n = (a->N + BN - 1) / BN;
+  const long long tiles = (long long)tiles_m * tiles_n;
+  const int grid = (int)std::min<long long>(tiles, num_sms());
+  kernel<<<grid, 256, Cfg::SMEM_BYTES, st>>>(maps, p);
+  STB_LAUNCH_CHECK("gemm_bf16_tn");
+  return 0;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+template <int HD>
+static int launch_attn_bwd(const stb_attn_bwd_args* a, const stb::AttnBwdMaps& maps, const stb::AttnBwdParams& p,
+                           cudaStream_t st) {
+  {
+    const long long warps = (long long)a->B * a->Sq * a->H;
+    stb::attn_bwd_delta_kernel<HD><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(a->o), a->o_b, a->o_s, a->o_h,
+        static_cast<const __nv_bfloat16*>(a->d_o), a->do_b, a->do_s, a->do_h, a->delta, a->B, a->H, a->Sq);
+    STB_LAUNCH_CHECK("attn_bwd_delta");
+  }
+  constexpr int SMEM = stb::AttnBwdCfg<HD>::SMEM_BYTES;
+  auto k1 = stb::attn_bwd_dkdv_kernel<HD>;
+  auto k2 = stb::attn_bwd_dq_kernel<HD>;
+  static bool configured = false;
+  if (!configured) {
+    if (int r = set_smem(k1, SMEM)) return r;
+    if (int r = set_smem(k2, SMEM)) return r;
+    configured = true;
+  }
+  k1<<<dim3((a->Sk + 127) / 128, a->H, a->B), 384, SMEM, st>>>(maps, p);
+  STB_LAUNCH_CHECK("attn_bwd_dkdv");
+  k2<<<dim3((a->Sq + 127) / 128, a->H, a->B), 384, SMEM, st>>>(maps, p);
+  STB_LAUNCH_CHECK("attn_bwd_dq");
+  return 0;
+}
+
+extern "C" {
+
+const char* stb_last_error(void) { return g_err.c_str(); }
+int stb_version(void) { return 100; }
+long long stb_launch_count(void) { return g_launches.load(); }
+void stb_reset_launch_count(void) { g_launches.store(0); }
+
+int stb_gemm_bf16(const stb_gemm_args* a, void* stream) {
+  if (int r = check_device()) return r;
+  if (!a || a->nseg < 1 || a->nseg > 3) return fail(STB_ERR_ARG, "nseg must be 1..3");
+  if (a->num_batches < 1 || a->rows_per_batch < 1 || a->N < 1) return fail(STB_ERR_ARG, "empty problem");
+  if (!aligned16(a->d) || (a->d_row_stride & 7) || (a->d_batch_stride & 7))
+    return fail(STB_ERR_ARG, "D must be 16-byte aligned with strides multiple of 8 elements");
+  if (a->bias && !aligned16(a->bias)) return fail(STB_ERR_ARG, "bias must be 16-byte aligned");
+  if (a->epi == STB_EPI_GATE_RES && (!a->gate || !a->res)) return fail(STB_ERR_ARG, "GATE_RES needs gate and res");
+  if (a->epi == STB_EPI_GATE_RES && (!aligned16(a->gate) || (a->gate_batch_stride & 7)))
+    return fail(STB_ERR_ARG, "gate must be 16-byte aligned");
+  if ((a->epi == STB_EPI_GATE_RES || a->epi == STB_EPI_ADD_RES) &&
+      (!a->res || !aligned16(a->res) || (a->res_row_stride & 7) || (a->res_batch_stride & 7)))
+    return fail(STB_ERR_ARG, "res must be given, 16-byte aligned, strides multiple of 8");
+  if (a->epi == STB_EPI_MUL_DGELU && !a->aux) return fail(STB_ERR_ARG, "MUL_DGELU needs aux");
+  if (a->aux && (!aligned16(a->aux) || (a->aux_row_stride & 7) || (a->aux_batch_stride & 7)))
+    return fail(STB_ERR_ARG, "aux must be 16-byte aligned, strides multiple of 8");
+  if (a->epi < 0 || a->epi > 4) return fail(STB_ERR_ARG, "unknown epilogue %d", a->epi);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int bn = a->tile_bn, mt = a->tile_mt;
+  if (bn == 0) bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  if (mt == 0) mt = 1;
+  if (mt == 1 && bn == 256) return launch_gemm<1, 256>(a, st);
+  if (mt == 2 && bn == 256) return launch_gemm<2, 256>(a, st);
+  if (mt == 1 && bn == 128) return launch_gemm<1, 128>(a, st);
+  if (mt == 2 && bn == 128) return launch_gemm<2, 128>(a, st);
+  if (mt == 1 && bn == 64) return launch_gemm<1, 64>(a, st);
+  return fail(STB_ERR_ARG, "unsupported tile config MT=%d BN=%d", mt, bn);
+}
+
+int stb_attn_fwd(const stb_attn_fwd_args* a, void* stream) {
+  if (int r = check_device()) return r;
+  if (!a || a->B < 1 || a->H < 1 || a->Sq < 1 || a->Sk < 1) return fail(STB_ERR_ARG, "empty attention problem");
+  if (a->HD != 128 && a->HD != 64) return fail(STB_ERR_UNSUPPORTED, "head_dim %d not supported (64 or 128)", a->HD);
+  if (!aligned16(a->o) || (a->o_s & 7) || (a->o_h & 7) || (a->o_b & 7)) return fail(STB_ERR_ARG, "O alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  stb::AttnFwdMaps maps;
+  auto mk = [&](CUtensorMap* m, const void* ptr, long long sb, long long ss, long long sh, int S) {
+    unsigned long long d[4] = {(unsigned long long)a->HD, (unsigned long long)a->H, (unsigned long long)S,
+                               (unsigned long long)a->B};
+    unsigned long long s[3] = {(unsigned long long)sh * 2ull, (unsigned long long)ss * 2ull, (unsigned long long)sb * 2ull};
+    unsigned bx[4] = {64, 1, 128, 1};
+    return make_map(m, ptr, 4, d, s, bx);
+  };
+  if (int r = mk(&maps.q, a->q, a->q_b, a->q_s, a->q_h, a->Sq)) return r;
+  if (int r = mk(&maps.k, a->k, a->k_b, a->k_s, a->k_h, a->Sk)) return r;
+  if (int r = mk(&maps.v, a->v, a->v_b, a->v_s, a->v_h, a->Sk)) return r;
+  stb::AttnFwdParams p;
+  p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk;
+  p.scale = a->scale;
+  p.O = static_cast<__nv_bfloat16*>(a->o);
+  p.o_b = a->o_b; p.o_s = a->o_s; p.o_h = a->o_h;
+  p.lse = a->lse;
+  dim3 grid((a->Sq + 255) / 256, a->H, a->B);
+  if (a->HD == 128) {
+    auto kernel = stb::attn_fwd_kernel<128>;
+    static bool configured = false;
+    if (!configured) {
+      if (int r = set_smem(kernel, stb::AttnFwdCfg<128>::SMEM_BYTES)) return r;
+      configured = true;
+    }
+    kernel<<<grid, 384, stb::AttnFwdCfg<128>::SMEM_BYTES, st>>>(maps, p);
+  } else {
+    auto kernel = stb::attn_fwd_kernel<64>;
+    static bool configured = false;
+    if (!configured) {
+      if (int r = set_smem(kernel, stb::AttnFwdCfg<64>::SMEM_BYTES)) return r;
+      configured = true;
+    }
+    kernel<<<grid, 384, stb::AttnFwdCfg<64>::SMEM_BYTES, st>>>(maps, p);
+  }
+  STB_LAUNCH_CHECK("attn_fwd");
+  return 0;
+}
+
+int stb_attn_bwd(const stb_attn_bwd_args* a, void* stream) {
+  if (int r = check_device()) return r;
+  if (!a || a->B < 1 || a->H < 1 || a->Sq < 1 || a->Sk < 1) return fail(STB_ERR_ARG, "empty attention problem");
+  if (a->HD != 128 && a->HD != 64) return fail(STB_ERR_UNSUPPORTED, "head_dim %d not supported (64 or 128)", a->HD);
+  if (!a->lse || !a->delta) return fail(STB_ERR_ARG, "attn_bwd needs lse and a delta scratch buffer");
+  auto al = [&](const void* ptr, long long sb, long long ss, long long sh) {
+    return aligned16(ptr) && !(sb & 7) && !(ss & 7) && !(sh & 7);
+  };
+  if (!al(a->dq, a->dq_b, a->dq_s, a->dq_h) || !al(a->dk, a->dk_b, a->dk_s, a->dk_h) ||
+      !al(a->dv, a->dv_b, a->dv_s, a->dv_h))
+    return fail(STB_ERR_ARG, "dq/dk/dv must be 16-byte aligned with strides multiple of 8 elements");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  stb::AttnBwdMaps maps;
+  auto mk = [&](CUtensorMap* m, const void* ptr, long long sb, long long ss, long long sh, int S) {
+    unsigned long long d[4] = {(unsigned long long)a->HD, (unsigned long long)a->H, (unsigned long long)S,
+                               (unsigned long long)a->B};
+    unsigned long long s[3] = {(unsigned long long)sh * 2ull, (unsigned long long)ss * 2ull, (unsigned long long)sb * 2ull};
+    unsigned bx[4] = {64, 1, 128, 1};
+    return make_map(m, ptr, 4, d, s, bx);
+  };
+  if (int r = mk(&maps.q, a->q, a->q_b, a->q_s, a->q_h, a->Sq)) return r;
+  if (int r = mk(&maps.k, a->k, a->k_b, a->k_s, a->k_h, a->Sk)) return r;
+  if (int r = mk(&maps.v, a->v, a->v_b, a->v_s, a->v_h, a->Sk)) return r;
+  if (int r = mk(&maps.d_o, a->d_o, a->do_b, a->do_s, a->do_h, a->Sq)) return r;
+  stb::AttnBwdParams p;
+  p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk;
+  p.scale = a->scale;
+  p.lse = a->lse;
+  p.delta = a->delta;
+  p.dq = static_cast<__nv_bfloat16*>(a->dq);
+  p.dk = static_cast<__nv_bfloat16*>(a->dk);
+  p.dv = static_cast<__nv_bfloat16*>(a->dv);
+  p.dq_b = a->dq_b; p.dq_s = a->dq_s; p.dq_h = a->dq_h;
+  p.dk_b = a->dk_b; p.dk_s = a->dk_s; p.dk_h = a->dk_h;
+  p.dv_b = a->dv_b; p.dv_s = a->dv_s; p.dv_h = a->dv_h;
+  if (a->HD == 128) return launch_attn_bwd<128>(a, maps, p, st);
+  return launch_attn_bwd<64>(a, maps, p, st);
+}
+
+int stb_ln_modulate_fwd(const void* x, long long x_b, long long x_s, const void* shift, const void* scale,
+                        long long mod_b, void* out, long long o_b, long long o_s, int B, int S, int D,
+                        float eps, void* stream) {
+  if (int r = check_device()) return r;
+  if ((D & 7) || D > 8192) return fail(STB_ERR_ARG, "D=%d must be a multiple of 8 and <= 8192", D);
+  if (!aligned16(x) || !aligned16(out) || !aligned16(shift) || !aligned16(scale) || (x_s & 7) || (x_b & 7) ||
+      (o_s & 7) || (o_b & 7) || (mod_b & 7))
+    return fail(STB_ERR_ARG, "ln_modulate_fwd alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows = B * S;
+  const int vpt = (D + 1023) / 1024;
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto SH = static_cast<const __nv_bfloat16*>(shift);
+  auto SC = static_cast<const __nv_bfloat16*>(scale);
+  auto O = static_cast<__nv_bfloat16*>(out);
+#define STB_LN_F(V) stb::ln_modulate_fwd_kernel<V><<<rows, 128, 0, st>>>(X, x_b, x_s, SH, SC, mod_b, O, o_b, o_s, S, D, eps)
+  switch (vpt) {
+    case 1: STB_LN_F(1); break;
+    case 2: STB_LN_F(2); break;
+    case 3: STB_LN_F(3); break;
+    case 4: STB_LN_F(4); break;
+    default: STB_LN_F(8); break;
+  }
+#undef STB_LN_F
+  STB_LAUNCH_CHECK("ln_modulate_fwd");
+  return 0;
+}
+
+int stb_ln_modulate_bwd(const void* dy, long long dy_b, long long dy_s, const void* x, long long x_b,
+                        long long x_s, const void* scale, long long mod_b, const void* add, long long add_b,
+                        long long add_s, void* dx, long long dx_b, long long dx_s, int B, int S, int D,
+                        float eps, void* stream) {
+  if (int r = check_device()) return r;
+  if ((D & 7) || D > 4096) return fail(STB_ERR_ARG, "D=%d must be a multiple of 8 and <= 4096", D);
+  if (!aligned16(x) || !aligned16(dy) || !aligned16(dx) || !aligned16(scale) || (add && !aligned16(add)))
+    return fail(STB_ERR_ARG, "ln_modulate_bwd alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows = B * S;
+  const int vpt = (D + 1023) / 1024;
+  auto DY = static_cast<const __nv_bfloat16*>(dy);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto SC = static_cast<const __nv_bfloat16*>(scale);
+  auto AD = static_cast<const __nv_bfloat16*>(add);
+  auto DX = static_cast<__nv_bfloat16*>(dx);
+#define STB_LN_B(V) \
+  stb::ln_modulate_bwd_kernel<V><<<rows, 128, 0, st>>>(DY, dy_b, dy_s, X, x_b, x_s, SC, mod_b, AD, add_b, add_s, DX, dx_b, dx_s, S, D, eps)
+  switch (vpt) {
+    case 1: STB_LN_B(1); break;
+    case 2: STB_LN_B(2); break;
+    case 3: STB_LN_B(3); break;
+    default: STB_LN_B(4); break;
+  }
+#undef STB_LN_B
+  STB_LAUNCH_CHECK("ln_modulate_bwd");
+  return 0;
+}
+
+int stb_qk_rmsnorm_rope_fwd(const void* src, long long src_b, long long src_s, int k_off, const void* wq,
+                            const void* wk, const void* wq_added, const void* wk_added, int s_split,
+                            const float* cos_t, const float* sin_t, void* q_out, void* k_out,
+                            long long dst_b, long long dst_s, int B, int S, int H, int HD, float eps,
+                            void* stream) {
+  if (int r = check_device()) return r;
+  if (HD != 128 && HD != 64) return fail(STB_ERR_UNSUPPORTED, "head_dim %d not supported", HD);
+  if ((src_s & 3) || (src_b & 3) || (k_off & 3) || (dst_s & 3) || (dst_b & 3)) return fail(STB_ERR_ARG, "qk_rmsnorm_rope alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long warps = (long long)B * S * H * 2;
+  const unsigned grid = (unsigned)((warps + 7) / 8);
+  auto SRC = static_cast<const __nv_bfloat16*>(src);
+  auto cast = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
+  if (HD == 128)
+    stb::qk_rmsnorm_rope_fwd_kernel<128><<<grid, 256, 0, st>>>(SRC, src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(k_out), dst_b, dst_s, B, S, H, eps);
+  else
+    stb::qk_rmsnorm_rope_fwd_kernel<64><<<grid, 256, 0, st>>>(SRC, src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(k_out), dst_b, dst_s, B, S, H, eps);
+  STB_LAUNCH_CHECK("qk_rmsnorm_rope_fwd");
+  return 0;
+}
+
+int stb_qk_rmsnorm_rope_bwd(const void* dq, const void* dk, long long d_b, long long d_s, const void* src,
+                            long long src_b, long long src_s, int k_off, const void* wq, const void* wk,
+                            const void* wq_added, const void* wk_added, int s_split, const float* cos_t,
+                            const float* sin_t, void* dsrc, long long ds_b, long long ds_s, int B, int S,
+                            int H, int HD, float eps, void* stream) {
+  if (int r = check_device()) return r;
+  if (HD != 128 && HD != 64) return fail(STB_ERR_UNSUPPORTED, "head_dim %d not supported", HD);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long warps = (long long)B * S * H * 2;
+  const unsigned grid = (unsigned)((warps + 7) / 8);
+  auto cast = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
+  if (HD == 128)
+    stb::qk_rmsnorm_rope_bwd_kernel<128><<<grid, 256, 0, st>>>(cast(dq), cast(dk), d_b, d_s, cast(src), src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(dsrc), ds_b, ds_s, B, S, H, eps);
+  else
+    stb::qk_rmsnorm_rope_bwd_kernel<64><<<grid, 256, 0, st>>>(cast(dq), cast(dk), d_b, d_s, cast(src), src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(dsrc), ds_b, ds_s, B, S, H, eps);
+  STB_LAUNCH_CHECK("qk_rmsnorm_rope_bwd");
+  return 0;
+}
+
+int stb_flow_prep_pack(const void* latents, const void* noise, const float* sigmas, void* noisy,
+                       void* packed, int B, int C, int Hh, int Ww, void* stream) {
+  if (int r = check_device()) return r;
+  if ((Hh & 1) || (Ww & 1)) return fail(STB_ERR_ARG, "latent H and W must be even for 2x2 patchify");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n = (long long)B * C * Hh * Ww;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 16);
+  stb::flow_prep_pack_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(latents), static_cast<const __nv_bfloat16*>(noise), sigmas, static_cast<__nv_bfloat16*>(noisy), static_cast<__nv_bfloat16*>(packed), B, C, Hh, Ww);
+  STB_LAUNCH_CHECK("flow_prep_pack");
+  return 0;
+}
+
+int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* noise, float* loss_out,
+                      void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, void* stream) {
+  if (int r = check_device()) return r;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  STB_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  const long long n = (long long)B * C * Hh * Ww;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
+  stb::flow_mse_loss_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pred_packed), static_cast<const __nv_bfloat16*>(latents), static_cast<const __nv_bfloat16*>(noise), loss_out, static_cast<__nv_bfloat16*>(dpred_packed), grad_scale, B, C, Hh, Ww);
+  STB_LAUNCH_CHECK("flow_mse_loss");
+  return 0;
+}
+
+int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, long long r_b, long long r_s,
+                  float* out, int B, int S, int R, int N, float alpha, void* stream) {
+  if (int r = check_device()) return r;
+  if (N & 1) return fail(STB_ERR_ARG, "N must be even");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long M = (long long)B * S;
+  const int col_blocks = (N / 2 + 255) / 256;
+  // enough row chunks to fill the machine ~4x
+  int chunks = std::max(1, (num_sms() * 4) / col_blocks);
+  long long mchunk = ((M + chunks - 1) / chunks + 63) / 64 * 64;
+  chunks = (int)((M + mchunk - 1) / mchunk);
+  dim3 grid(col_blocks, chunks);
+  auto LL = static_cast<const __nv_bfloat16*>(L);
+  auto RR = static_cast<const __nv_bfloat16*>(Rm);
+  switch (R) {
+    case 16: stb::skinny_tn_kernel<16><<<grid, 256, 0, st>>>(LL, l_b, l_s, RR, r_b, r_s, out, B, S, N, alpha, (int)mchunk); break;
+    case 32: stb::skinny_tn_kernel<32><<<grid, 256, 0, st>>>(LL, l_b, l_s, RR, r_b, r_s, out, B, S, N, alpha, (int)mchunk); break;
+    case 48: stb::skinny_tn_kernel<48><<<grid, 256, 0, st>>>(LL, l_b, l_s, RR, r_b, r_s, out, B, S, N, alpha, (int)mchunk); break;
+    case 64: stb::skinny_tn_kernel<64><<<grid, 256, 0, st>>>(LL, l_b, l_s, RR, r_b, r_s, out, B, S, N, alpha, (int)mchunk); break;
+    default: return fail(STB_ERR_UNSUPPORTED, "LoRA rank block R=%d not supported (16/32/48/64)", R);
+  }
+  STB_LAUNCH_CHECK("skinny_tn");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,489 @@
+// simpletuner_b200 — HBM-bound fused elementwise / row-reduction kernels of the diffusion step.
+// Each one collapses a chain of eager PyTorch ops of the reference into a single pass with 16-byte
+// coalesced accesses; the bf16 rounding points of the reference chain are reproduced so results
+// track the reference path bit-for-bit wherever that is cheap.
+#pragma once
+#include "common.cuh"
+
+namespace stb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// block-wide sum for 128-thread CTAs
+__device__ __forceinline__ float block_sum_128(float v, float* red /*[4]*/) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+
+// ------------------------------------------------------------------------------------------------
+// adaLN modulation:  out = LayerNorm(x; eps, no affine) * (1 + scale[b]) + shift[b]
+// reference: diffusers AdaLayerNormZero / ZeroSingle / Continuous as called at
+// flux/transformer.py:386-412 and the norm2 + modulation at :577-580.
+// One 128-thread CTA per row; the row lives in registers (VPT x 8 bf16 per thread).
+// ------------------------------------------------------------------------------------------------
+template <int VPT>
+__global__ void __launch_bounds__(128)
+ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_b, long long x_s,
+                       const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
+                       long long mod_b, __nv_bfloat16* __restrict__ out, long long o_b, long long o_s,
+                       int S, int D, float eps) {
+  __shared__ float red[4];
+  const int row = blockIdx.x;
+  const int b = row / S, s = row - b * S;
+  const __nv_bfloat16* xr = x + b * x_b + s * x_s;
+  float v[VPT][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * 128 + threadIdx.x) * 8;
+    if (c < D) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + c), v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+  }
+  const float mean = block_sum_128(sum, red) / D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * 128 + threadIdx.x) * 8;
+    if (c < D) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d = v[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum_128(sq, red) / D + eps);
+  const __nv_bfloat16* sh = shift + b * mod_b;
+  const __nv_bfloat16* sc = scale + b * mod_b;
+  __nv_bfloat16* orow = out + b * o_b + s * o_s;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * 128 + threadIdx.x) * 8;
+    if (c < D) {
+      float fs[8], fc[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(sh + c)), fs);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(sc + c)), fc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float ln = bf16r((v[i][j] - mean) * rstd);   // LayerNorm output tensor (bf16)
+        float t1 = bf16r(1.f + fc[j]);               // (1 + scale)
+        o[j] = bf16r(ln * t1) + fs[j];               // * then + , each a bf16 tensor op
+      }
+      *reinterpret_cast<uint4*>(orow + c) = pack8(o);
+    }
+  }
+}
+
+// Backward of the above w.r.t. x only (modulation parameters are frozen in LoRA training):
+//   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * (1 + scale);   out = dx (+ add)
+template <int VPT>
+__global__ void __launch_bounds__(128)
+ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_b, long long dy_s,
+                       const __nv_bfloat16* __restrict__ x, long long x_b, long long x_s,
+                       const __nv_bfloat16* __restrict__ scale, long long mod_b,
+                       const __nv_bfloat16* __restrict__ add, long long add_b, long long add_s,
+                       __nv_bfloat16* __restrict__ dx, long long dx_b, long long dx_s, int S, int D,
+                       float eps) {
+  __shared__ float red[4];
+  const int row = blockIdx.x;
+  const int b = row / S, s = row - b * S;
+  const __nv_bfloat16* xr = x + b * x_b + s * x_s;
+  const __nv_bfloat16* gr = dy + b * dy_b + s * dy_s;
+  const __nv_bfloat16* sc = scale + b * mod_b;
+  float v[VPT][8], g[VPT][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * 128 + threadIdx.x) * 8;
+    if (c < D) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + c), v[i]);
+      float fc[8];
+      unpack8(*reinterpret_cast<const uint4*>(gr + c), g[i]);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(sc + c)), fc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sum += v[i][j];
+        g[i][j] *= bf16r(1.f + fc[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f, g[i][j] = 0.f;
+    }
+  }
+  const float mean = block_sum_128(sum, red) / D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * 128 + threadIdx.x) * 8;
+    if (c < D) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d = v[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum_128(sq, red) / D + eps);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * 128 + threadIdx.x) * 8;
+    if (c < D) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float xh = (v[i][j] - mean) * rstd;
+        v[i][j] = xh;
+        sg += g[i][j];
+        sgx += g[i][j] * xh;
+      }
+    }
+  }
+  const float mg = block_sum_128(sg, red) / D;
+  const float mgx = block_sum_128(sgx, red) / D;
+  __nv_bfloat16* orow = dx + b * dx_b + s * dx_s;
+  const __nv_bfloat16* arow = add ? add + b * add_b + s * add_s : nullptr;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * 128 + threadIdx.x) * 8;
+    if (c < D) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - mg - v[i][j] * mgx);
+      if (arow) {
+        float a[8];
+        unpack8(*reinterpret_cast<const uint4*>(arow + c), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += a[j];
+      }
+      *reinterpret_cast<uint4*>(orow + c) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// QK RMSNorm + RoPE.  reference: diffusers RMSNorm (fp32 variance, cast, * weight) at
+// flux/transformer.py:138-141,159-162 and _apply_rotary_emb_anyshape at :73-98.
+// src: projection output, token-major [B, S, *] with q at column offset 0 and k at `k_off`
+//      (fused QKV buffer) — per (token, head) a contiguous HD vector at head stride HD.
+// dst: q_out / k_out [B, S, H, HD] (same strides for both).
+// One warp per (token, head); lane owns HD/32 consecutive elements (RoPE pairs stay in-lane).
+// Rows s < s_split use the "added" (text stream) norm weights wq1/wk1, the rest wq0/wk0.
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(256)
+qk_rmsnorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ src, long long src_b, long long src_s,
+                           int k_off, const __nv_bfloat16* __restrict__ wq0,
+                           const __nv_bfloat16* __restrict__ wk0, const __nv_bfloat16* __restrict__ wq1,
+                           const __nv_bfloat16* __restrict__ wk1, int s_split,
+                           const float* __restrict__ cosT, const float* __restrict__ sinT,
+                           __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ k_out,
+                           long long dst_b, long long dst_s, int B, int S, int H, float eps) {
+  constexpr int EPL = HD / 32;
+  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long total = (long long)B * S * H * 2;
+  if (wid >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int which = int(wid & 1);  // 0 = q, 1 = k
+  long long rem = wid >> 1;
+  const int h = int(rem % H);
+  rem /= H;
+  const int s = int(rem % S);
+  const int b = int(rem / S);
+  const __nv_bfloat16* in = src + b * src_b + s * src_s + (which ? k_off : 0) + h * HD + lane * EPL;
+  const __nv_bfloat16* w = (s < s_split) ? (which ? wk1 : wq1) : (which ? wk0 : wq0);
+  float x[EPL];
+  if constexpr (EPL == 4) {
+    uint2 u = *reinterpret_cast<const uint2*>(in);
+    x[0] = bf16_lo(u.x); x[1] = bf16_hi(u.x); x[2] = bf16_lo(u.y); x[3] = bf16_hi(u.y);
+  } else {
+    uint32_t u = *reinterpret_cast<const uint32_t*>(in);
+    x[0] = bf16_lo(u); x[1] = bf16_hi(u);
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) ss += x[i] * x[i];
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / HD + eps);
+  float y[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    float n = bf16r(x[i] * rstd);
+    y[i] = w ? bf16r(n * __bfloat162float(w[lane * EPL + i])) : n;
+  }
+  float o[EPL];
+  if (cosT) {
+    const float* cr = cosT + (long long)s * HD + lane * EPL;
+    const float* sr = sinT + (long long)s * HD + lane * EPL;
+#pragma unroll
+    for (int i = 0; i < EPL; i += 2) {
+      o[i] = y[i] * cr[i] + (-y[i + 1]) * sr[i];
+      o[i + 1] = y[i + 1] * cr[i + 1] + y[i] * sr[i + 1];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) o[i] = y[i];
+  }
+  __nv_bfloat16* out = (which ? k_out : q_out) + b * dst_b + s * dst_s + h * HD + lane * EPL;
+  if constexpr (EPL == 4) {
+    uint2 u;
+    u.x = pack_bf16x2(o[0], o[1]);
+    u.y = pack_bf16x2(o[2], o[3]);
+    *reinterpret_cast<uint2*>(out) = u;
+  } else {
+    *reinterpret_cast<uint32_t*>(out) = pack_bf16x2(o[0], o[1]);
+  }
+}
+
+// Backward: given dq/dk in post-RoPE space, produce gradient w.r.t. the projection outputs
+// (written into the q / k column ranges of the fused d_qkv buffer).  RMSNorm weights are frozen.
+//   dy = R^T d_out ;  g = dy * w ;  dx = rstd * (g - xhat * mean(g * xhat))
+template <int HD>
+__global__ void __launch_bounds__(256)
+qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bfloat16* __restrict__ dk,
+                           long long d_b, long long d_s, const __nv_bfloat16* __restrict__ src,
+                           long long src_b, long long src_s, int k_off,
+                           const __nv_bfloat16* __restrict__ wq0, const __nv_bfloat16* __restrict__ wk0,
+                           const __nv_bfloat16* __restrict__ wq1, const __nv_bfloat16* __restrict__ wk1,
+                           int s_split, const float* __restrict__ cosT, const float* __restrict__ sinT,
+                           __nv_bfloat16* __restrict__ dsrc, long long ds_b, long long ds_s, int B, int S,
+                           int H, float eps) {
+  constexpr int EPL = HD / 32;
+  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long total = (long long)B * S * H * 2;
+  if (wid >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int which = int(wid & 1);
+  long long rem = wid >> 1;
+  const int h = int(rem % H);
+  rem /= H;
+  const int s = int(rem % S);
+  const int b = int(rem / S);
+  const long long col = (which ? k_off : 0) + h * HD + lane * EPL;
+  const __nv_bfloat16* in = src + b * src_b + s * src_s + col;
+  const __nv_bfloat16* gin = (which ? dk : dq) + b * d_b + s * d_s + h * HD + lane * EPL;
+  const __nv_bfloat16* w = (s < s_split) ? (which ? wk1 : wq1) : (which ? wk0 : wq0);
+  float x[EPL], go[EPL];
+  if constexpr (EPL == 4) {
+    uint2 u = *reinterpret_cast<const uint2*>(in);
+    x[0] = bf16_lo(u.x); x[1] = bf16_hi(u.x); x[2] = bf16_lo(u.y); x[3] = bf16_hi(u.y);
+    uint2 g = *reinterpret_cast<const uint2*>(gin);
+    go[0] = bf16_lo(g.x); go[1] = bf16_hi(g.x); go[2] = bf16_lo(g.y); go[3] = bf16_hi(g.y);
+  } else {
+    uint32_t u = *reinterpret_cast<const uint32_t*>(in);
+    x[0] = bf16_lo(u); x[1] = bf16_hi(u);
+    uint32_t g = *reinterpret_cast<const uint32_t*>(gin);
+    go[0] = bf16_lo(g); go[1] = bf16_hi(g);
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) ss += x[i] * x[i];
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / HD + eps);
+  float dy[EPL];
+  if (cosT) {
+    const float* cr = cosT + (long long)s * HD + lane * EPL;
+    const float* sr = sinT + (long long)s * HD + lane * EPL;
+#pragma unroll
+    for (int i = 0; i < EPL; i += 2) {
+      // o[i] = y[i] c[i] - y[i+1] s[i];  o[i+1] = y[i+1] c[i+1] + y[i] s[i+1]
+      dy[i] = go[i] * cr[i] + go[i + 1] * sr[i + 1];
+      dy[i + 1] = go[i + 1] * cr[i + 1] - go[i] * sr[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) dy[i] = go[i];
+  }
+  float g[EPL], xh[EPL];
+  float sgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    g[i] = w ? dy[i] * __bfloat162float(w[lane * EPL + i]) : dy[i];
+    xh[i] = x[i] * rstd;
+    sgx += g[i] * xh[i];
+  }
+  sgx = warp_sum(sgx) / HD;
+  float o[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) o[i] = rstd * (g[i] - xh[i] * sgx);
+  __nv_bfloat16* out = dsrc + b * ds_b + s * ds_s + col;
+  if constexpr (EPL == 4) {
+    uint2 u;
+    u.x = pack_bf16x2(o[0], o[1]);
+    u.y = pack_bf16x2(o[2], o[3]);
+    *reinterpret_cast<uint2*>(out) = u;
+  } else {
+    *reinterpret_cast<uint32_t*>(out) = pack_bf16x2(o[0], o[1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flow-matching batch prep + Flux 2x2 patchify in one pass.
+// reference: common.py:4975-4992 (_prepare_flow_noisy_latents: (1-sigma) x + sigma eps),
+//            flux/__init__.py:25-30 (pack_latents).  latents/noise: [B, C, Hh, Ww] contiguous.
+// noisy (bf16, reference tensor dtype) is written both unpacked [B,C,Hh,Ww] and packed
+// [B, (Hh/2)(Ww/2), 4C];  packed index = ((c*2 + dy)*2 + dx).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+flow_prep_pack_kernel(const __nv_bfloat16* __restrict__ lat, const __nv_bfloat16* __restrict__ noise,
+                      const float* __restrict__ sigmas, __nv_bfloat16* __restrict__ noisy,
+                      __nv_bfloat16* __restrict__ packed, int B, int C, int Hh, int Ww) {
+  const long long n = (long long)B * C * Hh * Ww;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int w = int(r % Ww); r /= Ww;
+    const int hh = int(r % Hh); r /= Hh;
+    const int c = int(r % C);
+    const int b = int(r / C);
+    // reference arithmetic (common.py:4953-4960, 4989-4991): the sigma grid is cast to the latent
+    // dtype (bf16) first, then every op of (1 - g) * x + g * eps is a bf16 tensor op — reproduce
+    // each rounding so the result is bit-identical to the eager chain.
+    const float sg = bf16r(sigmas[b]);
+    const float x = __bfloat162float(lat[i]);
+    const float e = __bfloat162float(noise[i]);
+    const float v = bf16r(bf16r(1.f - sg) * x) + bf16r(sg * e);
+    const __nv_bfloat16 vb = __float2bfloat16(v);
+    if (noisy) noisy[i] = vb;
+    const int ph = hh >> 1, dy = hh & 1, pw = w >> 1, dx = w & 1;
+    const long long tok = (long long)ph * (Ww >> 1) + pw;
+    const long long pi = ((long long)b * ((Hh >> 1) * (Ww >> 1)) + tok) * (4 * C) + ((c * 2 + dy) * 2 + dx);
+    packed[pi] = vb;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loss: mean over batch of mean over (C,H,W) of (pred.float() - target.float())^2 with
+// target = noise - latents (flow matching, common.py:4610-4611, 6286, 6426-6429), where pred arrives
+// in the packed token layout (unpack_latents, flux/__init__.py:33-44, folded into the index math).
+// Also emits d loss / d pred in the packed layout (bf16) scaled by `grad_scale`.
+// partial sums -> atomicAdd into loss_out[0] (fp32), caller zeroes it.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+flow_mse_loss_kernel(const __nv_bfloat16* __restrict__ pred_packed, const __nv_bfloat16* __restrict__ lat,
+                     const __nv_bfloat16* __restrict__ noise, float* __restrict__ loss_out,
+                     __nv_bfloat16* __restrict__ dpred_packed, float grad_scale, int B, int C, int Hh,
+                     int Ww) {
+  __shared__ float red[8];
+  const long long n = (long long)B * C * Hh * Ww;
+  const float inv = 1.f / float((long long)C * Hh * Ww) / float(B);
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int w = int(r % Ww); r /= Ww;
+    const int hh = int(r % Hh); r /= Hh;
+    const int c = int(r % C);
+    const int b = int(r / C);
+    const int ph = hh >> 1, dy = hh & 1, pw = w >> 1, dx = w & 1;
+    const long long tok = (long long)ph * (Ww >> 1) + pw;
+    const long long pi = ((long long)b * ((Hh >> 1) * (Ww >> 1)) + tok) * (4 * C) + ((c * 2 + dy) * 2 + dx);
+    // target = noise - latents computed in the latent dtype (bf16 tensor), then .float()
+    const float tgt = bf16r(__bfloat162float(noise[i]) - __bfloat162float(lat[i]));
+    const float d = __bfloat162float(pred_packed[pi]) - tgt;
+    acc += d * d;
+    if (dpred_packed) dpred_packed[pi] = __float2bfloat16(2.f * d * inv * grad_scale);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(loss_out, v * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LoRA weight gradients (rank r <= 64), reference: autograd through peft lora.Linear
+//   y = x W^T + s * (x A^T) B^T   =>   dA = s * (dY B)^T x ,  dB = s * dY^T (x A^T)
+// Generic "skinny" product:  Out[r, n] (+)= alpha * sum_m  L[m, r] * Rm[m, n]
+// with L = [M, R] (R <= 64, contiguous rows), Rm = [M, N].  Split over M across CTAs, fp32 atomics.
+// Each CTA: 256 threads cover 256*VEC columns of N for a chunk of MCHUNK rows.
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256)
+skinny_tn_kernel(const __nv_bfloat16* __restrict__ L, long long l_b, long long l_s,
+                 const __nv_bfloat16* __restrict__ Rm, long long r_b, long long r_s,
+                 float* __restrict__ out /*[R, N] fp32*/, int B, int S, int N, float alpha, int mchunk) {
+  __shared__ __nv_bfloat16 sL[64][R];  // 64 rows of L at a time
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 2;
+  const long long m0 = (long long)blockIdx.y * mchunk;
+  const long long Mtot = (long long)B * S;
+  const long long m1 = min(Mtot, m0 + mchunk);
+  float acc0[R], acc1[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc0[r] = 0.f, acc1[r] = 0.f;
+  for (long long mb = m0; mb < m1; mb += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * R; i += 256) {
+      const int rr = i / R, cc = i - rr * R;
+      const long long m = mb + rr;
+      __nv_bfloat16 v = __float2bfloat16(0.f);
+      if (m < m1) {
+        const long long bb = m / S, ss = m - bb * S;
+        v = L[bb * l_b + ss * l_s + cc];
+      }
+      sL[rr][cc] = v;
+    }
+    __syncthreads();
+    if (n < N) {
+      const long long left = m1 - mb;
+      const int rows = left < 64 ? int(left) : 64;
+      for (int rr = 0; rr < rows; ++rr) {
+        const long long m = mb + rr;
+        const long long bb = m / S, ss = m - bb * S;
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(Rm + bb * r_b + ss * r_s + n);
+        const float x0 = bf16_lo(u), x1 = bf16_hi(u);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float lv = __bfloat162float(sL[rr][r]);
+          acc0[r] += lv * x0;
+          acc1[r] += lv * x1;
+        }
+      }
+    }
+  }
+  if (n < N) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      atomicAdd(out + (long long)r * N + n, alpha * acc0[r]);
+      if (n + 1 < N) atomicAdd(out + (long long)r * N + n + 1, alpha * acc1[r]);
+    }
+  }
+}
+
+// fp32 -> bf16 cast with optional transpose-free accumulate into an existing bf16 grad
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16(in[i]);
+}
+
+}  // namespace stb

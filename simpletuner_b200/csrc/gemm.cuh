@@ -1,0 +1,394 @@
+// simpletuner_b200 — persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[b, s, n] = epilogue( sum_seg  A_seg[b, s, :] . W_seg[n, :]  + bias[n] )
+//
+// Every operand is K-major bf16 ("TN": activations [rows, K], nn.Linear weights [N, K]), fp32
+// accumulation in TMEM.  Up to three K-segments are chained in one mainloop so that
+//   * torch.cat([attn, mlp], -1) @ W^T          (reference flux/transformer.py:460-464)
+//   * x @ W^T + (x A^T) B^T   (PEFT LoRA linear, reference common.py:1094-1117)
+// become extra k-blocks of the same tile instead of extra kernels / extra HBM round trips.
+//
+// Roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer (one thread), warp2 = TMEM
+// allocator, warps 4..7 = epilogue (TMEM -> registers -> fused epilogue -> global).
+// A CTA owns MT x 128 rows and BN columns of D per tile; TMEM holds 512/(MT*BN) accumulator
+// stages so the epilogue of tile i overlaps the mainloop of tile i+1 when there are >= 2.
+#pragma once
+#include "common.cuh"
+
+namespace stb {
+
+enum GemmEpi : int {
+  EPI_STORE = 0,        // D = acc + bias
+  EPI_GELU = 1,         // D = gelu_tanh(acc + bias); aux (optional) = acc + bias (pre-activation)
+  EPI_GATE_RES = 2,     // D = res + gate[b, n] * (acc + bias); optional nan_to_num
+  EPI_MUL_DGELU = 3,    // D = acc * gelu_tanh'(aux)          (dgrad through the activation)
+  EPI_ADD_RES = 4,      // D = acc + bias + res                (gradient accumulation)
+};
+
+struct GemmParams {
+  int rows_per_batch;  // S : rows in one batch slab of A / D
+  int num_batches;     // B
+  int N;
+  int nseg;
+  int kblocks[3];  // ceil(K_seg / 64)
+  int kmmas_last[3];  // UMMA_K=16 steps needed in the last k-block of the segment (1..4)
+  int epi;
+  int nan_to_num;
+  __nv_bfloat16* D;
+  long long d_batch_stride, d_row_stride;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* gate;
+  long long gate_batch_stride;
+  const __nv_bfloat16* res;
+  long long res_batch_stride, res_row_stride;
+  __nv_bfloat16* aux;  // EPI_GELU: written; EPI_MUL_DGELU: read
+  long long aux_batch_stride, aux_row_stride;
+};
+
+struct GemmMaps {
+  CUtensorMap a[3];  // 3-D (k, s, b), box (64, 128, 1), SWIZZLE_128B
+  CUtensorMap w[3];  // 2-D (k, n),   box (64, BN),      SWIZZLE_128B
+};
+
+template <int MT, int BN>
+struct GemmCfg {
+  static constexpr int BM = 128 * MT;
+  static constexpr int BK = 64;
+  static constexpr int A_BYTES = 128 * BK * 2;          // one 128-row A tile
+  static constexpr int W_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = MT * A_BYTES + W_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int ACC_COLS = MT * BN;
+  static constexpr int ACC_STAGES = (512 / ACC_COLS) >= 2 ? 2 : 1;
+  static constexpr int TMEM_COLS = (ACC_COLS * ACC_STAGES) <= 32    ? 32
+                                   : (ACC_COLS * ACC_STAGES) <= 64  ? 64
+                                   : (ACC_COLS * ACC_STAGES) <= 128 ? 128
+                                   : (ACC_COLS * ACC_STAGES) <= 256 ? 256
+                                                                    : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void gemm_tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+  // grouped rasterisation: bands of 8 m-tiles sweep all n-tiles -> square-ish L2 footprint
+  constexpr int GM = 8;
+  int per_group = GM * tiles_n;
+  int g = tile / per_group;
+  int first_m = g * GM;
+  int gsize = min(GM, tiles_m - first_m);
+  int within = tile - g * per_group;
+  tm = first_m + within % gsize;
+  tn = within / gsize;
+}
+
+template <int MT, int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
+  using Cfg = GemmCfg<MT, BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int ACC_STAGES = Cfg::ACC_STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto accf_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto acce_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_per_batch = (p.rows_per_batch + Cfg::BM - 1) / Cfg::BM;
+  const int tiles_m = tiles_per_batch * p.num_batches;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  int kb_total = 0;
+  for (int s = 0; s < p.nseg; ++s) kb_total += p.kblocks[s];
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) {
+      tma_prefetch_desc(&maps.a[s]);
+      tma_prefetch_desc(&maps.w[s]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(accf_bar(s), 1);
+      mbar_init(acce_bar(s), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int tm, tn;
+        gemm_tile_coords(tile, tiles_m, tiles_n, tm, tn);
+        const int b = tm / tiles_per_batch;
+        const int s0 = (tm - b * tiles_per_batch) * Cfg::BM;
+        const int n0 = tn * BN;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          for (int kb = 0; kb < p.kblocks[seg]; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              tma_load_3d(sa + mt * Cfg::A_BYTES, &maps.a[seg], full_bar(stage), kb * 64, s0 + mt * 128, b);
+            tma_load_2d(sa + MT * Cfg::A_BYTES, &maps.w[seg], full_bar(stage), kb * 64, n0);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(acce_bar(acc), acc_phase ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
+        uint32_t accumulate = 0;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          for (int kb = 0; kb < p.kblocks[seg]; ++kb) {
+            mbar_wait(full_bar(stage), phase, 3);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            const uint32_t sw = sa + MT * Cfg::A_BYTES;
+            const int nk = (kb == p.kblocks[seg] - 1) ? p.kmmas_last[seg] : 4;
+            for (int kk = 0; kk < nk; ++kk) {
+              const uint64_t bdesc = sdesc_kmajor(sw, kk * 16);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint64_t adesc = sdesc_kmajor(sa + mt * Cfg::A_BYTES, kk * 16);
+                mma_ss(d_base + mt * BN, adesc, bdesc, idesc, accumulate);
+              }
+              accumulate = 1;
+            }
+            tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        tc_commit(accf_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int tm, tn;
+      gemm_tile_coords(tile, tiles_m, tiles_n, tm, tn);
+      const int b = tm / tiles_per_batch;
+      const int s0 = (tm - b * tiles_per_batch) * Cfg::BM;
+      const int n0 = tn * BN;
+      mbar_wait(accf_bar(acc), acc_phase, 4);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int s = s0 + mt * 128 + ew * 32 + lane;
+        const bool row_ok = s < p.rows_per_batch;
+        __nv_bfloat16* drow = p.D + (long long)b * p.d_batch_stride + (long long)s * p.d_row_stride;
+        const __nv_bfloat16* rrow =
+            p.res ? p.res + (long long)b * p.res_batch_stride + (long long)s * p.res_row_stride : nullptr;
+        __nv_bfloat16* xrow =
+            p.aux ? p.aux + (long long)b * p.aux_batch_stride + (long long)s * p.aux_row_stride : nullptr;
+        const __nv_bfloat16* grow = p.gate ? p.gate + (long long)b * p.gate_batch_stride : nullptr;
+        const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + acc * Cfg::ACC_COLS + mt * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          if (n0 + c >= p.N) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + c, v);
+          tc_wait_ld();
+          const int n = n0 + c;
+          const bool full = (n + 32 <= p.N);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+            if (full) {
+              const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 u = __ldg(bp + q);
+                f[q * 8 + 0] += bf16_lo(u.x); f[q * 8 + 1] += bf16_hi(u.x);
+                f[q * 8 + 2] += bf16_lo(u.y); f[q * 8 + 3] += bf16_hi(u.y);
+                f[q * 8 + 4] += bf16_lo(u.z); f[q * 8 + 5] += bf16_hi(u.z);
+                f[q * 8 + 6] += bf16_lo(u.w); f[q * 8 + 7] += bf16_hi(u.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n + j < p.N) f[j] += __bfloat162float(p.bias[n + j]);
+            }
+          }
+          if (row_ok) {
+            if (p.epi == EPI_GELU) {
+              if (xrow) {
+                if (full) {
+                  uint4* xp = reinterpret_cast<uint4*>(xrow + n);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    uint4 u;
+                    u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                    u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                    u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                    u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                    xp[q] = u;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (n + j < p.N) xrow[n + j] = __float2bfloat16(f[j]);
+                }
+              }
+              // the activation sees the bf16-rounded pre-activation, as the reference's
+              // nn.Linear -> nn.GELU chain does (bf16 tensor between the two modules)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(__bfloat162float(__float2bfloat16(f[j])));
+            } else if (p.epi == EPI_GATE_RES) {
+              float g[32], r[32];
+              if (full) {
+                const uint4* gp = reinterpret_cast<const uint4*>(grow + n);
+                const uint4* rp = reinterpret_cast<const uint4*>(rrow + n);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4 u = __ldg(gp + q);
+                  g[q * 8 + 0] = bf16_lo(u.x); g[q * 8 + 1] = bf16_hi(u.x);
+                  g[q * 8 + 2] = bf16_lo(u.y); g[q * 8 + 3] = bf16_hi(u.y);
+                  g[q * 8 + 4] = bf16_lo(u.z); g[q * 8 + 5] = bf16_hi(u.z);
+                  g[q * 8 + 6] = bf16_lo(u.w); g[q * 8 + 7] = bf16_hi(u.w);
+                  uint4 w = rp[q];
+                  r[q * 8 + 0] = bf16_lo(w.x); r[q * 8 + 1] = bf16_hi(w.x);
+                  r[q * 8 + 2] = bf16_lo(w.y); r[q * 8 + 3] = bf16_hi(w.y);
+                  r[q * 8 + 4] = bf16_lo(w.z); r[q * 8 + 5] = bf16_hi(w.z);
+                  r[q * 8 + 6] = bf16_lo(w.w); r[q * 8 + 7] = bf16_hi(w.w);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  g[j] = (n + j < p.N) ? __bfloat162float(grow[n + j]) : 0.f;
+                  r[j] = (n + j < p.N) ? __bfloat162float(rrow[n + j]) : 0.f;
+                }
+              }
+              // reference order: bias -> (bf16 linear output) -> gate * y -> residual + (...)
+              // (flux/transformer.py:464-465, 584-586, 652-653); each step is a bf16 tensor there.
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float y = __bfloat162float(__float2bfloat16(f[j]));
+                float gy = __bfloat162float(__float2bfloat16(g[j] * y));
+                float o = r[j] + gy;
+                if (p.nan_to_num) {
+                  o = __bfloat162float(__float2bfloat16(o));
+                  if (o != o) o = 0.f;
+                  else if (o == INFINITY) o = 65504.f;
+                  else if (o == -INFINITY) o = -65504.f;
+                }
+                f[j] = o;
+              }
+            } else if (p.epi == EPI_MUL_DGELU) {
+              if (full) {
+                const uint4* xp = reinterpret_cast<const uint4*>(xrow + n);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4 u = xp[q];
+                  f[q * 8 + 0] *= gelu_tanh_grad(bf16_lo(u.x)); f[q * 8 + 1] *= gelu_tanh_grad(bf16_hi(u.x));
+                  f[q * 8 + 2] *= gelu_tanh_grad(bf16_lo(u.y)); f[q * 8 + 3] *= gelu_tanh_grad(bf16_hi(u.y));
+                  f[q * 8 + 4] *= gelu_tanh_grad(bf16_lo(u.z)); f[q * 8 + 5] *= gelu_tanh_grad(bf16_hi(u.z));
+                  f[q * 8 + 6] *= gelu_tanh_grad(bf16_lo(u.w)); f[q * 8 + 7] *= gelu_tanh_grad(bf16_hi(u.w));
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n + j < p.N) f[j] *= gelu_tanh_grad(__bfloat162float(xrow[n + j]));
+              }
+            } else if (p.epi == EPI_ADD_RES) {
+              if (full) {
+                const uint4* rp = reinterpret_cast<const uint4*>(rrow + n);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4 w = rp[q];
+                  f[q * 8 + 0] += bf16_lo(w.x); f[q * 8 + 1] += bf16_hi(w.x);
+                  f[q * 8 + 2] += bf16_lo(w.y); f[q * 8 + 3] += bf16_hi(w.y);
+                  f[q * 8 + 4] += bf16_lo(w.z); f[q * 8 + 5] += bf16_hi(w.z);
+                  f[q * 8 + 6] += bf16_lo(w.w); f[q * 8 + 7] += bf16_hi(w.w);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n + j < p.N) f[j] += __bfloat162float(rrow[n + j]);
+              }
+            }
+            if (full) {
+              uint4* dp = reinterpret_cast<uint4*>(drow + n);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 u;
+                u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                dp[q] = u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n + j < p.N) drow[n + j] = __float2bfloat16(f[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce_bar(acc));
+      if (++acc == ACC_STAGES) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace stb

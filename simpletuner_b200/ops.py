@@ -1,0 +1,265 @@
+"""Tensor-level launchers for libstb200 (no autograd here — see functional.py).
+
+Every function takes CUDA bf16 tensors (views with arbitrary batch/row strides are fine as long as
+the last dimension is contiguous), launches on torch's *current* stream and returns torch tensors
+that own their memory through torch's caching allocator.  PyTorch is plumbing only: all arithmetic
+happens inside libstb200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AttnBwdArgs, AttnFwdArgs, GemmArgs, check
+
+EPI_STORE, EPI_GELU, EPI_GATE_RES, EPI_MUL_DGELU, EPI_ADD_RES = 0, 1, 2, 3, 4
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _as3d(t: torch.Tensor) -> torch.Tensor:
+    """[M, K] -> [1, M, K]; [B, S, K] stays (views allowed)."""
+    if t.dim() == 2:
+        return t.unsqueeze(0)
+    if t.dim() != 3:
+        raise ValueError(f"expected a 2-D or 3-D tensor, got {tuple(t.shape)}")
+    return t
+
+
+def _chk(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.StbError(f"{name} must be a CUDA tensor (simpletuner_b200 has no CPU path)")
+    if t.dtype != torch.bfloat16:
+        raise TypeError(f"{name} must be bfloat16, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise ValueError(f"{name} must be contiguous in its last dimension")
+
+
+def gemm(
+    a_list: Sequence[torch.Tensor],
+    w_list: Sequence[torch.Tensor],
+    bias: Optional[torch.Tensor] = None,
+    *,
+    out: Optional[torch.Tensor] = None,
+    epi: int = EPI_STORE,
+    gate: Optional[torch.Tensor] = None,
+    res: Optional[torch.Tensor] = None,
+    aux: Optional[torch.Tensor] = None,
+    nan_to_num: bool = False,
+    tile: Tuple[int, int] = (0, 0),
+) -> torch.Tensor:
+    """out[b, s, :] = epi( sum_i a_list[i][b, s, :] @ w_list[i].T + bias ).
+
+    a_list[i]: [B, S, K_i] or [M, K_i];  w_list[i]: [N, K_i] (nn.Linear layout, row stride free).
+    gate: [B, N];  res / aux / out: same leading shape as a_list[0] with last dim N.
+    """
+    nseg = len(a_list)
+    assert 1 <= nseg <= 3 and len(w_list) == nseg
+    a0 = _as3d(a_list[0])
+    B, S, _ = a0.shape
+    N = w_list[0].shape[0]
+    squeeze = a_list[0].dim() == 2
+    if out is None:
+        out = torch.empty((B, S, N), device=a0.device, dtype=torch.bfloat16)
+    out3 = _as3d(out)
+    _chk(out3, "out")
+    args = GemmArgs()
+    args.num_batches, args.rows_per_batch, args.N, args.nseg = B, S, N, nseg
+    for i, (a, w) in enumerate(zip(a_list, w_list)):
+        a3 = _as3d(a)
+        _chk(a3, f"a[{i}]")
+        _chk(w, f"w[{i}]")
+        if a3.shape[0] != B or a3.shape[1] != S or w.shape[0] != N or w.shape[1] != a3.shape[2]:
+            raise ValueError(f"segment {i}: shapes {tuple(a3.shape)} x {tuple(w.shape)} do not match")
+        sg = args.seg[i]
+        sg.a, sg.a_batch_stride, sg.a_row_stride = a3.data_ptr(), a3.stride(0), a3.stride(1)
+        sg.w, sg.w_row_stride, sg.K = w.data_ptr(), w.stride(0), a3.shape[2]
+    args.d, args.d_batch_stride, args.d_row_stride = out3.data_ptr(), out3.stride(0), out3.stride(1)
+    args.bias = _ptr(bias)
+    args.epi = epi
+    args.nan_to_num = int(nan_to_num)
+    if gate is not None:
+        _chk(gate, "gate")
+        g2 = gate if gate.dim() == 2 else gate.reshape(B, N)
+        args.gate, args.gate_batch_stride = g2.data_ptr(), g2.stride(0)
+    if res is not None:
+        r3 = _as3d(res)
+        _chk(r3, "res")
+        args.res, args.res_batch_stride, args.res_row_stride = r3.data_ptr(), r3.stride(0), r3.stride(1)
+    if aux is not None:
+        x3 = _as3d(aux)
+        _chk(x3, "aux")
+        args.aux, args.aux_batch_stride, args.aux_row_stride = x3.data_ptr(), x3.stride(0), x3.stride(1)
+    args.tile_mt, args.tile_bn = tile
+    check(_lib.lib().stb_gemm_bf16(C.byref(args), _stream()))
+    return out.squeeze(0) if (squeeze and out.dim() == 3) else out
+
+
+def attn_fwd(q, k, v, scale: Optional[float] = None, out: Optional[torch.Tensor] = None):
+    """q/k/v: [B, S, H, HD] views (HD contiguous).  Returns (o [B,Sq,H,HD] bf16, lse [B,H,Sq] fp32)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, n)
+    B, Sq, H, HD = q.shape
+    Sk = k.shape[1]
+    if scale is None:
+        scale = HD ** -0.5
+    if out is None:
+        out = torch.empty((B, Sq, H, HD), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, Sq), device=q.device, dtype=torch.float32)
+    a = AttnFwdArgs()
+    a.B, a.H, a.Sq, a.Sk, a.HD, a.scale = B, H, Sq, Sk, HD, float(scale)
+    a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.q_b, a.q_s, a.q_h = q.stride(0), q.stride(1), q.stride(2)
+    a.k_b, a.k_s, a.k_h = k.stride(0), k.stride(1), k.stride(2)
+    a.v_b, a.v_s, a.v_h = v.stride(0), v.stride(1), v.stride(2)
+    a.o = out.data_ptr()
+    a.o_b, a.o_s, a.o_h = out.stride(0), out.stride(1), out.stride(2)
+    a.lse = lse.data_ptr()
+    check(_lib.lib().stb_attn_fwd(C.byref(a), _stream()))
+    return out, lse
+
+
+def attn_bwd(q, k, v, o, d_o, lse, scale: Optional[float] = None, dq=None, dk=None, dv=None):
+    """Backward of attn_fwd.  Returns (dq, dk, dv) shaped like q, k, v ([B, S, H, HD], bf16)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (d_o, "d_o")):
+        _chk(t, n)
+    B, Sq, H, HD = q.shape
+    Sk = k.shape[1]
+    if scale is None:
+        scale = HD ** -0.5
+    dq = torch.empty((B, Sq, H, HD), device=q.device, dtype=torch.bfloat16) if dq is None else dq
+    dk = torch.empty((B, Sk, H, HD), device=q.device, dtype=torch.bfloat16) if dk is None else dk
+    dv = torch.empty((B, Sk, H, HD), device=q.device, dtype=torch.bfloat16) if dv is None else dv
+    delta = torch.empty((B, H, Sq), device=q.device, dtype=torch.float32)
+    a = AttnBwdArgs()
+    a.B, a.H, a.Sq, a.Sk, a.HD, a.scale = B, H, Sq, Sk, HD, float(scale)
+    a.q, a.k, a.v, a.o, a.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr()
+    a.q_b, a.q_s, a.q_h = q.stride(0), q.stride(1), q.stride(2)
+    a.k_b, a.k_s, a.k_h = k.stride(0), k.stride(1), k.stride(2)
+    a.v_b, a.v_s, a.v_h = v.stride(0), v.stride(1), v.stride(2)
+    a.o_b, a.o_s, a.o_h = o.stride(0), o.stride(1), o.stride(2)
+    a.do_b, a.do_s, a.do_h = d_o.stride(0), d_o.stride(1), d_o.stride(2)
+    a.lse, a.delta, a.dq_accum = lse.data_ptr(), delta.data_ptr(), None
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.dq_b, a.dq_s, a.dq_h = dq.stride(0), dq.stride(1), dq.stride(2)
+    a.dk_b, a.dk_s, a.dk_h = dk.stride(0), dk.stride(1), dk.stride(2)
+    a.dv_b, a.dv_s, a.dv_h = dv.stride(0), dv.stride(1), dv.stride(2)
+    check(_lib.lib().stb_attn_bwd(C.byref(a), _stream()))
+    return dq, dk, dv
+
+
+def ln_modulate_fwd(x, shift, scale, eps: float = 1e-6, out=None):
+    """out = LayerNorm(x) * (1 + scale[:, None]) + shift[:, None];  x [B,S,D], shift/scale [B,D] views
+    that share one batch stride (slices of the same modulation tensor)."""
+    _chk(x, "x"); _chk(shift, "shift"); _chk(scale, "scale")
+    B, S, D = x.shape
+    assert shift.shape == (B, D) and scale.shape == (B, D) and shift.stride(0) == scale.stride(0)
+    if out is None:
+        out = torch.empty((B, S, D), device=x.device, dtype=torch.bfloat16)
+    check(_lib.lib().stb_ln_modulate_fwd(
+        x.data_ptr(), x.stride(0), x.stride(1), shift.data_ptr(), scale.data_ptr(), shift.stride(0),
+        out.data_ptr(), out.stride(0), out.stride(1), B, S, D, eps, _stream()))
+    return out
+
+
+def ln_modulate_bwd(dy, x, scale, add=None, eps: float = 1e-6, out=None):
+    """dx of ln_modulate_fwd w.r.t. x (+ add, the residual-branch gradient)."""
+    _chk(dy, "dy"); _chk(x, "x"); _chk(scale, "scale")
+    B, S, D = x.shape
+    if out is None:
+        out = torch.empty((B, S, D), device=x.device, dtype=torch.bfloat16)
+    ab, as_ = (add.stride(0), add.stride(1)) if add is not None else (0, 0)
+    check(_lib.lib().stb_ln_modulate_bwd(
+        dy.data_ptr(), dy.stride(0), dy.stride(1), x.data_ptr(), x.stride(0), x.stride(1),
+        scale.data_ptr(), scale.stride(0), _ptr(add), ab, as_,
+        out.data_ptr(), out.stride(0), out.stride(1), B, S, D, eps, _stream()))
+    return out
+
+
+def qk_rmsnorm_rope_fwd(src, k_off, H, HD, wq, wk, wq_added=None, wk_added=None, s_split=0,
+                        cos=None, sin=None, eps: float = 1e-6, q_out=None, k_out=None):
+    """src [B, S, C] projection output with q at column 0 and k at column k_off.
+    Returns q, k as [B, S, H, HD]."""
+    _chk(src, "src")
+    B, S, _ = src.shape
+    if q_out is None:
+        q_out = torch.empty((B, S, H, HD), device=src.device, dtype=torch.bfloat16)
+    if k_out is None:
+        k_out = torch.empty((B, S, H, HD), device=src.device, dtype=torch.bfloat16)
+    assert q_out.stride() == k_out.stride() and q_out.stride(2) == HD and q_out.stride(3) == 1
+    if cos is not None:
+        assert cos.dtype == torch.float32 and cos.is_contiguous() and cos.shape == (S, HD)
+        assert sin.dtype == torch.float32 and sin.is_contiguous() and sin.shape == (S, HD)
+    check(_lib.lib().stb_qk_rmsnorm_rope_fwd(
+        src.data_ptr(), src.stride(0), src.stride(1), k_off, _ptr(wq), _ptr(wk), _ptr(wq_added), _ptr(wk_added),
+        s_split, _ptr(cos), _ptr(sin), q_out.data_ptr(), k_out.data_ptr(), q_out.stride(0), q_out.stride(1),
+        B, S, H, HD, eps, _stream()))
+    return q_out, k_out
+
+
+def qk_rmsnorm_rope_bwd(dq, dk, src, k_off, H, HD, wq, wk, wq_added=None, wk_added=None, s_split=0,
+                        cos=None, sin=None, eps: float = 1e-6, dsrc=None):
+    """Writes the q / k column ranges of dsrc ([B, S, C], same layout as src)."""
+    B, S, _ = src.shape
+    assert dq.stride() == dk.stride() and dq.stride(2) == HD
+    if dsrc is None:
+        dsrc = torch.empty_like(src)
+    check(_lib.lib().stb_qk_rmsnorm_rope_bwd(
+        dq.data_ptr(), dk.data_ptr(), dq.stride(0), dq.stride(1), src.data_ptr(), src.stride(0), src.stride(1),
+        k_off, _ptr(wq), _ptr(wk), _ptr(wq_added), _ptr(wk_added), s_split, _ptr(cos), _ptr(sin),
+        dsrc.data_ptr(), dsrc.stride(0), dsrc.stride(1), B, S, H, HD, eps, _stream()))
+    return dsrc
+
+
+def flow_prep_pack(latents, noise, sigmas, want_unpacked: bool = True):
+    """Returns (noisy [B,C,H,W] or None, packed [B, H/2*W/2, 4C])."""
+    assert latents.is_contiguous() and noise.is_contiguous() and sigmas.dtype == torch.float32
+    _chk(latents, "latents"); _chk(noise, "noise")
+    B, Cc, Hh, Ww = latents.shape
+    noisy = torch.empty_like(latents) if want_unpacked else None
+    packed = torch.empty((B, (Hh // 2) * (Ww // 2), 4 * Cc), device=latents.device, dtype=torch.bfloat16)
+    check(_lib.lib().stb_flow_prep_pack(latents.data_ptr(), noise.data_ptr(), sigmas.contiguous().data_ptr(),
+                                        _ptr(noisy), packed.data_ptr(), B, Cc, Hh, Ww, _stream()))
+    return noisy, packed
+
+
+def flow_mse_loss(pred_packed, latents, noise, want_grad: bool = True, grad_scale: float = 1.0):
+    """Returns (loss fp32 scalar tensor [1], dpred_packed or None)."""
+    assert pred_packed.is_contiguous() and latents.is_contiguous() and noise.is_contiguous()
+    B, Cc, Hh, Ww = latents.shape
+    loss = torch.empty((1,), device=latents.device, dtype=torch.float32)
+    dpred = torch.empty_like(pred_packed) if want_grad else None
+    check(_lib.lib().stb_flow_mse_loss(pred_packed.data_ptr(), latents.data_ptr(), noise.data_ptr(),
+                                       loss.data_ptr(), _ptr(dpred), grad_scale, B, Cc, Hh, Ww, _stream()))
+    return loss, dpred
+
+
+def skinny_tn(L, Rm, alpha: float = 1.0, out: Optional[torch.Tensor] = None):
+    """out[r, n] += alpha * sum_m L[m, r] * Rm[m, n].  L [B,S,R] or [M,R]; Rm [B,S,N] or [M,N]; out fp32."""
+    L3, R3 = _as3d(L), _as3d(Rm)
+    _chk(L3, "L"); _chk(R3, "Rm")
+    B, S, R = L3.shape
+    N = R3.shape[2]
+    if out is None:
+        out = torch.zeros((R, N), device=L.device, dtype=torch.float32)
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    check(_lib.lib().stb_skinny_tn(L3.data_ptr(), L3.stride(0), L3.stride(1), R3.data_ptr(), R3.stride(0),
+                                   R3.stride(1), out.data_ptr(), B, S, R, N, alpha, _stream()))
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.lib().stb_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.lib().stb_reset_launch_count()

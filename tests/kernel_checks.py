@@ -1,0 +1,335 @@
+"""Kernel-level parity checks of libstb200 against plain PyTorch fp32 math on the same GPU tensors.
+
+Each check is a function returning a dict {"ok": bool, "max_err": ..., "tol": ..., ...}.  They are used
+by the `-m gpu` pytest tests and by tools/run_gpu_checks.py (which runs every check in its own
+subprocess so that a trapped kernel cannot poison the rest of the run).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from simpletuner_b200 import ops
+
+DEV = "cuda"
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(DEV)
+
+
+def _report(name, got, ref, atol, rtol, extra=None):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    nbad = int(bad.sum().item())
+    out = {
+        "name": name,
+        "ok": nbad == 0 and bool(torch.isfinite(got).all().item()),
+        "max_err": float(err.max().item()),
+        "ref_absmax": float(ref.abs().max().item()),
+        "n_bad": nbad,
+        "numel": got.numel(),
+    }
+    if nbad:
+        idx = torch.nonzero(bad)[:8].tolist()
+        out["first_bad"] = idx
+        # error structure along the last two dims in 16-wide blocks: reveals tile / descriptor mistakes
+        e2 = err.reshape(-1, err.shape[-1])
+        rows = e2.shape[0]
+        rb = max(1, rows // 8)
+        cb = max(1, e2.shape[1] // 8)
+        out["row_block_maxerr"] = [round(float(e2[i * rb:(i + 1) * rb].max().item()), 4) for i in range(min(8, math.ceil(rows / rb)))]
+        out["col_block_maxerr"] = [round(float(e2[:, j * cb:(j + 1) * cb].max().item()), 4) for j in range(min(8, math.ceil(e2.shape[1] / cb)))]
+    if extra:
+        out.update(extra)
+    return out
+
+
+# --------------------------------------------------------------------------------------------- GEMM
+def gelu_tanh(x):
+    return torch.nn.functional.gelu(x, approximate="tanh")
+
+
+def check_gemm(M=256, N=256, K=128, B=1, bias=False, epi=ops.EPI_STORE, tile=(0, 0), segs=None, strided=False,
+               nan_to_num=False, name=None):
+    """segs: list of extra K sizes appended as additional segments."""
+    Ks = [K] + list(segs or [])
+    S = M
+    a_list, w_list = [], []
+    for i, k in enumerate(Ks):
+        if strided:
+            full = _rand(B, S + 3, k + 16, seed=10 + i)
+            a_list.append(full[:, 1:S + 1, 8:8 + k])
+            wfull = _rand(N, k + 8, scale=0.5, seed=20 + i)
+            w_list.append(wfull[:, :k])
+        else:
+            a_list.append(_rand(B, S, k, seed=10 + i))
+            w_list.append(_rand(N, k, scale=0.5, seed=20 + i))
+    bias_t = _rand(N, seed=30) if bias else None
+    acc = sum(a.float() @ w.float().t() for a, w in zip(a_list, w_list))
+    if bias_t is not None:
+        acc = acc + bias_t.float()
+    gate = res = aux = None
+    kw = {}
+    if epi == ops.EPI_STORE:
+        ref = acc
+    elif epi == ops.EPI_GELU:
+        aux = torch.zeros(B, S, N, dtype=torch.bfloat16, device=DEV)
+        ref = gelu_tanh(acc.bfloat16().float())
+    elif epi == ops.EPI_GATE_RES:
+        gate = _rand(B, N, seed=31)
+        res = _rand(B, S, N, seed=32)
+        y = acc.bfloat16().float()
+        ref = res.float() + (gate.float()[:, None, :] * y).bfloat16().float()
+    elif epi == ops.EPI_MUL_DGELU:
+        aux = _rand(B, S, N, seed=33)
+        x = aux.float().requires_grad_(True)
+        gelu_tanh(x).sum().backward()
+        ref = acc * x.grad
+    elif epi == ops.EPI_ADD_RES:
+        res = _rand(B, S, N, seed=32)
+        ref = acc + res.float()
+    out = None
+    if strided:
+        outfull = torch.zeros(B, S + 2, N + 8, dtype=torch.bfloat16, device=DEV)
+        out = outfull[:, 1:S + 1, :N]
+    got = ops.gemm(a_list, w_list, bias_t, out=out, epi=epi, gate=gate, res=res, aux=aux, nan_to_num=nan_to_num, tile=tile)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max().item())
+    r = _report(name or f"gemm_M{M}_N{N}_K{Ks}_B{B}_epi{epi}_tile{tile}", got, ref, atol=scale * 6e-3, rtol=1.6e-2)
+    if epi == ops.EPI_GELU:
+        r2 = _report("aux", aux, acc, atol=float(acc.abs().max()) * 6e-3, rtol=1.6e-2)
+        r["aux_ok"] = r2["ok"]
+        r["ok"] = r["ok"] and r2["ok"]
+    if strided:
+        # nothing outside the view may be touched
+        mask = torch.ones_like(outfull, dtype=torch.bool)
+        mask[:, 1:S + 1, :N] = False
+        r["halo_clean"] = bool((outfull[mask] == 0).all().item())
+        r["ok"] = r["ok"] and r["halo_clean"]
+    return r
+
+
+# --------------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, scale):
+    # q,k,v [B,S,H,D] -> fp32 reference in [B,S,H,D]
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    lse = torch.logsumexp(s, dim=-1)
+    p = torch.softmax(s, dim=-1)
+    o = p @ vf
+    return o.permute(0, 2, 1, 3), lse
+
+
+def check_attn_fwd(B=1, H=2, Sq=256, Sk=None, HD=128, strided=False, name=None, qscale=1.0):
+    Sk = Sk or Sq
+    if strided:
+        # q/k/v as slices of a fused [B, S, 3*H*HD] projection buffer (the layout the model uses)
+        assert Sk == Sq
+        qkv = _rand(B, Sq, 3 * H * HD, seed=1, scale=qscale)
+        q = qkv[..., 0 * H * HD:1 * H * HD].unflatten(-1, (H, HD))
+        k = qkv[..., 1 * H * HD:2 * H * HD].unflatten(-1, (H, HD))
+        v = qkv[..., 2 * H * HD:3 * H * HD].unflatten(-1, (H, HD))
+    else:
+        q = _rand(B, Sq, H, HD, seed=1, scale=qscale)
+        k = _rand(B, Sk, H, HD, seed=2, scale=qscale)
+        v = _rand(B, Sk, H, HD, seed=3)
+    scale = HD ** -0.5
+    o, lse = ops.attn_fwd(q, k, v, scale)
+    torch.cuda.synchronize()
+    o_ref, lse_ref = _attn_ref(q, k, v, scale)
+    r = _report(name or f"attn_fwd_B{B}_H{H}_Sq{Sq}_Sk{Sk}_HD{HD}", o, o_ref, atol=2e-2 * float(o_ref.abs().max()), rtol=2e-2)
+    r2 = _report("lse", lse, lse_ref, atol=2e-2, rtol=1e-3)
+    r["lse_ok"] = r2["ok"]
+    r["lse_max_err"] = r2["max_err"]
+    r["ok"] = r["ok"] and r2["ok"]
+    return r
+
+
+def check_attn_bwd(B=1, H=2, Sq=256, Sk=None, HD=128, name=None):
+    Sk = Sk or Sq
+    q = _rand(B, Sq, H, HD, seed=1)
+    k = _rand(B, Sk, H, HD, seed=2)
+    v = _rand(B, Sk, H, HD, seed=3)
+    d_o = _rand(B, Sq, H, HD, seed=4)
+    scale = HD ** -0.5
+    o, lse = ops.attn_fwd(q, k, v, scale)
+    dq, dk, dv = ops.attn_bwd(q, k, v, o, d_o, lse, scale)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    o_ref, _ = _attn_ref(qf, kf, vf, scale)
+    o_ref.backward(d_o.float())
+    res = {}
+    ok = True
+    for nm, got, ref in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        r = _report(nm, got, ref, atol=3e-2 * float(ref.abs().max()), rtol=3e-2)
+        res[nm] = r
+        ok = ok and r["ok"]
+    return {"name": name or f"attn_bwd_B{B}_H{H}_Sq{Sq}_Sk{Sk}_HD{HD}", "ok": ok,
+            "max_err": max(res[n]["max_err"] for n in res), **{f"{n}_detail": res[n] for n in res if not res[n]["ok"]}}
+
+
+# --------------------------------------------------------------------------------------------- elementwise
+def check_ln_modulate(B=2, S=64, D=3072):
+    x = _rand(B, S, D, seed=1)
+    mod = _rand(B, 6 * D, seed=2, scale=0.3)
+    shift, scale = mod[:, :D], mod[:, D:2 * D]
+    out = ops.ln_modulate_fwd(x, shift, scale)
+    ln = torch.nn.functional.layer_norm(x.float(), (D,), eps=1e-6)
+    ref = ln * (1 + scale.float()[:, None]) + shift.float()[:, None]
+    r = _report(f"ln_modulate_fwd_D{D}", out, ref, atol=3e-2, rtol=2e-2)
+    # backward
+    dy = _rand(B, S, D, seed=3)
+    add = _rand(B, S, D, seed=4)
+    dx = ops.ln_modulate_bwd(dy, x, scale, add=add)
+    xf = x.float().requires_grad_(True)
+    lnf = torch.nn.functional.layer_norm(xf, (D,), eps=1e-6)
+    (lnf * (1 + scale.float().bfloat16().float()[:, None])).backward(dy.float())
+    ref_dx = xf.grad + add.float()
+    r2 = _report("ln_modulate_bwd", dx, ref_dx, atol=3e-2 * float(ref_dx.abs().max()), rtol=2e-2)
+    r["bwd_ok"] = r2["ok"]
+    r["bwd_max_err"] = r2["max_err"]
+    r["ok"] = r["ok"] and r2["ok"]
+    return r
+
+
+def _rope_tables(S, HD, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    ang = torch.rand(S, HD // 2, generator=g) * 6.28
+    cos = ang.cos().repeat_interleave(2, dim=-1).float().to(DEV).contiguous()
+    sin = ang.sin().repeat_interleave(2, dim=-1).float().to(DEV).contiguous()
+    return cos, sin
+
+
+def _rmsnorm_rope_ref(x, w, cos, sin, eps=1e-6):
+    # x [B,S,H,HD] fp32
+    var = x.pow(2).mean(-1, keepdim=True)
+    y = x * torch.rsqrt(var + eps) * w
+    xr, xi = y.reshape(*y.shape[:-1], -1, 2).unbind(-1)
+    rot = torch.stack([-xi, xr], dim=-1).flatten(3)
+    return y * cos[None, :, None, :] + rot * sin[None, :, None, :]
+
+
+def check_qk_rmsnorm_rope(B=2, S=96, H=4, HD=128, s_split=32):
+    Cc = 3 * H * HD
+    src = _rand(B, S, Cc, seed=1)
+    wq, wk, wq1, wk1 = (_rand(HD, seed=10 + i, scale=0.2) + 1 for i in range(4))
+    cos, sin = _rope_tables(S, HD)
+    q, k = ops.qk_rmsnorm_rope_fwd(src, H * HD, H, HD, wq, wk, wq1, wk1, s_split, cos, sin)
+    torch.cuda.synchronize()
+
+    def ref_of(xf):
+        xq = xf[..., :H * HD].unflatten(-1, (H, HD))
+        xk = xf[..., H * HD:2 * H * HD].unflatten(-1, (H, HD))
+        outq = torch.cat([_rmsnorm_rope_ref(xq[:, :s_split], wq1.float(), cos[:s_split], sin[:s_split]),
+                          _rmsnorm_rope_ref(xq[:, s_split:], wq.float(), cos[s_split:], sin[s_split:])], 1)
+        outk = torch.cat([_rmsnorm_rope_ref(xk[:, :s_split], wk1.float(), cos[:s_split], sin[:s_split]),
+                          _rmsnorm_rope_ref(xk[:, s_split:], wk.float(), cos[s_split:], sin[s_split:])], 1)
+        return outq, outk
+
+    xf = src.float().requires_grad_(True)
+    rq, rk = ref_of(xf)
+    r = _report(f"qk_rmsnorm_rope_fwd_HD{HD}", torch.cat([q, k], -1), torch.cat([rq, rk], -1), atol=4e-2, rtol=2e-2)
+    dq = _rand(B, S, H, HD, seed=20)
+    dk = _rand(B, S, H, HD, seed=21)
+    dsrc = torch.zeros_like(src)
+    ops.qk_rmsnorm_rope_bwd(dq, dk, src, H * HD, H, HD, wq, wk, wq1, wk1, s_split, cos, sin, dsrc=dsrc)
+    torch.cuda.synchronize()
+    (rq * dq.float()).sum().backward(retain_graph=True)
+    (rk * dk.float()).sum().backward()
+    ref = xf.grad[..., :2 * H * HD]
+    r2 = _report("qk_rmsnorm_rope_bwd", dsrc[..., :2 * H * HD], ref, atol=3e-2 * float(ref.abs().max()), rtol=3e-2)
+    r["bwd_ok"] = r2["ok"]
+    r["bwd_max_err"] = r2["max_err"]
+    r["v_untouched"] = bool((dsrc[..., 2 * H * HD:] == 0).all().item())
+    r["ok"] = r["ok"] and r2["ok"] and r["v_untouched"]
+    return r
+
+
+def check_flow(B=2, Cc=16, Hh=32, Ww=48):
+    lat = _rand(B, Cc, Hh, Ww, seed=1)
+    noise = _rand(B, Cc, Hh, Ww, seed=2)
+    sig = torch.tensor([0.25, 0.8125][:B] + [0.5] * max(0, B - 2), dtype=torch.float32, device=DEV)
+    noisy, packed = ops.flow_prep_pack(lat, noise, sig)
+    torch.cuda.synchronize()
+    # eager bf16 chain exactly as the reference writes it (common.py:4953-4960, 4989-4991)
+    grid = sig.view(B, 1, 1, 1).to(torch.bfloat16)
+    ref_noisy = (1.0 - grid) * lat + grid * noise
+    ref_packed = ref_noisy.view(B, Cc, Hh // 2, 2, Ww // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, (Hh // 2) * (Ww // 2), Cc * 4)
+    bit_noisy = bool(torch.equal(noisy, ref_noisy))
+    bit_packed = bool(torch.equal(packed, ref_packed))
+    pred = _rand(B, (Hh // 2) * (Ww // 2), Cc * 4, seed=3)
+    loss, dpred = ops.flow_mse_loss(pred, lat, noise)
+    torch.cuda.synchronize()
+    pf = pred.float().requires_grad_(True)
+    unp = pf.view(B, Hh // 2, Ww // 2, Cc, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, Cc, Hh, Ww)
+    tgt = (noise - lat).float()
+    ref_loss = torch.nn.functional.mse_loss(unp, tgt, reduction="none").mean(dim=(1, 2, 3)).mean()
+    ref_loss.backward()
+    lerr = abs(float(loss.item()) - float(ref_loss.item()))
+    r = _report("flow_loss_grad", dpred, pf.grad, atol=1e-2 * float(pf.grad.abs().max()), rtol=1e-2)
+    r.update({"name": "flow_prep_loss", "bit_exact_noisy": bit_noisy, "bit_exact_packed": bit_packed,
+              "loss": float(loss.item()), "loss_ref": float(ref_loss.item()), "loss_err": lerr})
+    r["ok"] = r["ok"] and bit_noisy and bit_packed and lerr <= 1e-5 * max(1.0, abs(float(ref_loss.item())))
+    return r
+
+
+def check_skinny(B=2, S=300, R=16, N=3072):
+    L = _rand(B, S, R, seed=1)
+    Rm = _rand(B, S, N, seed=2)
+    out = ops.skinny_tn(L, Rm, alpha=0.5)
+    torch.cuda.synchronize()
+    ref = 0.5 * (L.float().reshape(-1, R).t() @ Rm.float().reshape(-1, N))
+    return _report(f"skinny_tn_R{R}_N{N}", out, ref, atol=1e-3 * float(ref.abs().max()), rtol=1e-3)
+
+
+# --------------------------------------------------------------------------------------------- registry
+E = ops
+CHECKS = {
+    # GEMM: descriptor / pipeline basics first
+    "gemm_basic": lambda: check_gemm(256, 256, 128),
+    "gemm_k64": lambda: check_gemm(128, 256, 64),
+    "gemm_deepk": lambda: check_gemm(256, 512, 1024),
+    "gemm_tails": lambda: check_gemm(200, 328, 200, B=2),
+    "gemm_bn128": lambda: check_gemm(256, 384, 256, tile=(1, 128)),
+    "gemm_bn64": lambda: check_gemm(256, 64, 256, tile=(1, 64)),
+    "gemm_mt2": lambda: check_gemm(512, 512, 256, tile=(2, 256)),
+    "gemm_mt2_bn128": lambda: check_gemm(384, 256, 256, tile=(2, 128)),
+    "gemm_persistent": lambda: check_gemm(4096, 3072, 512),
+    "gemm_seg2": lambda: check_gemm(256, 256, 192, segs=[64]),
+    "gemm_seg3_lora": lambda: check_gemm(256, 512, 256, segs=[128, 16], bias=True),
+    "gemm_strided": lambda: check_gemm(200, 256, 136, B=2, strided=True, bias=True),
+    "gemm_bias": lambda: check_gemm(256, 256, 128, bias=True),
+    "gemm_gelu": lambda: check_gemm(256, 512, 128, bias=True, epi=E.EPI_GELU),
+    "gemm_gate_res": lambda: check_gemm(256, 256, 128, B=2, bias=True, epi=E.EPI_GATE_RES, nan_to_num=True),
+    "gemm_mul_dgelu": lambda: check_gemm(256, 256, 128, epi=E.EPI_MUL_DGELU),
+    "gemm_add_res": lambda: check_gemm(256, 256, 128, epi=E.EPI_ADD_RES),
+    "gemm_flux_shape": lambda: check_gemm(4096, 3072, 3072, B=1, bias=True),
+    # attention
+    "attn_fwd_256": lambda: check_attn_fwd(1, 2, 256),
+    "attn_fwd_128": lambda: check_attn_fwd(1, 1, 128),
+    "attn_fwd_512": lambda: check_attn_fwd(2, 3, 512),
+    "attn_fwd_ragged": lambda: check_attn_fwd(1, 2, 333, 417),
+    "attn_fwd_strided": lambda: check_attn_fwd(2, 4, 384, strided=True),
+    "attn_fwd_hd64": lambda: check_attn_fwd(1, 2, 320, HD=64),
+    "attn_fwd_long": lambda: check_attn_fwd(1, 2, 4608),
+    "attn_fwd_bigscore": lambda: check_attn_fwd(1, 2, 512, qscale=4.0),
+    "attn_bwd_256": lambda: check_attn_bwd(1, 2, 256),
+    "attn_bwd_128": lambda: check_attn_bwd(1, 1, 128),
+    "attn_bwd_ragged": lambda: check_attn_bwd(1, 2, 333, 417),
+    "attn_bwd_hd64": lambda: check_attn_bwd(1, 2, 320, HD=64),
+    "attn_bwd_long": lambda: check_attn_bwd(1, 2, 2304),
+    # elementwise
+    "ln_modulate": lambda: check_ln_modulate(),
+    "ln_modulate_d1536": lambda: check_ln_modulate(D=1536),
+    "qk_rmsnorm_rope": lambda: check_qk_rmsnorm_rope(),
+    "qk_rmsnorm_rope_hd64": lambda: check_qk_rmsnorm_rope(HD=64),
+    "flow": lambda: check_flow(),
+    "skinny": lambda: check_skinny(),
+    "skinny_r48": lambda: check_skinny(R=48, N=4096),
+}
