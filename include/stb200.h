@@ -150,6 +150,11 @@ int stb_flow_prep_pack(const void* latents, const void* noise, const float* sigm
 int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* noise, float* loss_out,
                       void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, void* stream);
 
+/* y[b, s, :] = gate[b, :] * x[b, s, :]  — gradient of `gate * linear(...)` w.r.t. the linear output
+ * (flux/transformer.py:464, 584, 652), applied before the dgrad GEMM. */
+int stb_gate_mul(const void* x, long long x_b, long long x_s, const void* gate, long long g_b, void* y,
+                 long long y_b, long long y_s, int B, int S, int D, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * LoRA weight gradients: out[r, n] += alpha * sum_m L[m, r] * Rm[m, n]   (fp32 out, R in 16..64)
  *   dA = s * (dY B)^T X   (L = dY B [M, r], Rm = X  [M, K])

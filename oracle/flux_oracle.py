@@ -398,8 +398,8 @@ def flow_loss(pred: Tensor, target: Tensor) -> Tensor:
 def flux_model_predict(P, cfg, noisy_latents, timesteps, prompt_embeds, pooled, guidance_value=1.0,
                        lora=None, lora_scale=1.0):
     """Flux._model_predict_single, default path (reference flux/model.py:707-864): pack, constant
-    guidance, img_ids, timesteps/1000, zero txt_ids, transformer, unpack (vae_scale_factor 8 -> the
-    wrapper passes pixel H, W = latent * 8)."""
+    guidance, img_ids, timesteps/1000, zero txt_ids, transformer, unpack (height=latent*8 with
+    vae_scale_factor=16, reference flux/model.py:856-861)."""
     B, Cc, Hh, Ww = noisy_latents.shape
     packed = pack_latents(noisy_latents, B, Cc, Hh, Ww)
     guidance = torch.full((B,), float(guidance_value), dtype=torch.float32) if cfg.guidance_embeds else None
@@ -407,7 +407,7 @@ def flux_model_predict(P, cfg, noisy_latents, timesteps, prompt_embeds, pooled, 
     txt_ids = torch.zeros(prompt_embeds.shape[1], 3)
     t = timesteps.to(torch.float32) / 1000.0
     out = flux_forward(P, cfg, packed, prompt_embeds, pooled, t, img_ids, txt_ids, guidance, lora, lora_scale)
-    return unpack_latents(out, Hh * 8, Ww * 8, 8)
+    return unpack_latents(out, Hh * 8, Ww * 8, 16)
 
 
 def flux_train_step_loss(P, cfg, batch, lora=None, lora_scale=1.0):

@@ -274,8 +274,17 @@ int stb_gemm_bf16(const stb_gemm_args* a, void* stream) {
   if (a->epi < 0 || a->epi > 4) return fail(STB_ERR_ARG, "unknown epilogue %d", a->epi);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int bn = a->tile_bn, mt = a->tile_mt;
-  if (bn == 0) bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
-  if (mt == 0) mt = 1;
+  if (bn == 0) {
+    bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+    // skinny-M problems (conditioning / modulation GEMMs, M = batch): spread the weight stream over more SMs
+    const long long t256 = (long long)((a->rows_per_batch + 127) / 128) * a->num_batches * ((a->N + 255) / 256);
+    if (bn == 256 && t256 < num_sms()) bn = 128;
+  }
+  if (mt == 0) {
+    // 256-row CTA tiles halve the per-FLOP L2->SMEM traffic; use them once there are >= 2 waves of them
+    const long long t2 = (long long)((a->rows_per_batch + 255) / 256) * a->num_batches * ((a->N + bn - 1) / bn);
+    mt = (bn >= 128 && t2 >= 2ll * num_sms()) ? 2 : 1;
+  }
   if (mt == 1 && bn == 256) return launch_gemm<1, 256>(a, st);
   if (mt == 2 && bn == 256) return launch_gemm<2, 256>(a, st);
   if (mt == 1 && bn == 128) return launch_gemm<1, 128>(a, st);
@@ -486,6 +495,20 @@ int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* 
   const int grid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
   stb::flow_mse_loss_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pred_packed), static_cast<const __nv_bfloat16*>(latents), static_cast<const __nv_bfloat16*>(noise), loss_out, static_cast<__nv_bfloat16*>(dpred_packed), grad_scale, B, C, Hh, Ww);
   STB_LAUNCH_CHECK("flow_mse_loss");
+  return 0;
+}
+
+int stb_gate_mul(const void* x, long long x_b, long long x_s, const void* gate, long long g_b, void* y,
+                 long long y_b, long long y_s, int B, int S, int D, void* stream) {
+  if (int r = check_device()) return r;
+  if ((D & 7) || !aligned16(x) || !aligned16(y) || !aligned16(gate) || (x_s & 7) || (x_b & 7) || (y_s & 7) ||
+      (y_b & 7) || (g_b & 7))
+    return fail(STB_ERR_ARG, "gate_mul alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = (long long)B * S * (D >> 3);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
+  stb::gate_mul_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_b, x_s, static_cast<const __nv_bfloat16*>(gate), g_b, static_cast<__nv_bfloat16*>(y), y_b, y_s, B, S, D);
+  STB_LAUNCH_CHECK("gate_mul");
   return 0;
 }
 

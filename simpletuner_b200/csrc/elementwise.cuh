@@ -478,6 +478,31 @@ skinny_tn_kernel(const __nv_bfloat16* __restrict__ L, long long l_b, long long l
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// y[b, s, :] = gate[b, :] * x[b, s, :]   (backward of `gate * linear(...)`, flux/transformer.py:464,
+// 584, 652 — the incoming gradient is scaled by the adaLN gate before the dgrad GEMM).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gate_mul_kernel(const __nv_bfloat16* __restrict__ x, long long x_b, long long x_s,
+                const __nv_bfloat16* __restrict__ gate, long long g_b, __nv_bfloat16* __restrict__ y,
+                long long y_b, long long y_s, int B, int S, int D) {
+  const int vec_per_row = D >> 3;
+  const long long total = (long long)B * S * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % vec_per_row) * 8;
+    const long long r = i / vec_per_row;
+    const int s = int(r % S);
+    const int b = int(r / S);
+    float xv[8], gv[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + b * x_b + s * x_s + c), xv);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gate + b * g_b + c)), gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = xv[j] * gv[j];
+    *reinterpret_cast<uint4*>(y + b * y_b + s * y_s + c) = pack8(o);
+  }
+}
+
 // fp32 -> bf16 cast with optional transpose-free accumulate into an existing bf16 grad
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {

@@ -1,0 +1,170 @@
+"""Flux training wrapper on libstb200 — mirror of the step-level API the reference Trainer calls
+(SURVEY.md §8b seam B9):
+
+  * `prepare_batch(batch, state)`   reference helpers/models/common.py:5862-6041 (flow-matching branch)
+  * `model_predict(prepared_batch)` reference helpers/models/flux/model.py:630-864 (`_model_predict_single`)
+  * `loss(prepared_batch, model_output)` / `loss_with_logs(...)`  common.py:6217-6430, xm_mixin.py:476-485
+
+Batch dict keys are the collate contract of the reference (training/collate.py:1316-1349):
+`latent_batch`, `prompt_embeds`, `add_text_embeds`; `prepare_batch` adds `latents`, `noise`,
+`input_noise`, `sigmas` ([B,1,1,1] after expand_sigmas), `timesteps`, `noisy_latents`,
+`encoder_hidden_states`, `added_cond_kwargs`.  Random draws use torch's default generators in the
+reference order (randn_like(latents) then randn((bsz,))) so a seeded run samples
+the same noise / sigmas.  All tensor arithmetic is libstb200 (flow_prep_pack / flow_mse_loss / the
+transformer); the patchify / unpatchify index math is folded into those two kernels.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Any, Dict, Optional
+
+import torch
+
+from .. import ops
+from ..training.schedule import sample_flow_sigmas
+from .blocks import FlowLossFn
+from .transformer import FluxTransformer2DModel
+
+
+def default_config(**over) -> SimpleNamespace:
+    """Hot-path-relevant reference defaults (SURVEY.md §5 'Config / flags')."""
+    cfg = dict(
+        weight_dtype=torch.bfloat16, base_weight_dtype=torch.bfloat16,
+        flow_matching=True, flow_schedule_shift=3.0, flow_schedule_auto_shift=False, flow_sigmoid_scale=1.0,
+        flow_use_uniform_schedule=False, flow_use_beta_schedule=False, flux_fast_schedule=False,
+        flux_guidance_mode="constant", flux_guidance_value=1.0,
+        input_perturbation=0.0, offset_noise=False, loss_type="l2", snr_gamma=None,
+        lora_rank=16, lora_alpha=None, lora_dropout=0.0, flux_lora_target="all",
+        flux_attention_masked_training=False,
+    )
+    cfg.update(over)
+    return SimpleNamespace(**cfg)
+
+
+class Flux:
+    """Drop-in for the reference `Flux(ImageModelFoundation)` step methods.  `self.model` is the
+    denoiser (optionally DDP-wrapped), `self.accelerator.device` the rank's CUDA device."""
+
+    NAME = "Flux.1"
+    PREDICTION_TYPE = "flow_matching"
+
+    def __init__(self, config: Optional[SimpleNamespace] = None, transformer: Optional[FluxTransformer2DModel] = None,
+                 device: Optional[torch.device] = None, **transformer_kwargs):
+        self.config = config or default_config()
+        dev = device or torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        self.accelerator = SimpleNamespace(device=dev)
+        self.noise_schedule = SimpleNamespace(config=SimpleNamespace(num_train_timesteps=1000, patch_size=2,
+                                                                       base_image_seq_len=256, max_image_seq_len=4096,
+                                                                       base_shift=0.5, max_shift=1.15))
+        self.model = transformer if transformer is not None else FluxTransformer2DModel(**transformer_kwargs)
+
+    # ------------------------------------------------------------------------------------------
+    def get_trained_component(self):
+        return self.model
+
+    def _denoiser(self) -> FluxTransformer2DModel:
+        m = self.model
+        return m.module if hasattr(m, "module") else m
+
+    def add_lora_adapter(self):
+        """common.py:1049-1117 for the Flux targets (flux/model.py:1235-1383)."""
+        c = self.config
+        if getattr(c, "lora_dropout", 0.0):
+            raise NotImplementedError("lora_dropout > 0 is not supported by the fused LoRA path (pin --lora_dropout=0)")
+        alpha = c.lora_alpha if c.lora_alpha is not None else c.lora_rank
+        from .transformer import FLUX_LORA_TARGETS
+        return self._denoiser().add_adapter(rank=c.lora_rank, lora_alpha=alpha,
+                                            target_modules=FLUX_LORA_TARGETS[c.flux_lora_target])
+
+    # ------------------------------------------------------------------------------------------
+    def prepare_batch(self, batch: Dict[str, Any], state: Dict[str, Any]) -> Dict[str, Any]:
+        if not batch:
+            return batch
+        c = self.config
+        dev = self.accelerator.device
+        kw = {"device": dev, "dtype": c.weight_dtype}
+        if batch.get("prompt_embeds") is not None:
+            batch["encoder_hidden_states"] = batch["prompt_embeds"].to(**kw, non_blocking=True)
+        pooled = batch.get("add_text_embeds")
+        batch["added_cond_kwargs"] = {}
+        if pooled is not None:
+            batch["added_cond_kwargs"]["text_embeds"] = pooled.to(**kw, non_blocking=True)
+        latents = batch.get("latent_batch")
+        if not hasattr(latents, "to"):
+            raise ValueError("Received invalid value for latents.")
+        batch["latents"] = latents.to(**kw, non_blocking=True).contiguous()
+        # noise, then sigma draw — same order and generators as common.py:5938, 5068
+        noise = torch.randn_like(batch["latents"])
+        bsz = batch["latents"].shape[0]
+        batch["noise"] = noise
+        if c.input_perturbation != 0:
+            raise NotImplementedError("input_perturbation is not part of the B200 step (reference default 0.0)")
+        batch["input_noise"] = noise
+        sigmas, timesteps = sample_flow_sigmas(c, self.noise_schedule, bsz, noise, dev)
+        batch["timesteps"] = timesteps
+        batch["sigmas"] = sigmas.view(-1, 1, 1, 1)  # expand_sigmas, common.py:6825-6828
+        # fused: noisy = (1 - s) x + s eps  AND  2x2 patchify  (common.py:4975-4992, flux/__init__.py:25-30)
+        noisy, packed = ops.flow_prep_pack(batch["latents"], batch["input_noise"], sigmas.float().contiguous(),
+                                           want_unpacked=True)
+        batch["noisy_latents"] = noisy
+        batch["_packed_noisy_latents"] = packed
+        return batch
+
+    # ------------------------------------------------------------------------------------------
+    def _guidance(self, bsz: int, device) -> Optional[torch.Tensor]:
+        if not self._denoiser().config.guidance_embeds:
+            return None
+        c = self.config
+        if c.flux_guidance_mode != "constant":
+            raise NotImplementedError("only flux_guidance_mode='constant' is implemented (reference default)")
+        return torch.full((bsz,), float(c.flux_guidance_value), device=device, dtype=torch.float32)
+
+    def model_predict(self, prepared_batch: Dict[str, Any]) -> Dict[str, Any]:
+        """flux/model.py:707-864.  Returns `model_prediction` in the PACKED token layout plus the
+        metadata needed to unpack; `unpacked_prediction()` materialises the reference's [B,C,H,W]
+        view on demand (the loss kernel consumes the packed layout directly)."""
+        pb = prepared_batch
+        lat = pb["latents"]
+        B, Cc, Hh, Ww = lat.shape
+        dev = self.accelerator.device
+        packed = pb.get("_packed_noisy_latents")
+        if packed is None:
+            from .functional import pack_latents
+            packed = pack_latents(pb["noisy_latents"], B, Cc, Hh, Ww)
+        img_ids = prepare_latent_image_ids(Hh, Ww)
+        txt_ids = torch.zeros(pb["encoder_hidden_states"].shape[1], 3)
+        # side effect kept from the reference: timesteps are overwritten with t / 1000 (flux/model.py:739-745)
+        pb["timesteps"] = pb["timesteps"].to(device=dev, dtype=torch.float32) / self.noise_schedule.config.num_train_timesteps
+        out = self.model(
+            hidden_states=packed, timestep=pb["timesteps"], guidance=self._guidance(B, dev),
+            pooled_projections=pb["added_cond_kwargs"]["text_embeds"], encoder_hidden_states=pb["encoder_hidden_states"],
+            txt_ids=txt_ids, img_ids=img_ids, joint_attention_kwargs=None, return_dict=False,
+        )[0]
+        return {"model_prediction": out, "model_prediction_layout": "packed", "latent_shape": (B, Cc, Hh, Ww),
+                "crepa_hidden_states": None, "hidden_states_buffer": None}
+
+    @staticmethod
+    def unpacked_prediction(model_output: Dict[str, Any]) -> torch.Tensor:
+        from .functional import unpack_latents
+        B, Cc, Hh, Ww = model_output["latent_shape"]
+        return unpack_latents(model_output["model_prediction"], Hh * 8, Ww * 8, 16)
+
+    # ------------------------------------------------------------------------------------------
+    def loss(self, prepared_batch: Dict[str, Any], model_output: Dict[str, Any], apply_conditioning_mask: bool = True):
+        """common.py:6217-6430, flow-matching / l2 branch: target = noise - latents (common.py:4610-4611),
+        mse in fp32, mean over (C,H,W) then over the batch."""
+        c = self.config
+        if c.loss_type != "l2" or c.snr_gamma:
+            raise NotImplementedError("only loss_type='l2' without SNR weighting is implemented (reference defaults)")
+        return FlowLossFn.apply(model_output["model_prediction"], prepared_batch["latents"], prepared_batch["noise"])
+
+    def loss_with_logs(self, prepared_batch, model_output, apply_conditioning_mask: bool = True):
+        return self.loss(prepared_batch, model_output, apply_conditioning_mask), None
+
+
+def prepare_latent_image_ids(height: int, width: int) -> torch.Tensor:
+    """flux/__init__.py:47-61: ids[S_img, 3] = (0, row, col) over the (H/2, W/2) patch grid, float32."""
+    ids = torch.zeros(height // 2, width // 2, 3)
+    ids[..., 1] = ids[..., 1] + torch.arange(height // 2)[:, None]
+    ids[..., 2] = ids[..., 2] + torch.arange(width // 2)[None, :]
+    return ids.reshape(-1, 3).to(torch.float32)

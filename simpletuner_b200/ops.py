@@ -243,6 +243,17 @@ def flow_mse_loss(pred_packed, latents, noise, want_grad: bool = True, grad_scal
     return loss, dpred
 
 
+def gate_mul(x, gate, out=None):
+    """out[b, s, :] = gate[b, :] * x[b, s, :]."""
+    _chk(x, "x"); _chk(gate, "gate")
+    B, S, D = x.shape
+    if out is None:
+        out = torch.empty((B, S, D), device=x.device, dtype=torch.bfloat16)
+    check(_lib.lib().stb_gate_mul(x.data_ptr(), x.stride(0), x.stride(1), gate.data_ptr(), gate.stride(0),
+                                  out.data_ptr(), out.stride(0), out.stride(1), B, S, D, _stream()))
+    return out
+
+
 def skinny_tn(L, Rm, alpha: float = 1.0, out: Optional[torch.Tensor] = None):
     """out[r, n] += alpha * sum_m L[m, r] * Rm[m, n].  L [B,S,R] or [M,R]; Rm [B,S,N] or [M,N]; out fp32."""
     L3, R3 = _as3d(L), _as3d(Rm)

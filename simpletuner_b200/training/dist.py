@@ -1,0 +1,95 @@
+"""Data-parallel metric collectives of the training step (host-side logic over torch.distributed).
+
+Behavioural mirror of reference helpers/data_backend/runtime/context_parallel_sync.py:235-348 for
+the pure data-parallel case the B200 path runs (one process per GPU, NCCL; Gloo in CPU tests):
+ranks may hold different local batch sizes (aspect buckets), so the logged loss is the
+sample-weighted world mean, and per-sample tensors are gathered with padding.
+These run at logging cadence, not inside the timed step (training/step.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass(frozen=True)
+class BatchLayout:
+    local_batch_size: int
+    global_batch_size: int
+    local_batch_offset: int
+    rank: int
+    world_size: int
+    batch_sizes: Tuple[int, ...]
+
+
+def _world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _all_gather_cat(t: torch.Tensor) -> torch.Tensor:
+    _, ws = _world()
+    out = [torch.empty_like(t) for _ in range(ws)]
+    dist.all_gather(out, t)
+    return torch.cat(out, dim=0)
+
+
+def resolve_batch_layout(local_batch_size: int, device=None) -> BatchLayout:
+    """context_parallel_sync.py:235-295 without model-parallel groups: global count and this rank's prefix offset."""
+    local_batch_size = int(local_batch_size)
+    if local_batch_size < 1:
+        raise ValueError("local_batch_size must be greater than 0.")
+    rank, ws = _world()
+    if ws == 1:
+        return BatchLayout(local_batch_size, local_batch_size, 0, 0, 1, (local_batch_size,))
+    count = torch.tensor([local_batch_size], device=device, dtype=torch.long)
+    sizes = tuple(int(v) for v in _all_gather_cat(count).cpu().tolist())
+    return BatchLayout(local_batch_size, sum(sizes), sum(sizes[:rank]), rank, ws, sizes)
+
+
+def gather_sample_weighted_scalar(value: torch.Tensor, local_batch_size: int) -> torch.Tensor:
+    """context_parallel_sync.py:327-348: sum_r(loss_r * n_r) / sum_r(n_r) from one [2] contribution per rank."""
+    local_batch_size = int(local_batch_size)
+    if local_batch_size < 1:
+        raise ValueError("local_batch_size must be greater than 0.")
+    if value.numel() != 1:
+        raise ValueError("Sample-weighted scalar gather requires a scalar tensor.")
+    value = value.detach().float().reshape(())
+    _, ws = _world()
+    if ws == 1:
+        return value
+    n = value.new_tensor(float(local_batch_size))
+    gathered = _all_gather_cat(torch.stack((value * n, n))).reshape(-1, 2)
+    totals = gathered.sum(dim=0)
+    return totals[0] / totals[1]
+
+
+def gather_variable_batch_tensor(tensor: torch.Tensor, layout: Optional[BatchLayout] = None) -> torch.Tensor:
+    """context_parallel_sync.py:298-324: gather per-sample tensors when ranks hold different batch sizes."""
+    if tensor.ndim < 1:
+        raise ValueError("Variable batch tensor gather requires a batch dimension.")
+    if layout is None:
+        layout = resolve_batch_layout(tensor.shape[0], tensor.device)
+    if layout.world_size == 1:
+        return tensor.detach()
+    mx = max(layout.batch_sizes)
+    padded = tensor.detach()
+    if padded.shape[0] < mx:
+        padded = torch.cat((padded, padded.new_zeros((mx - padded.shape[0], *padded.shape[1:]))), dim=0)
+    g = _all_gather_cat(padded).reshape(layout.world_size, mx, *padded.shape[1:])
+    return torch.cat([g[r, :layout.batch_sizes[r]] for r in range(layout.world_size)], dim=0)
+
+
+def device_seed(seed: int, rank: int, seed_for_each_device: bool = True) -> int:
+    """accelerate.utils.set_seed(seed, device_specific=True) as used at trainer.py:2554-2556: rank r seeds with seed + r."""
+    return seed + rank if seed_for_each_device else seed
+
+
+def shard_units(num_units: int, rank: int, world_size: int) -> range:
+    """Contiguous split of independent work units (micro-batches) across ranks for weak-scaling runs."""
+    per = num_units // world_size
+    return range(rank * per, (rank + 1) * per)

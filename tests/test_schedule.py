@@ -1,0 +1,103 @@
+"""CPU: host-side index / schedule logic and the oracle restatements, pinned bit-exactly against
+vectors produced by the reference's OWN source (oracle/make_golden.py -> tests/golden/)."""
+from types import SimpleNamespace
+
+import torch
+
+from oracle import flux_oracle as O
+from simpletuner_b200.flux import functional as FX
+from simpletuner_b200.flux.model import prepare_latent_image_ids
+from simpletuner_b200.training import schedule as S
+
+
+def test_pack_unpack_ids_bit_exact(golden):
+    lat = golden["pack.in"]
+    for mod in (FX, O):
+        assert torch.equal(mod.pack_latents(lat, 2, 16, 8, 12), golden["pack.out"])
+        assert torch.equal(mod.unpack_latents(golden["pack.out"], 64, 96, 16), golden["unpack.out"])
+    assert torch.equal(golden["unpack.out"], lat)  # round trip
+    assert torch.equal(prepare_latent_image_ids(8, 12), golden["ids.out_8x12"])
+    assert torch.equal(O.prepare_latent_image_ids(8, 12), golden["ids.out_8x12"])
+
+
+def test_flow_schedule_shift_bit_exact(golden):
+    sig = golden["shift.in"]
+    c3 = SimpleNamespace(flow_schedule_shift=3.0, flow_schedule_auto_shift=False)
+    c1 = SimpleNamespace(flow_schedule_shift=1.0, flow_schedule_auto_shift=False)
+    assert torch.equal(S.apply_flow_schedule_shift(c3, None, sig.clone(), None), golden["shift.out_s3"])
+    assert torch.equal(S.apply_flow_schedule_shift(c1, None, sig.clone(), None), golden["shift.out_s1"])
+    assert torch.equal(O.apply_flow_schedule_shift(sig.clone(), 3.0), golden["shift.out_s3"])
+    # known answer quoted in SURVEY.md §8c: [0.1, 0.5, 0.9] -> [0.25, 0.75, 0.9643]
+    torch.testing.assert_close(golden["shift.out_s3"][:3], torch.tensor([0.25, 0.75, 0.9643]), atol=1e-4, rtol=0)
+
+
+def test_auto_shift_matches_formula():
+    c = SimpleNamespace(flow_schedule_shift=0.0, flow_schedule_auto_shift=True)
+    sched = SimpleNamespace(config=SimpleNamespace(patch_size=2, base_image_seq_len=256, max_image_seq_len=4096,
+                                                   base_shift=0.5, max_shift=1.15))
+    noise = torch.zeros(1, 16, 128, 128)
+    out = S.apply_flow_schedule_shift(c, sched, torch.tensor([0.5]), noise)
+    import math
+    s = math.exp(1.15)  # seq_len 4096 -> mu = max_shift
+    torch.testing.assert_close(out, torch.tensor([0.5 * s / (1 + (s - 1) * 0.5)]))
+
+
+def test_timestep_weights_bit_exact(golden):
+    for strat, kw in (("none", {}), ("later", {}), ("earlier", {}), ("range", dict(timestep_bias_begin=200, timestep_bias_end=500))):
+        a = SimpleNamespace(timestep_bias_strategy=strat, timestep_bias_portion=0.25, timestep_bias_multiplier=2.0,
+                            timestep_bias_begin=kw.get("timestep_bias_begin", 0), timestep_bias_end=kw.get("timestep_bias_end", 1000))
+        assert torch.equal(S.generate_timestep_weights(a, 1000), golden[f"tsw.{strat}"])
+
+
+def test_segmented_timestep_selection_bit_exact_including_quirk_q1(golden):
+    cfg = SimpleNamespace(refiner_training=False, refiner_training_invert_schedule=False, refiner_training_strength=0.2)
+    for bsz in (2, 4, 7):
+        torch.manual_seed(42)
+        w = torch.ones(1000)
+        sel = S.segmented_timestep_selection(1000, bsz, w, cfg)
+        assert torch.equal(sel, golden[f"segsel.bsz{bsz}"])
+        assert sel.dtype == golden[f"segsel.bsz{bsz}"].dtype
+        # in-place normalisation of the caller's weights (quirk Q1)
+        assert torch.equal(w, golden[f"segsel.bsz{bsz}.weights_after"])
+    assert golden["segsel.bsz4"].tolist() == [960, 545, 311, 69]
+    # range property pinned by reference tests/test_custom_schedules.py:59-107
+    rcfg = SimpleNamespace(refiner_training=True, refiner_training_invert_schedule=True, refiner_training_strength=0.35)
+    sel = S.segmented_timestep_selection(1000, 4, torch.ones(1000), rcfg)
+    assert all(350 <= int(t) <= 999 for t in sel)
+    rcfg = SimpleNamespace(refiner_training=True, refiner_training_invert_schedule=False, refiner_training_strength=0.35)
+    sel = S.segmented_timestep_selection(1000, 4, torch.ones(1000), rcfg)
+    assert all(0 <= int(t) < 350 for t in sel)
+
+
+def test_sample_flow_sigmas_bit_exact(golden):
+    c = SimpleNamespace(flow_schedule_shift=3.0, flow_schedule_auto_shift=False, flow_sigmoid_scale=1.0)
+    torch.manual_seed(42)
+    sig, ts = S.sample_flow_sigmas(c, None, 4, torch.zeros(4, 16, 8, 8), "cpu")
+    assert torch.equal(sig, golden["sample_sigmas.seed42.sigmas"])
+    assert torch.equal(ts, golden["sample_sigmas.seed42.timesteps"])
+    torch.manual_seed(42)
+    sig2, _ = O.sample_flow_sigmas(4)
+    assert torch.equal(sig2, golden["sample_sigmas.seed42.sigmas"])
+
+
+def test_oracle_noisy_latents_and_target_bit_exact(golden):
+    assert golden["noisy.known_answer"].item() == 3.0  # reference tests/test_mixflow.py:76-87
+    for tag in ("f32", "bf16"):
+        lat, eps, sg = golden[f"noisy.{tag}.latents"], golden[f"noisy.{tag}.noise"], golden[f"noisy.{tag}.sigmas"]
+        assert torch.equal(O.flow_noisy_latents(lat, eps, sg), golden[f"noisy.{tag}.out"])
+        assert torch.equal(O.flow_target(lat, eps), golden[f"target.{tag}.out"])
+
+
+def test_oracle_rope_application_bit_exact(golden):
+    x, cos, sin = golden["rope.x"], golden["rope.cos"], golden["rope.sin"]
+    assert torch.equal(O.apply_rope(x, cos, sin), golden["rope.out"])
+    assert torch.equal(O.apply_rope(x.bfloat16(), cos, sin), golden["rope.out_bf16"])
+
+
+def test_rope_tables_product_equals_oracle():
+    from simpletuner_b200.flux.transformer import rope_tables
+    ids = torch.cat([torch.zeros(5, 3), O.prepare_latent_image_ids(8, 12)], 0)
+    c1, s1 = rope_tables(ids, (16, 56, 56))
+    c2, s2 = O.rope_tables(ids, (16, 56, 56))
+    assert torch.equal(c1, c2) and torch.equal(s1, s2)
+    assert torch.all(c1[:5] == 1) and torch.all(s1[:5] == 0)  # text tokens: identity rotation (quirk Q9)
