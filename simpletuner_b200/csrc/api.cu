@@ -17,6 +17,7 @@
 #include "attn_fwd.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "wgrad.cuh"
 
 namespace {
 
@@ -517,6 +518,54 @@ int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, l
   if (int r = check_device()) return r;
   if (N & 1) return fail(STB_ERR_ARG, "N must be even");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // tensor-core path: both operands TMA-able (16-byte aligned rows), rank block <= 64
+  if (R % 8 == 0 && R <= 64 && N % 8 == 0 && aligned16(L) && aligned16(Rm) && !(l_s & 7) && !(r_s & 7) &&
+      (B == 1 || (!(l_b & 7) && !(r_b & 7)))) {
+    stb::WgradMaps maps;
+    unsigned bx[3] = {64, 64, 1};
+    {
+      unsigned long long d[3] = {(unsigned long long)N, (unsigned long long)S, (unsigned long long)B};
+      unsigned long long sb[2] = {(unsigned long long)r_s * 2ull, (unsigned long long)(B == 1 ? r_s * (long long)S : r_b) * 2ull};
+      if (int r = make_map(&maps.rm, Rm, 3, d, sb, bx)) return r;
+    }
+    {
+      unsigned long long d[3] = {(unsigned long long)R, (unsigned long long)S, (unsigned long long)B};
+      unsigned long long sb[2] = {(unsigned long long)l_s * 2ull, (unsigned long long)(B == 1 ? l_s * (long long)S : l_b) * 2ull};
+      if (int r = make_map(&maps.l, L, 3, d, sb, bx)) return r;
+    }
+    stb::WgradParams p;
+    p.S = S; p.B = B; p.N = N; p.R = R;
+    p.alpha = alpha;
+    p.out = out;
+    const int n_tiles = (N + 127) / 128;
+    int spb = std::max(1, (2 * num_sms()) / std::max(1, n_tiles * B));     // ~2 CTAs' worth of work per SM
+    int rows = ((S + spb - 1) / spb + 63) / 64 * 64;
+    spb = (S + rows - 1) / rows;
+    p.rows_per_split = rows;
+    p.splits_per_batch = spb;
+    constexpr int SMEM = 6 * 24576 + 1024 + 256;
+    dim3 grid(n_tiles, spb * B);
+    const int rp = (R + 15) / 16 * 16;
+#define STB_WG(RPV)                                                          \
+  {                                                                          \
+    auto kern = stb::wgrad_tn_kernel<RPV>;                                   \
+    static bool configured = false;                                          \
+    if (!configured) {                                                       \
+      if (int r = set_smem(kern, SMEM)) return r;                            \
+      configured = true;                                                     \
+    }                                                                        \
+    kern<<<grid, 256, SMEM, st>>>(maps, p);                                  \
+  }
+    switch (rp) {
+      case 16: STB_WG(16) break;
+      case 32: STB_WG(32) break;
+      case 48: STB_WG(48) break;
+      default: STB_WG(64) break;
+    }
+#undef STB_WG
+    STB_LAUNCH_CHECK("wgrad_tn");
+    return 0;
+  }
   const long long M = (long long)B * S;
   const int col_blocks = (N / 2 + 255) / 256;
   // enough row chunks to fill the machine ~4x

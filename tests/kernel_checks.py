@@ -332,4 +332,7 @@ CHECKS = {
     "flow": lambda: check_flow(),
     "skinny": lambda: check_skinny(),
     "skinny_r48": lambda: check_skinny(R=48, N=4096),
+    "skinny_flux": lambda: check_skinny(B=4, S=4608, R=48, N=9216),
+    "skinny_ragged": lambda: check_skinny(B=3, S=333, R=16, N=200),
+    "skinny_cuda_core_path": lambda: check_skinny(B=2, S=100, R=16, N=250),
 }
