@@ -352,17 +352,21 @@ int stb_attn_bwd(const stb_attn_bwd_args* a, void* stream) {
     return fail(STB_ERR_ARG, "dq/dk/dv must be 16-byte aligned with strides multiple of 8 elements");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   stb::AttnBwdMaps maps;
-  auto mk = [&](CUtensorMap* m, const void* ptr, long long sb, long long ss, long long sh, int S) {
+  auto mk = [&](CUtensorMap* m, const void* ptr, long long sb, long long ss, long long sh, int S, unsigned rows) {
     unsigned long long d[4] = {(unsigned long long)a->HD, (unsigned long long)a->H, (unsigned long long)S,
                                (unsigned long long)a->B};
     unsigned long long s[3] = {(unsigned long long)sh * 2ull, (unsigned long long)ss * 2ull, (unsigned long long)sb * 2ull};
-    unsigned bx[4] = {64, 1, 128, 1};
+    unsigned bx[4] = {64, 1, rows, 1};
     return make_map(m, ptr, 4, d, s, bx);
   };
-  if (int r = mk(&maps.q, a->q, a->q_b, a->q_s, a->q_h, a->Sq)) return r;
-  if (int r = mk(&maps.k, a->k, a->k_b, a->k_s, a->k_h, a->Sk)) return r;
-  if (int r = mk(&maps.v, a->v, a->v_b, a->v_s, a->v_h, a->Sk)) return r;
-  if (int r = mk(&maps.d_o, a->d_o, a->do_b, a->do_s, a->do_h, a->Sq)) return r;
+  if (int r = mk(&maps.q128, a->q, a->q_b, a->q_s, a->q_h, a->Sq, 128)) return r;
+  if (int r = mk(&maps.k128, a->k, a->k_b, a->k_s, a->k_h, a->Sk, 128)) return r;
+  if (int r = mk(&maps.v128, a->v, a->v_b, a->v_s, a->v_h, a->Sk, 128)) return r;
+  if (int r = mk(&maps.do128, a->d_o, a->do_b, a->do_s, a->do_h, a->Sq, 128)) return r;
+  if (int r = mk(&maps.q64, a->q, a->q_b, a->q_s, a->q_h, a->Sq, 64)) return r;
+  if (int r = mk(&maps.k64, a->k, a->k_b, a->k_s, a->k_h, a->Sk, 64)) return r;
+  if (int r = mk(&maps.v64, a->v, a->v_b, a->v_s, a->v_h, a->Sk, 64)) return r;
+  if (int r = mk(&maps.do64, a->d_o, a->do_b, a->do_s, a->do_h, a->Sq, 64)) return r;
   stb::AttnBwdParams p;
   p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk;
   p.scale = a->scale;

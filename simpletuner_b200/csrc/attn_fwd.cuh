@@ -108,77 +108,92 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdMaps maps, const AttnFwdParams p)
   auto S_col = [&](int t) { return tmem_base + uint32_t(t * 128); };
   auto O_col = [&](int t) { return tmem_base + uint32_t(256 + t * 128); };
 
+  // Producer / MMA warps run their loops warp-uniformly; only the issuing instructions are executed by
+  // one elected lane, so descriptors live in uniform registers and UTCHMMA / UTMALDG issue back to back.
   if (warp == 8) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * TILE);
       for (int t = 0; t < 2; ++t)
         for (int a = 0; a < ATOMS; ++a)
           tma_load_4d(q_smem + t * TILE + a * ATOM_BYTES, &maps.q, q_full, a * 64, h, q0 + t * 128, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int stg = j % NSTG;
-        const uint32_t par = ((j / NSTG) & 1) ^ 1u;
-        mbar_wait(k_empty(stg), par, 10);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int stg = j % NSTG;
+      const uint32_t par = ((j / NSTG) & 1) ^ 1u;
+      mbar_wait(k_empty(stg), par, 10);
+      if (elect_one()) {
         mbar_arrive_expect_tx(k_full(stg), TILE);
         for (int a = 0; a < ATOMS; ++a)
           tma_load_4d(k_smem + stg * TILE + a * ATOM_BYTES, &maps.k, k_full(stg), a * 64, h, j * 128, b);
-        mbar_wait(v_empty(stg), par, 11);
+      }
+      __syncwarp();
+      mbar_wait(v_empty(stg), par, 11);
+      if (elect_one()) {
         mbar_arrive_expect_tx(v_full(stg), TILE);
         for (int a = 0; a < ATOMS; ++a)
           tma_load_4d(v_smem + stg * TILE + a * ATOM_BYTES, &maps.v, v_full(stg), a * 64, h, j * 128, b);
       }
+      __syncwarp();
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);   // P (TMEM)    x V (MN-major)
-      auto issue_S = [&](int t, int stg) {
-        const uint32_t qa = q_smem + t * TILE;
-        const uint32_t ka = k_smem + stg * TILE;
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // Q (K-major) x K (K-major)
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);   // P (TMEM)    x V (MN-major)
+    auto issue_S = [&](int t, int stg) {
+      const uint32_t qa = q_smem + t * TILE;
+      const uint32_t ka = k_smem + stg * TILE;
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint64_t ad = sdesc_kmajor(qa + (kk / 4) * ATOM_BYTES, (kk % 4) * 16);
-          const uint64_t bd = sdesc_kmajor(ka + (kk / 4) * ATOM_BYTES, (kk % 4) * 16);
-          mma_ss(S_col(t), ad, bd, idesc_s, kk > 0);
-        }
-      };
-      auto issue_PV = [&](int t, int stg, bool acc) {
-        const uint32_t va = v_smem + stg * TILE;
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        const uint64_t ad = sdesc_k(qa, (kk / 4) * ATOM_BYTES + (kk % 4) * 32);
+        const uint64_t bd = sdesc_k(ka, (kk / 4) * ATOM_BYTES + (kk % 4) * 32);
+        mma_ss(S_col(t), ad, bd, idesc_s, kk > 0);
+      }
+    };
+    auto issue_PV = [&](int t, int stg, bool acc) {
+      const uint32_t va = v_smem + stg * TILE;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {  // 128 keys / 16
-          const uint64_t bd = sdesc_mnmajor(va, kk * 16, ATOM_BYTES);
-          mma_ts(O_col(t), S_col(t) + kk * 8, bd, idesc_o, (acc || kk > 0) ? 1u : 0u);
-        }
-      };
-      mbar_wait(q_full, 0, 20);
-      mbar_wait(k_full(0), 0, 21);
-      tc_fence_after();
+      for (int kk = 0; kk < 8; ++kk) {  // 128 keys / 16
+        const uint64_t bd = sdesc_mn(va, kk * 2048, ATOM_BYTES);
+        mma_ts(O_col(t), S_col(t) + kk * 8, bd, idesc_o, (acc || kk > 0) ? 1u : 0u);
+      }
+    };
+    mbar_wait(q_full, 0, 20);
+    mbar_wait(k_full(0), 0, 21);
+    tc_fence_after();
+    if (elect_one()) {
       issue_S(0, 0);
       tc_commit(s_full(0));
       issue_S(1, 0);
       tc_commit(s_full(1));
       tc_commit(k_empty(0));
-      for (int j = 0; j < n_kv; ++j) {
-        const int stg = j % NSTG;
-        const uint32_t par = (j / NSTG) & 1;
-        const int stg_n = (j + 1) % NSTG;
-        const uint32_t par_n = ((j + 1) / NSTG) & 1;
-        const bool more = (j + 1 < n_kv);
-        mbar_wait(v_full(stg), par, 22);
-        if (more) mbar_wait(k_full(stg_n), par_n, 23);
-        // ---- tile A
-        mbar_wait(p_full(0), j & 1, 24);
-        tc_fence_after();
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int stg = j % NSTG;
+      const uint32_t par = (j / NSTG) & 1;
+      const int stg_n = (j + 1) % NSTG;
+      const uint32_t par_n = ((j + 1) / NSTG) & 1;
+      const bool more = (j + 1 < n_kv);
+      mbar_wait(v_full(stg), par, 22);
+      if (more) mbar_wait(k_full(stg_n), par_n, 23);
+      // ---- tile A
+      mbar_wait(p_full(0), j & 1, 24);
+      tc_fence_after();
+      if (elect_one()) {
         issue_PV(0, stg, j > 0);
         tc_commit(o_done(0));
         if (more) {
           issue_S(0, stg_n);
           tc_commit(s_full(0));
         }
-        // ---- tile B
-        mbar_wait(p_full(1), j & 1, 25);
-        tc_fence_after();
+      }
+      __syncwarp();
+      // ---- tile B
+      mbar_wait(p_full(1), j & 1, 25);
+      tc_fence_after();
+      if (elect_one()) {
         issue_PV(1, stg, j > 0);
         tc_commit(o_done(1));
         tc_commit(v_empty(stg));
@@ -188,6 +203,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdMaps maps, const AttnFwdParams p)
           tc_commit(k_empty(stg_n));
         }
       }
+      __syncwarp();
     }
   } else if (warp < 8) {
     // ===================== softmax warpgroups =====================
@@ -204,20 +220,28 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdMaps maps, const AttnFwdParams p)
       mbar_wait(s_full(t), j & 1, 30);
       tc_fence_after();
       const int kv_valid = p.Sk - j * 128;  // >= 1; < 128 only on the last, ragged tile
-      // ---- pass 1: row max
-      float m_tile = -INFINITY;
-#pragma unroll 1
+      const bool ragged = kv_valid < 128;   // CTA-uniform: only the last, ragged key tile pays for masking
+      // ---- pass 1: row max (TMEM read #1; 4 independent max chains)
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
       for (int c = 0; c < 128; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(s_t + c, v);
         tc_wait_ld();
+        if (ragged) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(v[i]);
-          if (c + i >= kv_valid) x = -INFINITY;
-          m_tile = fmaxf(m_tile, x);
+          for (int i = 0; i < 32; ++i)
+            if (c + i >= kv_valid) v[i] = 0xff800000u;  // -inf
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          m0 = fmaxf(m0, __uint_as_float(v[i]));
+          m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+          m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
         }
       }
+      const float m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       // ---- lazy rescale decision (warp-uniform, tcgen05.ld/st are warp-collective)
       const bool need = (m_tile - m_used) * sl2 > 8.0f;  // true on the first tile (m_used = -inf)
       if (__any_sync(0xffffffffu, need)) {
@@ -240,26 +264,31 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdMaps maps, const AttnFwdParams p)
           tc_wait_st();
         }
       }
-      // ---- pass 2: P = exp2(s*sl2 - m*sl2) -> bf16, in place over S
+      // ---- pass 2: P = exp2(s*sl2 - m*sl2) -> bf16, in place over S (TMEM read #2)
       const float mb = m_used * sl2;
-      float lsum = 0.f;
-#pragma unroll 1
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
       for (int c = 0; c < 128; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(s_t + c, v);
         tc_wait_ld();
+        if (ragged) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i >= kv_valid) v[i] = 0xff800000u;  // exp2(-inf) = 0
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float x0 = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mb));
-          float x1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -mb));
-          if (c + i >= kv_valid) x0 = 0.f;
-          if (c + i + 1 >= kv_valid) x1 = 0.f;
-          lsum += x0 + x1;
+          const float x0 = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mb));
+          const float x1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -mb));
+          l0 += x0;
+          l1 += x1;
           pk[i / 2] = pack_bf16x2(x0, x1);
         }
         tmem_st_32x32b_x16(s_t + c / 2, pk);
       }
+      const float lsum = l0 + l1;
       l += lsum;
       tc_wait_st();
       tc_fence_before();

@@ -135,8 +135,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -149,11 +149,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
           for (int kb = 0; kb < p.kblocks[seg]; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u, 1);
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-            mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              tma_load_3d(sa + mt * Cfg::A_BYTES, &maps.a[seg], full_bar(stage), kb * 64, s0 + mt * 128, b);
-            tma_load_2d(sa + MT * Cfg::A_BYTES, &maps.w[seg], full_bar(stage), kb * 64, n0);
+              for (int mt = 0; mt < MT; ++mt)
+                tma_load_3d(sa + mt * Cfg::A_BYTES, &maps.a[seg], full_bar(stage), kb * 64, s0 + mt * 128, b);
+              tma_load_2d(sa + MT * Cfg::A_BYTES, &maps.w[seg], full_bar(stage), kb * 64, n0);
+            }
+            __syncwarp();
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -163,8 +166,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -182,23 +185,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
             const uint32_t sw = sa + MT * Cfg::A_BYTES;
             const int nk = (kb == p.kblocks[seg] - 1) ? p.kmmas_last[seg] : 4;
-            for (int kk = 0; kk < nk; ++kk) {
-              const uint64_t bdesc = sdesc_kmajor(sw, kk * 16);
+            if (elect_one()) {
+              for (int kk = 0; kk < nk; ++kk) {
+                const uint64_t bdesc = sdesc_k(sw, kk * 32);
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                const uint64_t adesc = sdesc_kmajor(sa + mt * Cfg::A_BYTES, kk * 16);
-                mma_ss(d_base + mt * BN, adesc, bdesc, idesc, accumulate);
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint64_t adesc = sdesc_k(sa, mt * Cfg::A_BYTES + kk * 32);
+                  mma_ss(d_base + mt * BN, adesc, bdesc, idesc, accumulate);
+                }
+                accumulate = 1;
               }
-              accumulate = 1;
+              tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
             }
-            tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+            __syncwarp();
+            accumulate = 1;
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
             }
           }
         }
-        tc_commit(accf_bar(acc));  // accumulator complete -> epilogue
+        if (elect_one()) tc_commit(accf_bar(acc));  // accumulator complete -> epilogue
+        __syncwarp();
         if (++acc == ACC_STAGES) {
           acc = 0;
           acc_phase ^= 1u;

@@ -76,17 +76,20 @@ wgrad_tn_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u, 60);
         const uint32_t sa = smem_base + stage * STAGE_BYTES;
-        mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
         const int s = s_begin + kb * 64;
-        tma_load_3d(sa, &maps.rm, full_bar(stage), n0, s, b);
-        tma_load_3d(sa + 8192, &maps.rm, full_bar(stage), n0 + 64, s, b);
-        tma_load_3d(sa + A_BYTES, &maps.l, full_bar(stage), 0, s, b);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_3d(sa, &maps.rm, full_bar(stage), n0, s, b);
+          tma_load_3d(sa + 8192, &maps.rm, full_bar(stage), n0 + 64, s, b);
+          tma_load_3d(sa + A_BYTES, &maps.l, full_bar(stage), 0, s, b);
+        }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
@@ -94,7 +97,7 @@ wgrad_tn_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, RP, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
@@ -108,19 +111,24 @@ wgrad_tn_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         // >= S are zero-filled by TMA.
         const int rows_here = min(64, s_end - (s_begin + kb * 64));
         const int nk = (rows_here + 15) / 16;
-        for (int kk = 0; kk < nk; ++kk) {
-          const uint64_t ad = sdesc_mnmajor(sa, kk * 16, 8192);
-          const uint64_t bd = sdesc_mnmajor(sa + A_BYTES, kk * 16, 8192);
-          mma_ss(tmem_base, ad, bd, idesc, accumulate);
-          accumulate = 1;
+        if (elect_one()) {
+          for (int kk = 0; kk < nk; ++kk) {
+            const uint64_t ad = sdesc_mn(sa, kk * 2048, 8192);
+            const uint64_t bd = sdesc_mn(sa, A_BYTES + kk * 2048, 8192);
+            mma_ss(tmem_base, ad, bd, idesc, accumulate);
+            accumulate = 1;
+          }
+          tc_commit(empty_bar(stage));
         }
-        tc_commit(empty_bar(stage));
+        __syncwarp();
+        accumulate = 1;
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      tc_commit(acc_bar);
+      if (elect_one()) tc_commit(acc_bar);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
