@@ -283,8 +283,15 @@ int stb_gemm_bf16(const stb_gemm_args* a, void* stream) {
   }
   if (mt == 0) {
     // 256-row CTA tiles halve the per-FLOP L2->SMEM traffic; use them once there are >= 2 waves of them
+    // ... but the persistent grid pays for a partial last wave: pick the variant with the better wave fill
+    // (measured: both variants run the mainloop at about the same rate, profiles/r01).
+    auto fill = [&](int m) {
+      const long long t = (long long)((a->rows_per_batch + 128 * m - 1) / (128 * m)) * a->num_batches * ((a->N + bn - 1) / bn);
+      const long long waves = (t + num_sms() - 1) / num_sms();
+      return double(t) / double(waves * num_sms());
+    };
     const long long t2 = (long long)((a->rows_per_batch + 255) / 256) * a->num_batches * ((a->N + bn - 1) / bn);
-    mt = (bn >= 128 && t2 >= 2ll * num_sms()) ? 2 : 1;
+    mt = (bn >= 128 && t2 >= 2ll * num_sms() && fill(2) >= 0.98 * fill(1)) ? 2 : 1;
   }
   if (mt == 1 && bn == 256) return launch_gemm<1, 256>(a, st);
   if (mt == 2 && bn == 256) return launch_gemm<2, 256>(a, st);
@@ -448,7 +455,7 @@ int stb_qk_rmsnorm_rope_fwd(const void* src, long long src_b, long long src_s, i
   if (HD != 128 && HD != 64) return fail(STB_ERR_UNSUPPORTED, "head_dim %d not supported", HD);
   if ((src_s & 3) || (src_b & 3) || (k_off & 3) || (dst_s & 3) || (dst_b & 3)) return fail(STB_ERR_ARG, "qk_rmsnorm_rope alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long warps = (long long)B * S * H * 2;
+  const long long warps = (long long)B * S;  // one warp per token
   const unsigned grid = (unsigned)((warps + 7) / 8);
   auto SRC = static_cast<const __nv_bfloat16*>(src);
   auto cast = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
@@ -468,7 +475,7 @@ int stb_qk_rmsnorm_rope_bwd(const void* dq, const void* dk, long long d_b, long 
   if (int r = check_device()) return r;
   if (HD != 128 && HD != 64) return fail(STB_ERR_UNSUPPORTED, "head_dim %d not supported", HD);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long warps = (long long)B * S * H * 2;
+  const long long warps = (long long)B * S;  // one warp per token
   const unsigned grid = (unsigned)((warps + 7) / 8);
   auto cast = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
   if (HD == 128)

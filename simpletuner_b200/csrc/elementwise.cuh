@@ -191,9 +191,33 @@ ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_b, lon
 // src: projection output, token-major [B, S, *] with q at column offset 0 and k at `k_off`
 //      (fused QKV buffer) — per (token, head) a contiguous HD vector at head stride HD.
 // dst: q_out / k_out [B, S, H, HD] (same strides for both).
-// One warp per (token, head); lane owns HD/32 consecutive elements (RoPE pairs stay in-lane).
-// Rows s < s_split use the "added" (text stream) norm weights wq1/wk1, the rest wq0/wk0.
+// One warp per TOKEN: the token's cos/sin row and the four norm-weight slices are loaded once into
+// registers and reused for all 2*H (q|k, head) rows, which are processed 4 at a time for ILP; lane owns
+// HD/32 consecutive elements (RoPE pairs stay in-lane).  Rows s < s_split use the "added" (text
+// stream) norm weights wq1/wk1, the rest wq0/wk0.
 // ------------------------------------------------------------------------------------------------
+template <int EPL>
+__device__ __forceinline__ void ld_row(const __nv_bfloat16* p, float (&x)[EPL]) {
+  if constexpr (EPL == 4) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    x[0] = bf16_lo(u.x); x[1] = bf16_hi(u.x); x[2] = bf16_lo(u.y); x[3] = bf16_hi(u.y);
+  } else {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+    x[0] = bf16_lo(u); x[1] = bf16_hi(u);
+  }
+}
+template <int EPL>
+__device__ __forceinline__ void st_row(__nv_bfloat16* p, const float (&o)[EPL]) {
+  if constexpr (EPL == 4) {
+    uint2 u;
+    u.x = pack_bf16x2(o[0], o[1]);
+    u.y = pack_bf16x2(o[2], o[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+  } else {
+    *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(o[0], o[1]);
+  }
+}
+
 template <int HD>
 __global__ void __launch_bounds__(256)
 qk_rmsnorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ src, long long src_b, long long src_s,
@@ -204,58 +228,71 @@ qk_rmsnorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ src, long long src_
                            __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ k_out,
                            long long dst_b, long long dst_s, int B, int S, int H, float eps) {
   constexpr int EPL = HD / 32;
-  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const long long total = (long long)B * S * H * 2;
-  if (wid >= total) return;
+  constexpr int U = 4;  // rows in flight per warp
+  const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= (long long)B * S) return;
   const int lane = threadIdx.x & 31;
-  const int which = int(wid & 1);  // 0 = q, 1 = k
-  long long rem = wid >> 1;
-  const int h = int(rem % H);
-  rem /= H;
-  const int s = int(rem % S);
-  const int b = int(rem / S);
-  const __nv_bfloat16* in = src + b * src_b + s * src_s + (which ? k_off : 0) + h * HD + lane * EPL;
-  const __nv_bfloat16* w = (s < s_split) ? (which ? wk1 : wq1) : (which ? wk0 : wq0);
-  float x[EPL];
-  if constexpr (EPL == 4) {
-    uint2 u = *reinterpret_cast<const uint2*>(in);
-    x[0] = bf16_lo(u.x); x[1] = bf16_hi(u.x); x[2] = bf16_lo(u.y); x[3] = bf16_hi(u.y);
-  } else {
-    uint32_t u = *reinterpret_cast<const uint32_t*>(in);
-    x[0] = bf16_lo(u); x[1] = bf16_hi(u);
-  }
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < EPL; ++i) ss += x[i] * x[i];
-  ss = warp_sum(ss);
-  const float rstd = rsqrtf(ss / HD + eps);
-  float y[EPL];
+  const int s = int(tok % S);
+  const int b = int(tok / S);
+  const bool txt = s < s_split;
+  const __nv_bfloat16* wq = txt ? wq1 : wq0;
+  const __nv_bfloat16* wk = txt ? wk1 : wk0;
+  float wqv[EPL], wkv[EPL], cs[EPL], sn[EPL];
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
-    float n = bf16r(x[i] * rstd);
-    y[i] = w ? bf16r(n * __bfloat162float(w[lane * EPL + i])) : n;
+    wqv[i] = wq ? __bfloat162float(wq[lane * EPL + i]) : 1.f;
+    wkv[i] = wk ? __bfloat162float(wk[lane * EPL + i]) : 1.f;
+    cs[i] = cosT ? cosT[(long long)s * HD + lane * EPL + i] : 1.f;
+    sn[i] = sinT ? sinT[(long long)s * HD + lane * EPL + i] : 0.f;
   }
-  float o[EPL];
-  if (cosT) {
-    const float* cr = cosT + (long long)s * HD + lane * EPL;
-    const float* sr = sinT + (long long)s * HD + lane * EPL;
+  const __nv_bfloat16* in_tok = src + b * src_b + s * src_s + lane * EPL;
+  const long long out_tok = b * dst_b + s * dst_s + lane * EPL;
+  const int rows = 2 * H;  // row r: which = r / H (0 = q, 1 = k), head = r % H
+  for (int r0 = 0; r0 < rows; r0 += U) {
+    float x[U][EPL];
 #pragma unroll
-    for (int i = 0; i < EPL; i += 2) {
-      o[i] = y[i] * cr[i] + (-y[i + 1]) * sr[i];
-      o[i + 1] = y[i + 1] * cr[i + 1] + y[i] * sr[i + 1];
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + u;
+      if (r < rows) {
+        const int which = r >= H, hh = which ? r - H : r;
+        ld_row<EPL>(in_tok + (which ? k_off : 0) + hh * HD, x[u]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) x[u][i] = 0.f;
+      }
     }
-  } else {
+    float ss[U];
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) o[i] = y[i];
-  }
-  __nv_bfloat16* out = (which ? k_out : q_out) + b * dst_b + s * dst_s + h * HD + lane * EPL;
-  if constexpr (EPL == 4) {
-    uint2 u;
-    u.x = pack_bf16x2(o[0], o[1]);
-    u.y = pack_bf16x2(o[2], o[3]);
-    *reinterpret_cast<uint2*>(out) = u;
-  } else {
-    *reinterpret_cast<uint32_t*>(out) = pack_bf16x2(o[0], o[1]);
+    for (int u = 0; u < U; ++u) {
+      ss[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) ss[u] += x[u][i] * x[u][i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + u;
+      if (r >= rows) continue;
+      const int which = r >= H, hh = which ? r - H : r;
+      const float rstd = rsqrtf(ss[u] / HD + eps);
+      const bool has_w = which ? (wk != nullptr) : (wq != nullptr);
+      float y[EPL], o[EPL];
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const float n = bf16r(x[u][i] * rstd);  // fp32 normalise, cast to the weight dtype ...
+        y[i] = has_w ? bf16r(n * (which ? wkv[i] : wqv[i])) : n;  // ... then * weight (bf16 tensor op)
+      }
+#pragma unroll
+      for (int i = 0; i < EPL; i += 2) {
+        o[i] = y[i] * cs[i] + (-y[i + 1]) * sn[i];
+        o[i + 1] = y[i + 1] * cs[i + 1] + y[i] * sn[i + 1];
+      }
+      st_row<EPL>((which ? k_out : q_out) + out_tok + hh * HD, o);
+    }
   }
 }
 
@@ -273,71 +310,81 @@ qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bflo
                            __nv_bfloat16* __restrict__ dsrc, long long ds_b, long long ds_s, int B, int S,
                            int H, float eps) {
   constexpr int EPL = HD / 32;
-  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const long long total = (long long)B * S * H * 2;
-  if (wid >= total) return;
+  constexpr int U = 4;
+  const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= (long long)B * S) return;
   const int lane = threadIdx.x & 31;
-  const int which = int(wid & 1);
-  long long rem = wid >> 1;
-  const int h = int(rem % H);
-  rem /= H;
-  const int s = int(rem % S);
-  const int b = int(rem / S);
-  const long long col = (which ? k_off : 0) + h * HD + lane * EPL;
-  const __nv_bfloat16* in = src + b * src_b + s * src_s + col;
-  const __nv_bfloat16* gin = (which ? dk : dq) + b * d_b + s * d_s + h * HD + lane * EPL;
-  const __nv_bfloat16* w = (s < s_split) ? (which ? wk1 : wq1) : (which ? wk0 : wq0);
-  float x[EPL], go[EPL];
-  if constexpr (EPL == 4) {
-    uint2 u = *reinterpret_cast<const uint2*>(in);
-    x[0] = bf16_lo(u.x); x[1] = bf16_hi(u.x); x[2] = bf16_lo(u.y); x[3] = bf16_hi(u.y);
-    uint2 g = *reinterpret_cast<const uint2*>(gin);
-    go[0] = bf16_lo(g.x); go[1] = bf16_hi(g.x); go[2] = bf16_lo(g.y); go[3] = bf16_hi(g.y);
-  } else {
-    uint32_t u = *reinterpret_cast<const uint32_t*>(in);
-    x[0] = bf16_lo(u); x[1] = bf16_hi(u);
-    uint32_t g = *reinterpret_cast<const uint32_t*>(gin);
-    go[0] = bf16_lo(g); go[1] = bf16_hi(g);
-  }
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < EPL; ++i) ss += x[i] * x[i];
-  ss = warp_sum(ss);
-  const float rstd = rsqrtf(ss / HD + eps);
-  float dy[EPL];
-  if (cosT) {
-    const float* cr = cosT + (long long)s * HD + lane * EPL;
-    const float* sr = sinT + (long long)s * HD + lane * EPL;
-#pragma unroll
-    for (int i = 0; i < EPL; i += 2) {
-      // o[i] = y[i] c[i] - y[i+1] s[i];  o[i+1] = y[i+1] c[i+1] + y[i] s[i+1]
-      dy[i] = go[i] * cr[i] + go[i + 1] * sr[i + 1];
-      dy[i + 1] = go[i + 1] * cr[i + 1] - go[i] * sr[i];
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) dy[i] = go[i];
-  }
-  float g[EPL], xh[EPL];
-  float sgx = 0.f;
+  const int s = int(tok % S);
+  const int b = int(tok / S);
+  const bool txt = s < s_split;
+  const __nv_bfloat16* wq = txt ? wq1 : wq0;
+  const __nv_bfloat16* wk = txt ? wk1 : wk0;
+  float wqv[EPL], wkv[EPL], cs[EPL], sn[EPL];
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
-    g[i] = w ? dy[i] * __bfloat162float(w[lane * EPL + i]) : dy[i];
-    xh[i] = x[i] * rstd;
-    sgx += g[i] * xh[i];
+    wqv[i] = wq ? __bfloat162float(wq[lane * EPL + i]) : 1.f;
+    wkv[i] = wk ? __bfloat162float(wk[lane * EPL + i]) : 1.f;
+    cs[i] = cosT ? cosT[(long long)s * HD + lane * EPL + i] : 1.f;
+    sn[i] = sinT ? sinT[(long long)s * HD + lane * EPL + i] : 0.f;
   }
-  sgx = warp_sum(sgx) / HD;
-  float o[EPL];
+  const __nv_bfloat16* in_tok = src + b * src_b + s * src_s + lane * EPL;
+  __nv_bfloat16* out_tok = dsrc + b * ds_b + s * ds_s + lane * EPL;
+  const long long g_tok = b * d_b + s * d_s + lane * EPL;
+  const int rows = 2 * H;
+  for (int r0 = 0; r0 < rows; r0 += U) {
+    float x[U][EPL], go[U][EPL];
 #pragma unroll
-  for (int i = 0; i < EPL; ++i) o[i] = rstd * (g[i] - xh[i] * sgx);
-  __nv_bfloat16* out = dsrc + b * ds_b + s * ds_s + col;
-  if constexpr (EPL == 4) {
-    uint2 u;
-    u.x = pack_bf16x2(o[0], o[1]);
-    u.y = pack_bf16x2(o[2], o[3]);
-    *reinterpret_cast<uint2*>(out) = u;
-  } else {
-    *reinterpret_cast<uint32_t*>(out) = pack_bf16x2(o[0], o[1]);
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + u;
+      if (r < rows) {
+        const int which = r >= H, hh = which ? r - H : r;
+        ld_row<EPL>(in_tok + (which ? k_off : 0) + hh * HD, x[u]);
+        ld_row<EPL>((which ? dk : dq) + g_tok + hh * HD, go[u]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) x[u][i] = 0.f, go[u][i] = 0.f;
+      }
+    }
+    float ss[U], sgx[U], g[U][EPL];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int which = (r0 + u) >= H;
+      ss[u] = 0.f;
+      sgx[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPL; i += 2) {
+        // o[i] = y[i] c[i] - y[i+1] s[i];  o[i+1] = y[i+1] c[i+1] + y[i] s[i+1]
+        const float dy0 = go[u][i] * cs[i] + go[u][i + 1] * sn[i + 1];
+        const float dy1 = go[u][i + 1] * cs[i + 1] - go[u][i] * sn[i];
+        g[u][i] = dy0 * (which ? wkv[i] : wqv[i]);
+        g[u][i + 1] = dy1 * (which ? wkv[i + 1] : wqv[i + 1]);
+      }
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        ss[u] += x[u][i] * x[u][i];
+        sgx[u] += g[u][i] * x[u][i];  // scaled by rstd below
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
+        sgx[u] += __shfl_xor_sync(0xffffffffu, sgx[u], o);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + u;
+      if (r >= rows) continue;
+      const int which = r >= H, hh = which ? r - H : r;
+      const float rstd = rsqrtf(ss[u] / HD + eps);
+      const float m = sgx[u] * rstd / HD;  // mean(g * xhat)
+      float o[EPL];
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) o[i] = rstd * (g[u][i] - (x[u][i] * rstd) * m);
+      st_row<EPL>(out_tok + (which ? k_off : 0) + hh * HD, o);
+    }
   }
 }
 
