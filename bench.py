@@ -344,7 +344,9 @@ def run_b200(args):
     ms_e2e = timed_region(e2e_step, args.steps)
 
     # ---- per-kernel pass (extra step, outside both timed regions)
-    kern = profile_kernels(lambda b: step(b), dict(dev_batches[0])) if rank == 0 else None
+    # (every rank runs it: the step contains the DDP gradient all-reduce)
+    kern = profile_kernels(lambda b: step(b), dict(dev_batches[0]))
+    barrier()
     mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
 
     if rank == 0:
