@@ -359,9 +359,15 @@ def run_b200(args):
         roof = None
         if kern and "gemm_big" in kern:
             gb = kern["gemm_big"]
+            traffic = None
+            tp = ROOT / "profiles" / "r01" / "gemm_traffic.json"
+            if tp.exists():  # dram__bytes_read+write of one ncu --set full capture of this kernel (committed summary)
+                tj = json.loads(tp.read_text())
+                traffic = {"dram_bytes_per_launch": tj["dram_bytes_total"], "algorithmic_bytes": tj["algorithmic_bytes"],
+                           "shape": tj["shape"], "source": tj["source"]}
             roof = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05, all >=0.1 TFLOP launches of one step)",
                     "achieved": gb["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": round(gb["tflops"] / peak_tf, 4),
-                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})", "traffic": None,
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})", "traffic": traffic,
                     "avg_launch_ms": gb["avg_ms"], "tflop_per_launch": gb["tflop_per_launch"], "launches_per_step": gb["launches"]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -76,7 +76,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // store 128 x HD fp32 accumulator rows (this thread's TMEM lane) as bf16 to a global row
 template <int HD>
-__device__ __forceinline__ void store_acc_row(uint32_t taddr, __nv_bfloat16* grow, bool row_ok) {
+__device__ __forceinline__ void store_acc_row(uint32_t taddr, __nv_bfloat16* grow, bool row_ok, float mul = 1.f) {
 #pragma unroll 1
   for (int c = 0; c < HD; c += 32) {
     uint32_t v[32];
@@ -87,10 +87,10 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, __nv_bfloat16* gro
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
-        u.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
-        u.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
-        u.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+        u.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * mul, __uint_as_float(v[q * 8 + 1]) * mul);
+        u.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * mul, __uint_as_float(v[q * 8 + 3]) * mul);
+        u.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * mul, __uint_as_float(v[q * 8 + 5]) * mul);
+        u.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * mul, __uint_as_float(v[q * 8 + 7]) * mul);
         dp[q] = u;
       }
     }
@@ -235,7 +235,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
         if (elect_one()) issue_scores(w ^ 1, stg_n);  // overlaps the compute warpgroup working on tile i
         __syncwarp();
       }
-      mbar_wait(p_full(w), (i >> 1) & 1, 44);
+      mbar_wait(p_full(w), (i >> 1) & 1, 44);   // P^T and dS^T of tile i are both in TMEM
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -243,11 +243,6 @@ attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
           const uint64_t bd = sdesc_mn(do_smem(stg), kk * 2048, ATOM64);
           mma_ts(DV, X(w) + 8 * kk, bd, idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
         }
-      }
-      __syncwarp();
-      mbar_wait(ds_full(w), (i >> 1) & 1, 45);
-      tc_fence_after();
-      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t bd = sdesc_mn(q_smem(stg), kk * 2048, ATOM64);
@@ -283,48 +278,36 @@ attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
       const float* del_s = lse_s + 64;
       const float nxt = (i + 2 < n_q) ? load_stat(i + 2) : 0.f;
       mbar_wait(st_full(w), it & 1, 46);
+      mbar_wait(dpt_full(w), it & 1, 47);
       tc_fence_after();
-      float pv[64];
+      // one pass: P^T = exp2(S^T*sl2 - lse), dS^T = P^T o (dP^T - Delta)  (the softmax scale of dS is
+      // applied once to the dK accumulator in the epilogue)
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(X(w) + lane_off + 32 * c, v);
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32b_x32(X(w) + lane_off + 32 * c, sv);
+        tmem_ld_32x32b_x32(Y(w) + lane_off + 32 * c, dv);
         tc_wait_ld();
-        uint32_t pk[16];
+        uint32_t pk[16], dk_[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const int q = 32 * c + j;
-          const float x0 = ex2f(fmaf(__uint_as_float(v[j]), sl2, -lse_s[q]));
-          const float x1 = ex2f(fmaf(__uint_as_float(v[j + 1]), sl2, -lse_s[q + 1]));
-          pv[q] = x0;
-          pv[q + 1] = x1;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(lse_s + 32 * c + j);   // smem broadcast
+          const float4 d4 = *reinterpret_cast<const float4*>(del_s + 32 * c + j);
+          const float x0 = ex2f(fmaf(__uint_as_float(sv[j + 0]), sl2, -l4.x));
+          const float x1 = ex2f(fmaf(__uint_as_float(sv[j + 1]), sl2, -l4.y));
+          const float x2 = ex2f(fmaf(__uint_as_float(sv[j + 2]), sl2, -l4.z));
+          const float x3 = ex2f(fmaf(__uint_as_float(sv[j + 3]), sl2, -l4.w));
           pk[j / 2] = pack_bf16x2(x0, x1);
+          pk[j / 2 + 1] = pack_bf16x2(x2, x3);
+          dk_[j / 2] = pack_bf16x2(x0 * (__uint_as_float(dv[j + 0]) - d4.x), x1 * (__uint_as_float(dv[j + 1]) - d4.y));
+          dk_[j / 2 + 1] = pack_bf16x2(x2 * (__uint_as_float(dv[j + 2]) - d4.z), x3 * (__uint_as_float(dv[j + 3]) - d4.w));
         }
         tmem_st_32x32b_x16(X(w) + lane_off + 16 * c, pk);
+        tmem_st_32x32b_x16(Y(w) + lane_off + 16 * c, dk_);
       }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(p_full(w));
-      mbar_wait(dpt_full(w), it & 1, 47);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(Y(w) + lane_off + 32 * c, v);
-        tc_wait_ld();
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const int q = 32 * c + j;
-          const float d0 = pv[q] * (__uint_as_float(v[j]) - del_s[q]) * p.scale;
-          const float d1 = pv[q + 1] * (__uint_as_float(v[j + 1]) - del_s[q + 1]) * p.scale;
-          pk[j / 2] = pack_bf16x2(d0, d1);
-        }
-        tmem_st_32x32b_x16(Y(w) + lane_off + 16 * c, pk);
-      }
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(ds_full(w));
       if (i + 2 < n_q) my_stat[((it + 1) & 1) * 128 + wt] = nxt;
       named_bar_sync(1 + w, 128);
     }
@@ -336,7 +319,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
     if (w == 0)
       store_acc_row<HD>(DV + lane_off, p.dv + (long long)b * p.dv_b + (long long)kv * p.dv_s + (long long)h * p.dv_h, row_ok);
     else
-      store_acc_row<HD>(DK + lane_off, p.dk + (long long)b * p.dk_b + (long long)kv * p.dk_s + (long long)h * p.dk_h, row_ok);
+      store_acc_row<HD>(DK + lane_off, p.dk + (long long)b * p.dk_b + (long long)kv * p.dk_s + (long long)h * p.dk_h, row_ok, p.scale);
   }
 
   tc_fence_before();
@@ -526,8 +509,8 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
         for (int i = 0; i < 32; i += 2) {
           const float p0 = ex2f(fmaf(__uint_as_float(sv[i]), sl2, -lse2));
           const float p1 = ex2f(fmaf(__uint_as_float(sv[i + 1]), sl2, -lse2));
-          const float d0 = p0 * (__uint_as_float(dv[i]) - delta) * p.scale;
-          const float d1 = p1 * (__uint_as_float(dv[i + 1]) - delta) * p.scale;
+          const float d0 = p0 * (__uint_as_float(dv[i]) - delta);       // softmax scale applied in the epilogue
+          const float d1 = p1 * (__uint_as_float(dv[i + 1]) - delta);
           pk[i / 2] = pack_bf16x2(d0, d1);
         }
         tmem_st_32x32b_x16(Yb(w) + lane_off + 16 * c, pk);
@@ -552,10 +535,10 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+            u.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * p.scale, __uint_as_float(v[q * 8 + 1]) * p.scale);
+            u.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * p.scale, __uint_as_float(v[q * 8 + 3]) * p.scale);
+            u.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * p.scale, __uint_as_float(v[q * 8 + 5]) * p.scale);
+            u.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * p.scale, __uint_as_float(v[q * 8 + 7]) * p.scale);
             dp[q] = u;
           }
         }
