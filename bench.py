@@ -200,7 +200,7 @@ class CpuBaseline:
     """Depth-reduced Flux LoRA train step (full width 3072, full 4608-token sequence, B=1) through the fp32
     CPU oracle; `step()` returns seconds for fwd + LoRA backward; `summary()` extrapolates linearly in depth."""
 
-    def __init__(self, threads=None, blocks=(1, 1), seq=(S_IMG, S_TXT)):
+    def __init__(self, threads=None, blocks=(0, 1), seq=(S_IMG, S_TXT)):
         from oracle import flux_oracle as O
 
         self.O = O
@@ -252,7 +252,7 @@ def run_reference(args):
             times.append(dt)
     sec = cb.summary(statistics.mean(times))["extrapolated_full_depth_sec"]
     value = 1.0 / sec
-    sample = ("fp32 CPU oracle, B=1, 1 double + 1 single Flux block at full width (D=3072) and full sequence (4096+512 tokens), "
+    sample = ("fp32 CPU oracle, B=1, ONE single-stream Flux block (of 19 double + 38 single; both kinds cost 1.31 TFLOP fwd) at full width (D=3072) and full sequence (4096+512 tokens), "
               "fwd + LoRA backward; per-block time extrapolated linearly to 19+38 blocks")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -395,7 +395,7 @@ def run_b200(args):
             try:
                 cb = cpu_baseline_sample()
                 line["cpu_baseline"] = {"value": cb["images_per_sec"], "unit": UNIT, "cores": cb["threads"], "kind": "port",
-                                        "sample": "fp32 CPU oracle, B=1, 1 double + 1 single block at full width/sequence, fwd + LoRA bwd, "
+                                        "sample": "fp32 CPU oracle, B=1, one single-stream block at full width/sequence, fwd + LoRA bwd, "
                                                   f"{cb['sec_per_sample_step']:.1f} s measured, extrapolated linearly to 57 blocks"}
             except Exception as e:  # noqa
                 line["cpu_baseline"] = {"error": str(e)[:200]}

@@ -142,13 +142,14 @@ int stb_qk_rmsnorm_rope_bwd(const void* dq, const void* dk, long long d_b, long 
  *                        written unpacked (optional) and packed (flux/__init__.py:25-30).
  *   stb_flow_mse_loss  : mean_b mean_chw (pred.float() - (noise - latents).float())^2
  *                        (common.py:4610-4611, 6286, 6426-6429) with pred in packed layout
- *                        (unpack_latents, flux/__init__.py:33-44); optional d loss/d pred (packed).
+ *                        (layout 0: Flux unpack_latents order, flux/__init__.py:33-44; layout 1: SD3
+ *                        unpatchify order "nhwpqc->nchpwq", sd3/transformer.py:894); optional d loss/d pred.
  * latents/noise: bf16 [B, C, Hh, Ww] contiguous; sigmas fp32 [B]; loss_out fp32 [1] (zeroed here).
  * ------------------------------------------------------------------------------------------- */
 int stb_flow_prep_pack(const void* latents, const void* noise, const float* sigmas, void* noisy,
                        void* packed, int B, int C, int Hh, int Ww, void* stream);
 int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* noise, float* loss_out,
-                      void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, void* stream);
+                      void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, void* stream);
 
 /* y[b, s, :] = gate[b, :] * x[b, s, :]  — gradient of `gate * linear(...)` w.r.t. the linear output
  * (flux/transformer.py:464, 584, 652), applied before the dgrad GEMM. */

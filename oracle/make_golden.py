@@ -102,6 +102,19 @@ def main():
     except Exception as e:  # pragma: no cover - records why, the test then skips this vector
         g["sample_sigmas.error"] = repr(e)
 
+    # ---- min_snr_gamma.py:4-43 compute_snr, collate.py:59-98 compute_time_ids
+    snr = rx.functions("helpers/training/min_snr_gamma.py", ["compute_snr"])["compute_snr"]
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2
+    sched = SimpleNamespace(alphas_cumprod=torch.cumprod(1.0 - betas, dim=0))
+    ts = torch.tensor([0, 1, 250, 500, 731, 999])
+    g["snr.timesteps"] = ts
+    g["snr.out"] = snr(ts, sched)
+    g["snr.out_softmin"] = snr(ts, sched, use_soft_min=True, sigma_data=0.5)
+    cti = rx.functions("helpers/training/collate.py", ["compute_time_ids"],
+                       extra_ns={"StateTracker": SimpleNamespace(is_sdxl_refiner=lambda: False)})["compute_time_ids"]
+    g["time_ids.a"] = cti((1024, 768), (4, 96, 128), torch.float32, crop_coordinates=[0, 0])
+    g["time_ids.b"] = cti((1536, 640), (4, 80, 192), torch.bfloat16, crop_coordinates=[12, 34])
+
     OUT.parent.mkdir(parents=True, exist_ok=True)
     torch.save(g, OUT)
     print(f"wrote {OUT} with {len(g)} entries")

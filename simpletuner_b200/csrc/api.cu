@@ -499,13 +499,14 @@ int stb_flow_prep_pack(const void* latents, const void* noise, const float* sigm
 }
 
 int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* noise, float* loss_out,
-                      void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, void* stream) {
+                      void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, void* stream) {
   if (int r = check_device()) return r;
+  if (layout != 0 && layout != 1) return fail(STB_ERR_ARG, "flow_mse_loss layout must be 0 (Flux) or 1 (SD3)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   STB_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
   const long long n = (long long)B * C * Hh * Ww;
   const int grid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
-  stb::flow_mse_loss_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pred_packed), static_cast<const __nv_bfloat16*>(latents), static_cast<const __nv_bfloat16*>(noise), loss_out, static_cast<__nv_bfloat16*>(dpred_packed), grad_scale, B, C, Hh, Ww);
+  stb::flow_mse_loss_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pred_packed), static_cast<const __nv_bfloat16*>(latents), static_cast<const __nv_bfloat16*>(noise), loss_out, static_cast<__nv_bfloat16*>(dpred_packed), grad_scale, B, C, Hh, Ww, layout);
   STB_LAUNCH_CHECK("flow_mse_loss");
   return 0;
 }
@@ -529,8 +530,8 @@ int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, l
   if (int r = check_device()) return r;
   if (N & 1) return fail(STB_ERR_ARG, "N must be even");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // tensor-core path: both operands TMA-able (16-byte aligned rows), rank block <= 64
-  if (R % 8 == 0 && R <= 64 && N % 8 == 0 && aligned16(L) && aligned16(Rm) && !(l_s & 7) && !(r_s & 7) &&
+  // tensor-core path: both operands TMA-able (16-byte aligned rows), rank block <= 128
+  if (R % 8 == 0 && R <= 128 && N % 8 == 0 && aligned16(L) && aligned16(Rm) && !(l_s & 7) && !(r_s & 7) &&
       (B == 1 || (!(l_b & 7) && !(r_b & 7)))) {
     stb::WgradMaps maps;
     unsigned bx[3] = {64, 64, 1};
@@ -554,12 +555,12 @@ int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, l
     spb = (S + rows - 1) / rows;
     p.rows_per_split = rows;
     p.splits_per_batch = spb;
-    constexpr int SMEM = 6 * 24576 + 1024 + 256;
     dim3 grid(n_tiles, spb * B);
     const int rp = (R + 15) / 16 * 16;
 #define STB_WG(RPV)                                                          \
   {                                                                          \
     auto kern = stb::wgrad_tn_kernel<RPV>;                                   \
+    constexpr int SMEM = stb::WgradCfg<RPV>::SMEM_BYTES;                     \
     static bool configured = false;                                          \
     if (!configured) {                                                       \
       if (int r = set_smem(kern, SMEM)) return r;                            \
@@ -571,7 +572,11 @@ int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, l
       case 16: STB_WG(16) break;
       case 32: STB_WG(32) break;
       case 48: STB_WG(48) break;
-      default: STB_WG(64) break;
+      case 64: STB_WG(64) break;
+      case 80: STB_WG(80) break;
+      case 96: STB_WG(96) break;
+      case 112: STB_WG(112) break;
+      default: STB_WG(128) break;
     }
 #undef STB_WG
     STB_LAUNCH_CHECK("wgrad_tn");

@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(256)
 flow_mse_loss_kernel(const __nv_bfloat16* __restrict__ pred_packed, const __nv_bfloat16* __restrict__ lat,
                      const __nv_bfloat16* __restrict__ noise, float* __restrict__ loss_out,
                      __nv_bfloat16* __restrict__ dpred_packed, float grad_scale, int B, int C, int Hh,
-                     int Ww) {
+                     int Ww, int layout) {
   __shared__ float red[8];
   const long long n = (long long)B * C * Hh * Ww;
   const float inv = 1.f / float((long long)C * Hh * Ww) / float(B);
@@ -448,7 +448,9 @@ flow_mse_loss_kernel(const __nv_bfloat16* __restrict__ pred_packed, const __nv_b
     const int b = int(r / C);
     const int ph = hh >> 1, dy = hh & 1, pw = w >> 1, dx = w & 1;
     const long long tok = (long long)ph * (Ww >> 1) + pw;
-    const long long pi = ((long long)b * ((Hh >> 1) * (Ww >> 1)) + tok) * (4 * C) + ((c * 2 + dy) * 2 + dx);
+    // token features: Flux pack_latents order (c, dy, dx)  |  SD3 unpatchify order (dy, dx, c) ("nhwpqc->nchpwq")
+    const int feat = layout == 0 ? ((c * 2 + dy) * 2 + dx) : ((dy * 2 + dx) * C + c);
+    const long long pi = ((long long)b * ((Hh >> 1) * (Ww >> 1)) + tok) * (4 * C) + feat;
     // target = noise - latents computed in the latent dtype (bf16 tensor), then .float()
     const float tgt = bf16r(__bfloat162float(noise[i]) - __bfloat162float(lat[i]));
     const float d = __bfloat162float(pred_packed[pi]) - tgt;

@@ -27,13 +27,24 @@ struct WgradMaps {
   CUtensorMap l;   // 3-D (r, s, b) box (64, 64, 1) SWIZZLE_128B
 };
 
-template <int RP>  // padded rank block: 16, 32, 48, 64
+template <int RP>
+struct WgradCfg {
+  static constexpr int R_ATOMS = (RP + 63) / 64;          // [64 rows x 64 r] boxes of the L operand
+  static constexpr int A_BYTES = 2 * 8192;                // two [64 rows x 64 n] atoms
+  static constexpr int B_BYTES = 8192 * R_ATOMS;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = RP <= 32 ? 32 : (RP <= 64 ? 64 : 128);
+};
+
+template <int RP>  // padded rank block: multiple of 16, <= 128
 __global__ void __launch_bounds__(256, 1)
 wgrad_tn_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
-  constexpr int STAGES = 6;
-  constexpr int A_BYTES = 2 * 8192;  // two [64 rows x 64 n] atoms
-  constexpr int B_BYTES = 8192;      // one [64 rows x 64 r] atom
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  using Cfg = WgradCfg<RP>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int A_BYTES = Cfg::A_BYTES;
+  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -67,7 +78,7 @@ wgrad_tn_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 64);
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -87,7 +98,9 @@ wgrad_tn_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
           mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
           tma_load_3d(sa, &maps.rm, full_bar(stage), n0, s, b);
           tma_load_3d(sa + 8192, &maps.rm, full_bar(stage), n0 + 64, s, b);
-          tma_load_3d(sa + A_BYTES, &maps.l, full_bar(stage), 0, s, b);
+#pragma unroll
+          for (int ra = 0; ra < Cfg::R_ATOMS; ++ra)
+            tma_load_3d(sa + A_BYTES + ra * 8192, &maps.l, full_bar(stage), ra * 64, s, b);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -152,7 +165,7 @@ wgrad_tn_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

@@ -78,6 +78,7 @@ class LoraPack:
     scaling: float
     members: List[Optional[int]]  # index into the flat (A, B) parameter list, None = member not adapted
     n_out: int                    # rows per member
+    rank_padded: int = 0          # per-member column block inside the stacks (rank rounded up to 8)
 
 
 def pack_lora(params: List[Optional[Tuple[torch.Tensor, torch.Tensor]]], n_out: int, k_in: int, scaling: float,
@@ -87,22 +88,25 @@ def pack_lora(params: List[Optional[Tuple[torch.Tensor, torch.Tensor]]], n_out: 
     if not present:
         return None
     r = present[0][0].shape[0]
+    rp = (r + 7) // 8 * 8   # rank padded with zero rows/columns so every TMA row stride is 16-byte aligned
     M = len(params)
-    a_stack = torch.zeros((M * r, k_in), device=device, dtype=dtype)
-    b_ext = torch.zeros((M * n_out, M * r), device=device, dtype=dtype)
+    if M * rp > 128:
+        raise NotImplementedError(f"fused LoRA group of {M} x rank {r} exceeds the 128-wide rank block")
+    a_stack = torch.zeros((M * rp, k_in), device=device, dtype=dtype)
+    b_ext = torch.zeros((M * n_out, M * rp), device=device, dtype=dtype)
     members: List[Optional[int]] = []
     for m, p in enumerate(params):
         if p is None:
             members.append(None)
             continue
         a, b = p
-        a_stack[m * r:(m + 1) * r].copy_(a.detach())
-        blk = b_ext[m * n_out:(m + 1) * n_out, m * r:(m + 1) * r]
+        a_stack[m * rp:m * rp + r].copy_(a.detach())
+        blk = b_ext[m * n_out:(m + 1) * n_out, m * rp:m * rp + r]
         blk.copy_(b.detach())
         if scaling != 1.0:
             blk.mul_(scaling)
         members.append(m)
-    return LoraPack(a_stack, _t(a_stack), b_ext, _t(b_ext), r, scaling, members, n_out)
+    return LoraPack(a_stack, _t(a_stack), b_ext, _t(b_ext), r, scaling, members, n_out, rp)
 
 
 def _lora_down(x: torch.Tensor, pack: LoraPack) -> torch.Tensor:
@@ -116,13 +120,13 @@ def _lora_grads(pack: LoraPack, x: torch.Tensor, t_down: torch.Tensor, dy: torch
     d_a = ops.skinny_tn(t_up, x)        # [R, K] fp32
     d_bt = ops.skinny_tn(t_down, dy)    # [R, N] fp32
     out = []
-    r = pack.rank
+    r, rp = pack.rank, (pack.rank_padded or pack.rank)
     for m, idx in enumerate(pack.members):
         if idx is None:
             out.append((None, None))
             continue
-        da = d_a[m * r:(m + 1) * r]
-        dbt = d_bt[m * r:(m + 1) * r, m * pack.n_out:(m + 1) * pack.n_out]
+        da = d_a[m * rp:m * rp + r]
+        dbt = d_bt[m * rp:m * rp + r, m * pack.n_out:(m + 1) * pack.n_out]
         db = dbt.t()
         if pack.scaling != 1.0:
             db = db * pack.scaling
@@ -150,15 +154,54 @@ def _linear_lora_dgrad(dy, w_t, pack: Optional[LoraPack], **kw):
 
 
 # ------------------------------------------------------------------------------------------------
-# Double-stream block
+# shared: q / k preparation (per-head RMSNorm + RoPE, or plain views when the model has neither)
+# ------------------------------------------------------------------------------------------------
+def _qk_fwd(qkv, D, H, hd, img_plan: AttnPlan, txt_plan: Optional[AttnPlan], S_txt, cos, sin):
+    if img_plan.norm_q is None and cos is None:  # SD3-medium (qk_norm=None): nothing to compute
+        return qkv[:, :, 0:D].unflatten(-1, (H, hd)), qkv[:, :, D:2 * D].unflatten(-1, (H, hd))
+    tq = txt_plan.norm_q if txt_plan is not None else None
+    tk = txt_plan.norm_k if txt_plan is not None else None
+    return ops.qk_rmsnorm_rope_fwd(qkv, D, H, hd, img_plan.norm_q, img_plan.norm_k, tq, tk, S_txt, cos, sin, EPS)
+
+
+def _attn_core_bwd(qkv, o, d_o, lse, D, H, hd, img_plan, txt_plan, S_txt, cos, sin):
+    """Returns d_qkv [B, S, 3D] given d_o; recomputes q, k."""
+    B, S, _ = qkv.shape
+    q, k = _qk_fwd(qkv, D, H, hd, img_plan, txt_plan, S_txt, cos, sin)
+    v = qkv[:, :, 2 * D:].unflatten(-1, (H, hd))
+    d_qkv = torch.empty_like(qkv)
+    dv = d_qkv[:, :, 2 * D:].unflatten(-1, (H, hd))
+    if img_plan.norm_q is None and cos is None:
+        ops.attn_bwd(q, k, v, o.view(B, S, H, hd), d_o.view(B, S, H, hd), lse,
+                     dq=d_qkv[:, :, 0:D].unflatten(-1, (H, hd)), dk=d_qkv[:, :, D:2 * D].unflatten(-1, (H, hd)), dv=dv)
+        return d_qkv
+    dq = torch.empty_like(q)
+    dk = torch.empty_like(k)
+    ops.attn_bwd(q, k, v, o.view(B, S, H, hd), d_o.view(B, S, H, hd), lse, dq=dq, dk=dk, dv=dv)
+    del q, k
+    tq = txt_plan.norm_q if txt_plan is not None else None
+    tk = txt_plan.norm_k if txt_plan is not None else None
+    ops.qk_rmsnorm_rope_bwd(dq, dk, qkv, D, H, hd, img_plan.norm_q, img_plan.norm_k, tq, tk, S_txt, cos, sin, EPS, dsrc=d_qkv)
+    return d_qkv
+
+
+# ------------------------------------------------------------------------------------------------
+# Double-stream (joint) block — Flux FluxTransformerBlock and SD3 JointTransformerBlock
 # ------------------------------------------------------------------------------------------------
 class DoubleBlockFn(torch.autograd.Function):
-    """h_out = FluxTransformerBlock(h_in) on the joint [B, S_txt + S_img, D] buffer.
+    """h_out = JointBlock(h_in) on the joint [B, S_txt + S_img, D] buffer (text rows first).
 
-    inputs: h, mod_img [B, 6D], mod_txt [B, 6D] (adaLN vectors, no grad), cos, sin, static (plans /
-    sizes), then the flat LoRA tensors in the order
-      img: to_q.A, to_q.B, to_k.A, to_k.B, to_v.A, to_v.B, to_out.A, to_out.B,
-      txt: add_q.A, add_q.B, add_k.A, ..., to_add_out.A, to_add_out.B      (None where not adapted)
+    Flux (reference flux/transformer.py:563-687) and SD3 (reference sd3/transformer.py:145-241; the joint
+    attention is permutation-invariant without RoPE, so the [image, text] order of JointAttnProcessor2_0 is
+    irrelevant).  `st` flags: `nan_to_num_txt` (Flux), `dual` (SD3.5 image-only attn2 fed by a second
+    modulation of LayerNorm(h): mod_img then has 9 chunks), `context_pre_only` (SD3 last block: the text
+    stream only feeds q/k/v; mod_txt = [scale | shift] as AdaLayerNormContinuous chunks it).
+
+    inputs: h, mod_img [B, 6D|9D], mod_txt [B, 6D|2D] (adaLN vectors, no grad), cos, sin (or None), st, then the
+    flat LoRA tensors (None where not adapted) in the order
+      img : to_q.A, to_q.B, to_k.A, to_k.B, to_v.A, to_v.B, to_out.A, to_out.B            [0..7]
+      txt : add_q.A, add_q.B, add_k.*, add_v.*, to_add_out.A, to_add_out.B               [8..15]
+      attn2: to_q.A, to_q.B, to_k.*, to_v.*, to_out.A, to_out.B                          [16..23]
     """
 
     @staticmethod
@@ -167,7 +210,11 @@ class DoubleBlockFn(torch.autograd.Function):
         S_txt, H, hd = st["S_txt"], st["H"], st["hd"]
         plans: Dict[str, object] = st["plans"]
         scaling = st["lora_scaling"]
+        pre_only = st.get("context_pre_only", False)
+        dual = st.get("dual", False)
+        nan_txt = st.get("nan_to_num_txt", True)
         dev = h.device
+        lora = list(lora) + [None] * (24 - len(lora))
         streams = (("txt", slice(0, S_txt), mod_txt, 8), ("img", slice(S_txt, S), mod_img, 0))
 
         def lp(base, n_members, n_out, k_in):
@@ -177,67 +224,109 @@ class DoubleBlockFn(torch.autograd.Function):
                 ps.append(None if a is None else (a, b))
             return pack_lora(ps, n_out, k_in, scaling, dev)
 
+        def mod_shift_scale(name, mod):
+            if name == "txt" and pre_only:
+                return mod[:, D:2 * D], mod[:, 0:D]
+            return mod[:, 0:D], mod[:, D:2 * D]
+
         packs = {}
         qkv = torch.empty((B, S, 3 * D), device=dev, dtype=torch.bfloat16)
-        saved_small = {}
+        small = {}
         for name, sl, mod, base in streams:
             ap: AttnPlan = plans[name + "_attn"]
             packs[name + "_qkv"] = lp(base, 3, D, D)
-            packs[name + "_out"] = lp(base + 6, 1, D, D)
-            nh = ops.ln_modulate_fwd(h[:, sl], mod[:, 0:D], mod[:, D:2 * D], EPS)
+            packs[name + "_out"] = lp(base + 6, 1, D, D) if ap.w_out is not None else None
+            sh, sc = mod_shift_scale(name, mod)
+            nh = ops.ln_modulate_fwd(h[:, sl], sh, sc, EPS)
             _, t = _linear_lora_fwd(nh, ap.w_qkv, ap.b_qkv, packs[name + "_qkv"], out=qkv[:, sl])
-            saved_small[name + "_t_qkv"] = t
+            small[name + "_t_qkv"] = t
         ia: AttnPlan = plans["img_attn"]
         ta: AttnPlan = plans["txt_attn"]
-        q, k = ops.qk_rmsnorm_rope_fwd(qkv, D, H, hd, ia.norm_q, ia.norm_k, ta.norm_q, ta.norm_k, S_txt, cos, sin, EPS)
+        q, k = _qk_fwd(qkv, D, H, hd, ia, ta, S_txt, cos, sin)
         v = qkv[:, :, 2 * D:].unflatten(-1, (H, hd))
         o, lse = ops.attn_fwd(q, k, v)
         del q, k
         o = o.view(B, S, D)
         h1 = torch.empty_like(h)
         h2 = torch.empty_like(h)
-        mlp_pre = {}
         for name, sl, mod, base in streams:
             ap = plans[name + "_attn"]
-            mp: MlpPlan = plans[name + "_mlp"]
+            if name == "txt" and pre_only:
+                h1[:, sl].copy_(h[:, sl])
+                h2[:, sl].copy_(h[:, sl])
+                small[name + "_t_out"] = None
+                continue
             _, t = _linear_lora_fwd(o[:, sl], ap.w_out, ap.b_out, packs[name + "_out"], out=h1[:, sl],
                                     epi=ops.EPI_GATE_RES, gate=mod[:, 2 * D:3 * D], res=h[:, sl])
-            saved_small[name + "_t_out"] = t
+            small[name + "_t_out"] = t
+        qkv2 = o2 = lse2 = None
+        if dual:
+            isl = slice(S_txt, S)
+            a2: AttnPlan = plans["img_attn2"]
+            packs["a2_qkv"] = lp(16, 3, D, D)
+            packs["a2_out"] = lp(22, 1, D, D)
+            nh2a = ops.ln_modulate_fwd(h[:, isl], mod_img[:, 6 * D:7 * D], mod_img[:, 7 * D:8 * D], EPS)
+            qkv2, t = _linear_lora_fwd(nh2a, a2.w_qkv, a2.b_qkv, packs["a2_qkv"])
+            del nh2a
+            small["a2_t_qkv"] = t
+            q2, k2 = _qk_fwd(qkv2, D, H, hd, a2, None, 0, None, None)
+            o2, lse2 = ops.attn_fwd(q2, k2, qkv2[:, :, 2 * D:].unflatten(-1, (H, hd)))
+            del q2, k2
+            o2 = o2.view(B, S - S_txt, D)
+            # h1_img += gate_msa2 * to_out2(o2)   (in place: every element is read then written by one thread)
+            _, t = _linear_lora_fwd(o2, a2.w_out, a2.b_out, packs["a2_out"], out=h1[:, isl], epi=ops.EPI_GATE_RES,
+                                    gate=mod_img[:, 8 * D:9 * D], res=h1[:, isl])
+            small["a2_t_out"] = t
+        mlp_pre = {}
+        for name, sl, mod, base in streams:
+            if name == "txt" and pre_only:
+                mlp_pre[name] = None
+                continue
+            mp: MlpPlan = plans[name + "_mlp"]
             nh2 = ops.ln_modulate_fwd(h1[:, sl], mod[:, 3 * D:4 * D], mod[:, 4 * D:5 * D], EPS)
             pre = torch.empty((B, sl.stop - sl.start, 4 * D), device=dev, dtype=torch.bfloat16)
             act = ops.gemm([nh2], [mp.w1], mp.b1, epi=ops.EPI_GELU, aux=pre)
             del nh2
             ops.gemm([act], [mp.w2], mp.b2, out=h2[:, sl], epi=ops.EPI_GATE_RES, gate=mod[:, 5 * D:6 * D],
-                     res=h1[:, sl], nan_to_num=(name == "txt"))
+                     res=h1[:, sl], nan_to_num=(name == "txt" and nan_txt))
             del act
             mlp_pre[name] = pre
         ctx.st = st
         ctx.packs = packs
-        ctx.n_lora = len(lora)
+        ctx.n_lora_in = st.get("_n_lora", 16)
         ctx.lora_present = [x is not None for x in lora]
-        ctx.save_for_backward(h, mod_img, mod_txt, cos, sin, qkv, o, lse, h1, mlp_pre["txt"], mlp_pre["img"],
-                              *(saved_small[k] if saved_small[k] is not None else h.new_empty(0)
-                                for k in ("txt_t_qkv", "img_t_qkv", "txt_t_out", "img_t_out")))
+        E = h.new_empty(0)
+        keep = lambda t: t if t is not None else E
+        ctx.save_for_backward(h, mod_img, mod_txt, keep(cos), keep(sin), qkv, o, lse, h1, keep(mlp_pre["txt"]), mlp_pre["img"],
+                              keep(small["txt_t_qkv"]), keep(small["img_t_qkv"]), keep(small["txt_t_out"]), keep(small["img_t_out"]),
+                              keep(qkv2), keep(o2), keep(lse2), keep(small.get("a2_t_qkv")), keep(small.get("a2_t_out")))
         return h2
 
     @staticmethod
     def backward(ctx, dh2):
-        (h, mod_img, mod_txt, cos, sin, qkv, o, lse, h1, pre_txt, pre_img,
-         t_qkv_txt, t_qkv_img, t_out_txt, t_out_img) = ctx.saved_tensors
+        (h, mod_img, mod_txt, cos, sin, qkv, o, lse, h1, pre_txt, pre_img, t_qkv_txt, t_qkv_img, t_out_txt, t_out_img,
+         qkv2, o2, lse2, t_qkv_a2, t_out_a2) = ctx.saved_tensors
+        cos = cos if cos.numel() else None
+        sin = sin if sin.numel() else None
         st = ctx.st
         packs = ctx.packs
         B, S, D = h.shape
         S_txt, H, hd = st["S_txt"], st["H"], st["hd"]
         plans = st["plans"]
-        dev = h.device
+        pre_only = st.get("context_pre_only", False)
+        dual = st.get("dual", False)
         dh2 = dh2.contiguous()
         streams = (("txt", slice(0, S_txt), mod_txt, 8, pre_txt, t_qkv_txt, t_out_txt),
                    ("img", slice(S_txt, S), mod_img, 0, pre_img, t_qkv_img, t_out_img))
-        grads: List[Optional[torch.Tensor]] = [None] * ctx.n_lora
+        grads: List[Optional[torch.Tensor]] = [None] * 24
         dh1 = torch.empty_like(h)
         d_o = torch.empty_like(o)
         for name, sl, mod, base, pre, t_qkv, t_out in streams:
             ap: AttnPlan = plans[name + "_attn"]
+            if name == "txt" and pre_only:
+                dh1[:, sl].copy_(dh2[:, sl])
+                d_o[:, sl].zero_()
+                continue
             mp: MlpPlan = plans[name + "_mlp"]
             # ---- MLP branch: h2 = h1 + gate_mlp * fc2(gelu(fc1(LNmod(h1))))
             g2 = ops.gate_mul(dh2[:, sl], mod[:, 5 * D:6 * D])
@@ -255,36 +344,53 @@ class DoubleBlockFn(torch.autograd.Function):
                 (da, db), = _lora_grads(pk, o[:, sl], t_out, g1, t_up)
                 grads[base + 6], grads[base + 7] = da, db
             del g1
-        # ---- attention core
-        ia: AttnPlan = plans["img_attn"]
-        ta: AttnPlan = plans["txt_attn"]
-        q, k = ops.qk_rmsnorm_rope_fwd(qkv, D, H, hd, ia.norm_q, ia.norm_k, ta.norm_q, ta.norm_k, S_txt, cos, sin, EPS)
-        v = qkv[:, :, 2 * D:].unflatten(-1, (H, hd))
-        d_qkv = torch.empty_like(qkv)
-        dq = torch.empty_like(q)
-        dk = torch.empty_like(k)
-        ops.attn_bwd(q, k, v, o.view(B, S, H, hd), d_o.view(B, S, H, hd), lse, dq=dq, dk=dk,
-                     dv=d_qkv[:, :, 2 * D:].unflatten(-1, (H, hd)))
-        del q, k
-        ops.qk_rmsnorm_rope_bwd(dq, dk, qkv, D, H, hd, ia.norm_q, ia.norm_k, ta.norm_q, ta.norm_k, S_txt, cos, sin,
-                                EPS, dsrc=d_qkv)
-        del dq, dk
+        # ---- image-only second attention (SD3.5 dual attention)
+        d_nh2a = None
+        if dual:
+            isl = slice(S_txt, S)
+            a2: AttnPlan = plans["img_attn2"]
+            g = ops.gate_mul(dh1[:, isl], mod_img[:, 8 * D:9 * D])
+            pk = packs["a2_out"]
+            d_o2, t_up = _linear_lora_dgrad(g, a2.w_out_t, pk)
+            if pk is not None:
+                (da, db), = _lora_grads(pk, o2, t_out_a2, g, t_up)
+                grads[22], grads[23] = da, db
+            del g
+            d_qkv2 = _attn_core_bwd(qkv2, o2, d_o2, lse2, D, H, hd, a2, None, 0, None, None)
+            del d_o2
+            pk = packs["a2_qkv"]
+            d_nh2a, t_up = _linear_lora_dgrad(d_qkv2, a2.w_qkv_t, pk)
+            if pk is not None:
+                nh2a = ops.ln_modulate_fwd(h[:, isl], mod_img[:, 6 * D:7 * D], mod_img[:, 7 * D:8 * D], EPS)
+                for m, (da, db) in enumerate(_lora_grads(pk, nh2a, t_qkv_a2, d_qkv2, t_up)):
+                    grads[16 + 2 * m], grads[16 + 2 * m + 1] = da, db
+                del nh2a
+            del d_qkv2
+        # ---- joint attention core
+        d_qkv = _attn_core_bwd(qkv, o, d_o, lse, D, H, hd, plans["img_attn"], plans["txt_attn"], S_txt, cos, sin)
         dh = torch.empty_like(h)
         for name, sl, mod, base, pre, t_qkv, t_out in streams:
             ap = plans[name + "_attn"]
             pk = packs[name + "_qkv"]
+            if name == "txt" and pre_only:
+                sh_, sc_ = mod[:, D:2 * D], mod[:, 0:D]
+            else:
+                sh_, sc_ = mod[:, 0:D], mod[:, D:2 * D]
             d_nh, t_up = _linear_lora_dgrad(d_qkv[:, sl], ap.w_qkv_t, pk)
             if pk is not None:
-                nh = ops.ln_modulate_fwd(h[:, sl], mod[:, 0:D], mod[:, D:2 * D], EPS)
+                nh = ops.ln_modulate_fwd(h[:, sl], sh_, sc_, EPS)
                 for m, (da, db) in enumerate(_lora_grads(pk, nh, t_qkv, d_qkv[:, sl], t_up)):
                     grads[base + 2 * m], grads[base + 2 * m + 1] = da, db
                 del nh
-            ops.ln_modulate_bwd(d_nh, h[:, sl], mod[:, D:2 * D], add=dh1[:, sl], eps=EPS, out=dh[:, sl])
+            ops.ln_modulate_bwd(d_nh, h[:, sl], sc_, add=dh1[:, sl], eps=EPS, out=dh[:, sl])
             del d_nh
-        for i, present in enumerate(ctx.lora_present):
-            if not present:
-                grads[i] = None
-        return (dh, None, None, None, None, None, *grads)
+        if dual:
+            isl = slice(S_txt, S)
+            ops.ln_modulate_bwd(d_nh2a, h[:, isl], mod_img[:, 7 * D:8 * D], add=dh[:, isl], eps=EPS, out=dh[:, isl])
+        out_grads = []
+        for i in range(ctx.n_lora_in):
+            out_grads.append(grads[i] if ctx.lora_present[i] else None)
+        return (dh, None, None, None, None, None, *out_grads)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -340,16 +446,8 @@ class SingleBlockFn(torch.autograd.Function):
         d_o = ops.gemm([g], [mp.w2_t[:D]], None)
         d_pre = ops.gemm([g], [mp.w2_t[D:]], None, epi=ops.EPI_MUL_DGELU, aux=pre)
         del g
-        q, k = ops.qk_rmsnorm_rope_fwd(qkv, D, H, hd, ap.norm_q, ap.norm_k, None, None, 0, cos, sin, EPS)
-        v = qkv[:, :, 2 * D:].unflatten(-1, (H, hd))
-        d_qkv = torch.empty_like(qkv)
-        dq = torch.empty_like(q)
-        dk = torch.empty_like(k)
-        ops.attn_bwd(q, k, v, o.view(B, S, H, hd), d_o.view(B, S, H, hd), lse, dq=dq, dk=dk,
-                     dv=d_qkv[:, :, 2 * D:].unflatten(-1, (H, hd)))
-        del q, k, d_o
-        ops.qk_rmsnorm_rope_bwd(dq, dk, qkv, D, H, hd, ap.norm_q, ap.norm_k, None, None, 0, cos, sin, EPS, dsrc=d_qkv)
-        del dq, dk
+        d_qkv = _attn_core_bwd(qkv, o, d_o, lse, D, H, hd, ap, None, 0, cos, sin)
+        del d_o
         grads: List[Optional[torch.Tensor]] = [None] * 6
         # d_nh = d_pre W_mlp + d_qkv W_qkv (+ LoRA)  — one GEMM, two/three K-segments
         if pk is None:
@@ -401,8 +499,8 @@ class FlowLossFn(torch.autograd.Function):
     """loss = mean_b mean_chw (unpack(pred) - (noise - latents))^2 ; backward = precomputed d loss/d pred."""
 
     @staticmethod
-    def forward(ctx, pred_packed, latents, noise):
-        loss, dpred = ops.flow_mse_loss(pred_packed.contiguous(), latents, noise, want_grad=True)
+    def forward(ctx, pred_packed, latents, noise, layout=0):
+        loss, dpred = ops.flow_mse_loss(pred_packed.contiguous(), latents, noise, want_grad=True, layout=layout)
         ctx.save_for_backward(dpred)
         return loss[0]
 
@@ -410,4 +508,4 @@ class FlowLossFn(torch.autograd.Function):
     def backward(ctx, g):
         (dpred,) = ctx.saved_tensors
         # g is the scalar upstream gradient (1.0 for loss.backward()); keep it on-device
-        return (dpred * g.to(dpred.dtype)), None, None
+        return (dpred * g.to(dpred.dtype)), None, None, None

@@ -334,8 +334,8 @@ class FluxTransformer2DModel(nn.Module):
             raise NotImplementedError(
                 "lora_dropout > 0 is not implemented in the fused LoRA epilogue yet (reference default 0.1, "
                 "sections/lora.py:130-137); parity runs pin --lora_dropout=0")
-        if rank not in (16,):
-            raise NotImplementedError("fused LoRA path currently supports rank 16 (BASELINE config 2)")
+        if not 1 <= rank <= 40:
+            raise NotImplementedError("fused LoRA path supports rank 1..40 (three fused projections share a 128-wide rank block)")
         lora_alpha = float(lora_alpha) if lora_alpha is not None else float(rank)  # common.py:1090-1093
         targets = list(target_modules) if target_modules is not None else FLUX_LORA_TARGETS["all"]
         supported = set(FLUX_LORA_TARGETS["all"])

@@ -232,14 +232,14 @@ def flow_prep_pack(latents, noise, sigmas, want_unpacked: bool = True):
     return noisy, packed
 
 
-def flow_mse_loss(pred_packed, latents, noise, want_grad: bool = True, grad_scale: float = 1.0):
+def flow_mse_loss(pred_packed, latents, noise, want_grad: bool = True, grad_scale: float = 1.0, layout: int = 0):
     """Returns (loss fp32 scalar tensor [1], dpred_packed or None)."""
     assert pred_packed.is_contiguous() and latents.is_contiguous() and noise.is_contiguous()
     B, Cc, Hh, Ww = latents.shape
     loss = torch.empty((1,), device=latents.device, dtype=torch.float32)
     dpred = torch.empty_like(pred_packed) if want_grad else None
     check(_lib.lib().stb_flow_mse_loss(pred_packed.data_ptr(), latents.data_ptr(), noise.data_ptr(),
-                                       loss.data_ptr(), _ptr(dpred), grad_scale, B, Cc, Hh, Ww, _stream()))
+                                       loss.data_ptr(), _ptr(dpred), grad_scale, B, Cc, Hh, Ww, layout, _stream()))
     return loss, dpred
 
 

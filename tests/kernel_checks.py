@@ -336,3 +336,5 @@ CHECKS = {
     "skinny_ragged": lambda: check_skinny(B=3, S=333, R=16, N=200),
     "skinny_cuda_core_path": lambda: check_skinny(B=2, S=100, R=16, N=250),
 }
+CHECKS["skinny_r96"] = lambda: check_skinny(B=2, S=700, R=96, N=1536)
+CHECKS["skinny_r24"] = lambda: check_skinny(B=1, S=300, R=24, N=512)

@@ -43,7 +43,8 @@ def test_fullsize_properties(full):
     assert torch.equal(prep1["noisy_latents"], prep2["noisy_latents"])
     l1 = w.loss(prep1, out1)
     l2 = w.loss(prep2, out2)
-    assert torch.equal(l1, l2) and torch.isfinite(l1)
+    # the loss kernel reduces per-block partial sums with fp32 atomics: equal up to summation order
+    assert torch.isfinite(l1) and abs(float(l1) - float(l2)) <= 1e-6 * abs(float(l1))
     # ---- pack / unpack round trip at full latent size
     from simpletuner_b200.flux.functional import pack_latents, unpack_latents
     assert torch.equal(prep1["_packed_noisy_latents"], pack_latents(prep1["noisy_latents"], 4, 16, 128, 128))
