@@ -28,6 +28,7 @@ def _predict(w, batch, seed):
     torch.manual_seed(seed)
     torch.cuda.manual_seed(seed)
     prep = w.prepare_batch({k: v.clone() for k, v in batch.items()}, {"global_step": 0})
+    prep["_raw_timesteps"] = prep["timesteps"].clone()  # model_predict overwrites `timesteps` with t / 1000
     out = w.model_predict(prep)
     return prep, out
 
@@ -55,7 +56,7 @@ def test_fullsize_properties(full):
         pp = dict(prep1)
         for k in ("latents", "noise", "input_noise", "noisy_latents", "_packed_noisy_latents", "encoder_hidden_states", "sigmas"):
             pp[k] = prep1[k][perm].contiguous()
-        pp["timesteps"] = (prep1["timesteps"] * 1000)[perm]      # model_predict rescaled it in place
+        pp["timesteps"] = prep1["_raw_timesteps"][perm]
         pp["added_cond_kwargs"] = {"text_embeds": prep1["added_cond_kwargs"]["text_embeds"][perm].contiguous()}
         outp = w.model_predict(pp)
     assert torch.equal(outp["model_prediction"], out1["model_prediction"][perm])
