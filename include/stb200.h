@@ -165,6 +165,29 @@ int stb_gate_mul(const void* x, long long x_b, long long x_s, const void* gate, 
 int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, long long r_b, long long r_s,
                   float* out, int B, int S, int R, int N, float alpha, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * VAE latent encode (diffusers AutoencoderKL.encode as called at reference common.py:2766-2772 from
+ * caching/vae.py:1311; sampling caching/vae.py:1337; scaling foundation_mixins.py:68-81).
+ * Activations are NHWC bf16; every 3x3 conv is a tcgen05 implicit GEMM (9 shifted K-segments, the halo
+ * is zero-filled by TMA); 1x1 convs / attention projections are stb_gemm_bf16 over pixels.
+ *   stb_conv3x3_nhwc : out[B,Ho,Wo,Co] = conv3x3(x[B,H,W,Ci]; w[Co, 9*Ci] tap-major (dy,dx,ci)) + bias (+ res)
+ *                      stride 1: padding 1;  stride 2: F.pad(x,(0,1,0,1)) then stride-2 (Downsample2D)
+ *   stb_conv_in_3ch  : conv_in on the NCHW pixel tensor [B,3,H,W] (w OIHW [C,3,3,3]) -> NHWC [B,H,W,C]
+ *   stb_groupnorm_nhwc : GroupNorm(G, eps, affine) (+ SiLU) over NHWC; stats = fp32 scratch [B*G*2]
+ *   stb_softmax_rows : in-place softmax(scale * s) over rows of the mid-block attention scores
+ *   stb_gaussian_sample_scale : z = (mean + exp(.5 clamp(logvar,-30,20)) * eps - shift) * scale, NHWC moments
+ *                      [B,h*w,2L] + NCHW eps [B,L,h,w] -> NCHW latents [B,L,h,w]
+ * ------------------------------------------------------------------------------------------- */
+int stb_conv3x3_nhwc(const void* x, const void* w, const void* bias, const void* res, void* out, int B, int H, int W,
+                     int C_in, int C_out, int stride, void* stream);
+int stb_conv_in_3ch(const void* pixels, const void* w, const void* bias, void* out, int B, int H, int W, int C,
+                    void* stream);
+int stb_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, void* out, float* stats, int B, int HW,
+                       int C, int G, float eps, int silu, void* stream);
+int stb_softmax_rows(void* s, long long row_stride, int rows, int cols, float scale, void* stream);
+int stb_gaussian_sample_scale(const void* moments, const void* eps, void* out, int B, int L, int hw, float shift,
+                              float scale, int has_shift, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

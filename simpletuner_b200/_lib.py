@@ -124,6 +124,11 @@ SYMBOLS = {
     "stb_flow_mse_loss": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P]),
     "stb_gate_mul": (_I, [_P, _LL, _LL, _P, _LL, _P, _LL, _LL, _I, _I, _I, _P]),
     "stb_skinny_tn": (_I, [_P, _LL, _LL, _P, _LL, _LL, _P, _I, _I, _I, _I, _F, _P]),
+    "stb_conv3x3_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "stb_conv_in_3ch": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "stb_groupnorm_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "stb_softmax_rows": (_I, [_P, _LL, _I, _I, _F, _P]),
+    "stb_gaussian_sample_scale": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _I, _P]),
 }
 
 _lock = threading.Lock()

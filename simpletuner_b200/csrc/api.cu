@@ -17,6 +17,7 @@
 #include "attn_fwd.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "vae.cuh"
 #include "wgrad.cuh"
 
 namespace {
@@ -151,6 +152,24 @@ int make_map_f32(CUtensorMap* out, const void* ptr, int rank, const unsigned lon
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(STB_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed with CUresult %d", int(r));
+  return 0;
+}
+
+// bf16 SWIZZLE_128B map with per-dimension traversal strides (strided conv windows); not cached
+int make_map_strided(CUtensorMap* out, const void* ptr, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_bytes, const unsigned* box, const unsigned* estrides) {
+  auto fn = encode_fn();
+  if (!fn) return fail(STB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail(STB_ERR_ARG, "tensor base pointer must be 16-byte aligned");
+  cuuint64_t gdim[4];
+  cuuint64_t gstr[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) gdim[i] = dims[i], bx[i] = box[i], es[i] = estrides[i];
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(STB_ERR_CUDA, "cuTensorMapEncodeTiled(strided) failed with CUresult %d", int(r));
   return 0;
 }
 
@@ -599,6 +618,136 @@ int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, l
     default: return fail(STB_ERR_UNSUPPORTED, "LoRA rank block R=%d not supported (16/32/48/64)", R);
   }
   STB_LAUNCH_CHECK("skinny_tn");
+  return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- VAE latent encode
+template <int BN>
+static int launch_conv3x3(const void* x, const void* w, const void* bias, const void* res, void* out, int B, int H,
+                          int W, int C_in, int C_out, int stride, cudaStream_t st) {
+  using Cfg = stb::GemmCfg<1, BN>;
+  const int H_out = stride == 1 ? H : H / 2, W_out = stride == 1 ? W : W / 2;
+  stb::GemmMaps maps;
+  std::memset(&maps, 0, sizeof maps);
+  {
+    unsigned long long d[4] = {(unsigned long long)C_in, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};
+    unsigned long long sb[3] = {(unsigned long long)C_in * 2ull, (unsigned long long)W * C_in * 2ull,
+                                (unsigned long long)H * W * C_in * 2ull};
+    unsigned bx[4] = {64, (unsigned)(128 * stride), 1, 1};  // traversed span: 128 elements at stride `stride`
+    unsigned es[4] = {1, (unsigned)stride, 1, 1};
+    if (int r = make_map_strided(&maps.a[0], x, 4, d, sb, bx, es)) return r;
+  }
+  {
+    unsigned long long d[2] = {(unsigned long long)9 * C_in, (unsigned long long)C_out};
+    unsigned long long sb[1] = {(unsigned long long)9 * C_in * 2ull};
+    unsigned bx[2] = {64, (unsigned)BN};
+    if (int r = make_map(&maps.w[0], w, 2, d, sb, bx)) return r;
+  }
+  stb::GemmParams p;
+  std::memset(&p, 0, sizeof p);
+  p.rows_per_batch = W_out;
+  p.num_batches = B * H_out;
+  p.N = C_out;
+  p.nseg = 1;
+  p.kblocks[0] = 9 * (C_in / 64);
+  p.kmmas_last[0] = 4;
+  p.epi = res ? stb::EPI_ADD_RES : stb::EPI_STORE;
+  p.D = static_cast<__nv_bfloat16*>(out);
+  p.d_batch_stride = (long long)W_out * C_out;
+  p.d_row_stride = C_out;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.res = static_cast<const __nv_bfloat16*>(res);
+  p.res_batch_stride = p.d_batch_stride;
+  p.res_row_stride = C_out;
+  p.conv_h_out = H_out;
+  p.conv_stride = stride;
+  p.conv_pad = stride == 1 ? 1 : 0;
+  p.conv_cblocks = C_in / 64;
+  auto kernel = stb::gemm_bf16_tn_kernel<1, BN, true>;
+  static bool configured = false;
+  if (!configured) {
+    if (int r = set_smem(kernel, Cfg::SMEM_BYTES)) return r;
+    configured = true;
+  }
+  const long long tiles = (long long)((W_out + 127) / 128) * p.num_batches * ((C_out + BN - 1) / BN);
+  const int grid = (int)std::min<long long>(tiles, num_sms());
+  kernel<<<grid, 256, Cfg::SMEM_BYTES, st>>>(maps, p);
+  STB_LAUNCH_CHECK("conv3x3_nhwc");
+  return 0;
+}
+
+extern "C" {
+
+int stb_conv3x3_nhwc(const void* x, const void* w, const void* bias, const void* res, void* out, int B, int H, int W,
+                     int C_in, int C_out, int stride, void* stream) {
+  if (int r = check_device()) return r;
+  if (C_in % 64 || C_out % 8) return fail(STB_ERR_ARG, "conv3x3_nhwc needs C_in %% 64 == 0 and C_out %% 8 == 0 (got %d, %d)", C_in, C_out);
+  if (stride != 1 && stride != 2) return fail(STB_ERR_ARG, "conv3x3_nhwc stride must be 1 or 2");
+  if (stride == 2 && ((H | W) & 1)) return fail(STB_ERR_ARG, "stride-2 conv needs even H, W");
+  if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (res && !aligned16(res)) || (bias && !aligned16(bias)))
+    return fail(STB_ERR_ARG, "conv3x3_nhwc alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (C_out > 128) return launch_conv3x3<256>(x, w, bias, res, out, B, H, W, C_in, C_out, stride, st);
+  if (C_out > 64) return launch_conv3x3<128>(x, w, bias, res, out, B, H, W, C_in, C_out, stride, st);
+  return launch_conv3x3<64>(x, w, bias, res, out, B, H, W, C_in, C_out, stride, st);
+}
+
+int stb_conv_in_3ch(const void* pixels, const void* w, const void* bias, void* out, int B, int H, int W, int C,
+                    void* stream) {
+  if (int r = check_device()) return r;
+  if (C % 8 || C > 512) return fail(STB_ERR_ARG, "conv_in_3ch: C must be a multiple of 8, <= 512");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = (long long)B * H * W * (C / 8);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
+  const int smem = (C * 27 + C) * (int)sizeof(float);
+  auto kernel = stb::conv_in_3ch_kernel;
+  static bool configured = false;
+  if (!configured) {
+    if (int r = set_smem(kernel, 512 * 28 * (int)sizeof(float))) return r;
+    configured = true;
+  }
+  kernel<<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(pixels), static_cast<const __nv_bfloat16*>(w),
+                                  static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(out), B, H, W, C);
+  STB_LAUNCH_CHECK("conv_in_3ch");
+  return 0;
+}
+
+int stb_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, void* out, float* stats, int B, int HW,
+                       int C, int G, float eps, int silu, void* stream) {
+  if (int r = check_device()) return r;
+  if (C % 8 || C > 512 || G > 64 || C % G || ((C / G) != 4 && (C / G) % 8)) return fail(STB_ERR_ARG, "groupnorm_nhwc: unsupported C=%d G=%d", C, G);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  STB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * G, st));
+  const int chunks = std::max(1, std::min((HW + 255) / 256, (num_sms() * 4 + B - 1) / B));
+  const int ppc = (HW + chunks - 1) / chunks;
+  stb::groupnorm_stats_kernel<<<dim3((HW + ppc - 1) / ppc, B), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), stats, HW, C, G, ppc);
+  STB_LAUNCH_CHECK("groupnorm_stats");
+  const long long total = (long long)B * HW * (C / 8);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
+  stb::groupnorm_apply_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), stats, static_cast<const __nv_bfloat16*>(gamma),
+                                                     static_cast<const __nv_bfloat16*>(beta), static_cast<__nv_bfloat16*>(out), B, HW, C, G, eps, silu);
+  STB_LAUNCH_CHECK("groupnorm_apply");
+  return 0;
+}
+
+int stb_softmax_rows(void* s, long long row_stride, int rows, int cols, float scale, void* stream) {
+  if (int r = check_device()) return r;
+  if (cols % 8 || (row_stride & 7) || !aligned16(s)) return fail(STB_ERR_ARG, "softmax_rows alignment");
+  stb::softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(s), row_stride, cols, scale);
+  STB_LAUNCH_CHECK("softmax_rows");
+  return 0;
+}
+
+int stb_gaussian_sample_scale(const void* moments, const void* eps, void* out, int B, int L, int hw, float shift,
+                              float scale, int has_shift, void* stream) {
+  if (int r = check_device()) return r;
+  const long long total = (long long)B * L * hw;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
+  stb::gaussian_sample_scale_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(moments), static_cast<const __nv_bfloat16*>(eps), static_cast<__nv_bfloat16*>(out), B, L, hw, shift, scale, has_shift);
+  STB_LAUNCH_CHECK("gaussian_sample_scale");
   return 0;
 }
 

@@ -43,6 +43,10 @@ struct GemmParams {
   long long res_batch_stride, res_row_stride;
   __nv_bfloat16* aux;  // EPI_GELU: written; EPI_MUL_DGELU: read
   long long aux_batch_stride, aux_row_stride;
+  // CONV mode (3x3 NHWC implicit GEMM): a "batch" is one output image row, a "row" an output pixel x.
+  // maps.a[0] is then a 4-D map (c, x, y, img) with box (64, 128, 1, 1) and x element-stride = conv_stride;
+  // k-block kb covers tap kb / conv_cblocks (dy = tap / 3, dx = tap % 3) and channels (kb % conv_cblocks) * 64.
+  int conv_h_out, conv_stride, conv_pad, conv_cblocks;
 };
 
 struct GemmMaps {
@@ -80,7 +84,7 @@ __device__ __forceinline__ void gemm_tile_coords(int tile, int tiles_m, int tile
   tn = within / gsize;
 }
 
-template <int MT, int BN>
+template <int MT, int BN, bool CONV = false>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using Cfg = GemmCfg<MT, BN>;
@@ -151,9 +155,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
             if (elect_one()) {
               mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+              if constexpr (CONV) {
+                // implicit-GEMM 3x3 conv: shifted input window; TMA zero-fills the halo (x / y out of range)
+                const int tap = kb / p.conv_cblocks;
+                const int c0 = (kb - tap * p.conv_cblocks) * 64;
+                const int img = b / p.conv_h_out, yo = b - img * p.conv_h_out;
+                const int dy = tap / 3, dx = tap - dy * 3;
+                tma_load_4d(sa, &maps.a[0], full_bar(stage), c0, s0 * p.conv_stride + dx - p.conv_pad,
+                            yo * p.conv_stride + dy - p.conv_pad, img);
+              } else {
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt)
-                tma_load_3d(sa + mt * Cfg::A_BYTES, &maps.a[seg], full_bar(stage), kb * 64, s0 + mt * 128, b);
+                for (int mt = 0; mt < MT; ++mt)
+                  tma_load_3d(sa + mt * Cfg::A_BYTES, &maps.a[seg], full_bar(stage), kb * 64, s0 + mt * 128, b);
+              }
               tma_load_2d(sa + MT * Cfg::A_BYTES, &maps.w[seg], full_bar(stage), kb * 64, n0);
             }
             __syncwarp();

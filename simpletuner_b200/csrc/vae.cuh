@@ -1,0 +1,209 @@
+// simpletuner_b200 — non-GEMM kernels of the VAE latent-encode path (AutoencoderKL encoder), sm_100a.
+// Activations are NHWC bf16 so that every 3x3 / 1x1 conv is a tcgen05 GEMM over pixels
+// (gemm.cuh, CONV mode: 9 shifted K-segments whose halo TMA zero-fills).  Here: the HBM-bound pieces.
+//   conv_in_3ch_kernel     : 3 -> C conv3x3 on the NCHW pixel tensor (K = 27: CUDA cores), writes NHWC
+//   groupnorm_stats_kernel : per (image, group) sum / sum-of-squares over H*W*(C/G)   (fp32 atomics)
+//   groupnorm_apply_kernel : (x - mean) * rstd * gamma + beta, optional SiLU, bf16 NHWC
+//   softmax_rows_kernel    : in-place row softmax of the mid-block attention scores (fp32 math)
+//   gaussian_sample_scale  : z = (mean + exp(0.5 clamp(logvar)) * eps - shift) * scale -> NCHW latents
+// reference: diffusers AutoencoderKL.encode as called at common.py:2766-2772, sampling at caching/vae.py:1337,
+// scaling at foundation_mixins.py:68-81.
+#pragma once
+#include "common.cuh"
+#include "elementwise.cuh"
+
+namespace stb {
+
+// pixels: [B, 3, H, W] bf16 (NCHW, as the reference hands them to vae.encode); w: [C, 3, 3, 3] (OIHW); out NHWC.
+// one thread = one output pixel x 8 output channels
+__global__ void __launch_bounds__(256)
+conv_in_3ch_kernel(const __nv_bfloat16* __restrict__ px, const __nv_bfloat16* __restrict__ w,
+                   const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C) {
+  extern __shared__ float sw[];  // [C][27] + [C]
+  for (int i = threadIdx.x; i < C * 27; i += blockDim.x) sw[i] = __bfloat162float(w[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[C * 27 + i] = __bfloat162float(bias[i]);
+  __syncthreads();
+  const int cgroups = C / 8;
+  const long long total = (long long)B * H * W * cgroups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = int(idx % cgroups);
+    long long pix = idx / cgroups;
+    const int x = int(pix % W);
+    pix /= W;
+    const int y = int(pix % H);
+    const int b = int(pix / H);
+    float in[27];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int yy = y + dy - 1, xx = x + dx - 1;
+          in[(c * 3 + dy) * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                                          ? __bfloat162float(px[(((long long)b * 3 + c) * H + yy) * W + xx])
+                                          : 0.f;
+        }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = cg * 8 + j;
+      float acc = sw[C * 27 + co];
+#pragma unroll
+      for (int t = 0; t < 27; ++t) acc += in[t] * sw[co * 27 + t];
+      o[j] = acc;
+    }
+    *reinterpret_cast<uint4*>(out + (((long long)b * H + y) * W + x) * C + cg * 8) = pack8(o);
+  }
+}
+
+// x: NHWC [B, HW, C]; stats: fp32 [B, G, 2] (zeroed by the caller).  grid = (chunks, B); each CTA reduces a
+// contiguous chunk of pixels for all channels; C <= 512, channels-per-group cpg = C / G (multiple of 2).
+__global__ void __launch_bounds__(256)
+groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, int HW, int C, int G,
+                       int pix_per_cta) {
+  __shared__ float s_sum[64], s_sq[64];
+  const int b = blockIdx.y;
+  if (threadIdx.x < G) s_sum[threadIdx.x] = 0.f, s_sq[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int vec_per_pix = C / 8;
+  const int cpg = C / G;
+  const long long p0 = (long long)blockIdx.x * pix_per_cta;
+  const long long p1 = min((long long)HW, p0 + pix_per_cta);
+  const __nv_bfloat16* xb = x + (long long)b * HW * C;
+  // thread -> one fixed 8-channel vector column (its group(s) are fixed), striding over the chunk's pixels
+  const int rows_par = blockDim.x / vec_per_pix;  // vec_per_pix <= 64 (C <= 512)
+  const int r0 = threadIdx.x / vec_per_pix;
+  if (r0 < rows_par) {
+    const int v = threadIdx.x % vec_per_pix;
+    float f[8];
+    float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;  // two groups at most per 8-vector when cpg == 4
+    for (long long pix = p0 + r0; pix < p1; pix += rows_par) {
+      unpack8(*reinterpret_cast<const uint4*>(xb + pix * C + v * 8), f);
+      if (cpg >= 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a0 += f[j], q0 += f[j] * f[j];
+      } else {  // cpg == 4: channels 0..3 -> group g, 4..7 -> group g + 1
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a0 += f[j], q0 += f[j] * f[j];
+#pragma unroll
+        for (int j = 4; j < 8; ++j) a1 += f[j], q1 += f[j] * f[j];
+      }
+    }
+    const int g0 = (v * 8) / cpg;
+    atomicAdd(&s_sum[g0], a0);
+    atomicAdd(&s_sq[g0], q0);
+    if (cpg < 8) {
+      atomicAdd(&s_sum[g0 + 1], a1);
+      atomicAdd(&s_sq[g0 + 1], q1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    atomicAdd(&stats[((long long)b * G + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
+    atomicAdd(&stats[((long long)b * G + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
+                       const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                       __nv_bfloat16* __restrict__ out, int B, int HW, int C, int G, float eps, int silu) {
+  const int vec_per_pix = C / 8;
+  const int cpg = C / G;
+  const float inv_n = 1.f / (float(HW) * float(cpg));
+  const long long total = (long long)B * HW * vec_per_pix;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = int(i % vec_per_pix);
+    const long long pix = i / vec_per_pix;
+    const int b = int(pix / HW);
+    float f[8], gm[8], bt[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + pix * C + v * 8), f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + v * 8)), gm);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(beta + v * 8)), bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (v * 8 + j) / cpg;
+      const float s = stats[((long long)b * G + g) * 2 + 0];
+      const float q = stats[((long long)b * G + g) * 2 + 1];
+      const float mean = s * inv_n;
+      const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      float y = (f[j] - mean) * rstd * gm[j] + bt[j];
+      if (silu) {
+        y = bf16r(y);                 // GroupNorm output tensor (bf16), then nn.SiLU
+        y = y / (1.f + __expf(-y));
+      }
+      o[j] = y;
+    }
+    *reinterpret_cast<uint4*>(out + pix * C + v * 8) = pack8(o);
+  }
+}
+
+// in-place softmax over the last dimension of s [rows, cols] (bf16 storage, fp32 math), logits pre-scaled by `scale`
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(__nv_bfloat16* __restrict__ s, long long row_stride, int cols, float scale) {
+  __shared__ float red[8];
+  __nv_bfloat16* row = s + (long long)blockIdx.x * row_stride;
+  float m = -INFINITY;
+  for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(row + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m = fmaxf(m, f[j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(row + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += __expf((f[j] - m) * scale);
+  }
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = red[0] + red[1] + red[2] + red[3] + red[4] + red[5] + red[6] + red[7];
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(row + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __expf((f[j] - m) * scale) * inv;
+    *reinterpret_cast<uint4*>(row + c) = pack8(f);
+  }
+}
+
+// moments: NHWC [B, h*w, 2L] (mean | logvar); eps: NCHW [B, L, h, w]; out: NCHW [B, L, h, w] (bf16)
+__global__ void __launch_bounds__(256)
+gaussian_sample_scale_kernel(const __nv_bfloat16* __restrict__ moments, const __nv_bfloat16* __restrict__ eps,
+                             __nv_bfloat16* __restrict__ out, int B, int L, int hw, float shift, float scale,
+                             int has_shift) {
+  const long long total = (long long)B * L * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = int(i % hw);
+    const long long r = i / hw;
+    const int c = int(r % L);
+    const int b = int(r / L);
+    const __nv_bfloat16* mrow = moments + ((long long)b * hw + p) * (2 * L);
+    const float mean = __bfloat162float(mrow[c]);
+    const float logvar = fminf(fmaxf(__bfloat162float(mrow[L + c]), -30.f), 20.f);
+    // DiagonalGaussianDistribution: std = exp(0.5 * logvar) (bf16 tensor), sample = mean + std * eps (bf16 ops)
+    const float std = bf16r(__expf(0.5f * bf16r(logvar)));
+    float z = bf16r(mean + bf16r(std * __bfloat162float(eps[i])));
+    z = has_shift ? bf16r(bf16r(z - shift) * scale) : bf16r(z * scale);
+    out[i] = __float2bfloat16(z);
+  }
+}
+
+}  // namespace stb

@@ -274,3 +274,66 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     _lib.lib().stb_reset_launch_count()
+
+
+# ---------------------------------------------------------------------------------------------- VAE encode
+def conv3x3_nhwc(x, w9, bias=None, res=None, stride: int = 1, out=None):
+    """x [B,H,W,Ci] NHWC contiguous; w9 [Co, 9*Ci] tap-major; returns [B,Ho,Wo,Co]."""
+    _chk(x, "x"); _chk(w9, "w9")
+    assert x.is_contiguous() and w9.is_contiguous()
+    B, H, W, Ci = x.shape
+    Co = w9.shape[0]
+    assert w9.shape[1] == 9 * Ci
+    Ho, Wo = (H, W) if stride == 1 else (H // 2, W // 2)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Co), device=x.device, dtype=torch.bfloat16)
+    if res is not None:
+        assert res.is_contiguous() and res.shape == out.shape
+    check(_lib.lib().stb_conv3x3_nhwc(x.data_ptr(), w9.data_ptr(), _ptr(bias), _ptr(res), out.data_ptr(),
+                                      B, H, W, Ci, Co, stride, _stream()))
+    return out
+
+
+def conv_in_3ch(pixels, w, bias):
+    """pixels [B,3,H,W] NCHW bf16; w [C,3,3,3]; returns NHWC [B,H,W,C]."""
+    _chk(pixels, "pixels")
+    assert pixels.is_contiguous() and w.is_contiguous()
+    B, _, H, W = pixels.shape
+    C = w.shape[0]
+    out = torch.empty((B, H, W, C), device=pixels.device, dtype=torch.bfloat16)
+    check(_lib.lib().stb_conv_in_3ch(pixels.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, C, _stream()))
+    return out
+
+
+def groupnorm_nhwc(x, gamma, beta, groups: int = 32, eps: float = 1e-6, silu: bool = True, out=None):
+    """x [B, ..., C] NHWC contiguous."""
+    _chk(x, "x")
+    assert x.is_contiguous()
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    if out is None:
+        out = torch.empty_like(x)
+    stats = torch.empty((B * groups * 2,), device=x.device, dtype=torch.float32)
+    check(_lib.lib().stb_groupnorm_nhwc(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), stats.data_ptr(),
+                                        B, HW, C, groups, eps, int(silu), _stream()))
+    return out
+
+
+def softmax_rows_(s, scale: float):
+    """in-place softmax(scale * s) over the last dim of a contiguous [..., cols] bf16 tensor."""
+    _chk(s, "s")
+    assert s.is_contiguous()
+    cols = s.shape[-1]
+    check(_lib.lib().stb_softmax_rows(s.data_ptr(), cols, s.numel() // cols, cols, scale, _stream()))
+    return s
+
+
+def gaussian_sample_scale(moments_nhwc, eps_nchw, shift, scale):
+    """moments [B, h, w, 2L] NHWC; eps [B, L, h, w]; returns scaled latents [B, L, h, w]."""
+    B, h, w, L2 = moments_nhwc.shape
+    L = L2 // 2
+    assert moments_nhwc.is_contiguous() and eps_nchw.is_contiguous() and eps_nchw.shape == (B, L, h, w)
+    out = torch.empty((B, L, h, w), device=moments_nhwc.device, dtype=torch.bfloat16)
+    check(_lib.lib().stb_gaussian_sample_scale(moments_nhwc.data_ptr(), eps_nchw.data_ptr(), out.data_ptr(), B, L, h * w,
+                                               float(shift or 0.0), float(scale), int(shift is not None), _stream()))
+    return out

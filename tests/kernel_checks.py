@@ -338,3 +338,93 @@ CHECKS = {
 }
 CHECKS["skinny_r96"] = lambda: check_skinny(B=2, S=700, R=96, N=1536)
 CHECKS["skinny_r24"] = lambda: check_skinny(B=1, S=300, R=24, N=512)
+
+
+# --------------------------------------------------------------------------------------------- VAE encode kernels
+def check_conv3x3(B=2, H=24, W=40, Ci=64, Co=128, stride=1, bias=True, res=False):
+    import torch.nn.functional as F
+    x = _rand(B, H, W, Ci, seed=1)
+    w = _rand(Co, Ci, 3, 3, scale=(9 * Ci) ** -0.5, seed=2)
+    bv = _rand(Co, scale=0.1, seed=3) if bias else None
+    Ho, Wo = (H, W) if stride == 1 else (H // 2, W // 2)
+    rv = _rand(B, Ho, Wo, Co, seed=4) if res else None
+    w9 = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    out = ops.conv3x3_nhwc(x, w9, bv, rv, stride)
+    torch.cuda.synchronize()
+    xn = x.float().permute(0, 3, 1, 2)
+    if stride == 1:
+        ref = F.conv2d(xn, w.float(), bv.float() if bias else None, padding=1)
+    else:
+        ref = F.conv2d(F.pad(xn, (0, 1, 0, 1)), w.float(), bv.float() if bias else None, stride=2)
+    ref = ref.permute(0, 2, 3, 1)
+    if res:
+        ref = ref + rv.float()
+    return _report(f"conv3x3_s{stride}_{Ci}to{Co}_{H}x{W}", out, ref, atol=2e-2, rtol=1e-2)
+
+
+def check_conv_in(B=2, H=20, W=36, C=128):
+    import torch.nn.functional as F
+    x = _rand(B, 3, H, W, seed=1)
+    w = _rand(C, 3, 3, 3, scale=27 ** -0.5, seed=2)
+    bv = _rand(C, scale=0.1, seed=3)
+    out = ops.conv_in_3ch(x, w, bv)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), w.float(), bv.float(), padding=1).permute(0, 2, 3, 1)
+    return _report("conv_in_3ch", out, ref, atol=1e-2, rtol=1e-2)
+
+
+def check_groupnorm(B=2, H=16, W=24, C=128, G=32, silu=True, mean=0.0):
+    import torch.nn.functional as F
+    x = (_rand(B, H, W, C, seed=1).float() + mean).bfloat16()
+    gm = (1.0 + 0.1 * _rand(C, seed=2).float()).bfloat16()
+    bt = _rand(C, scale=0.1, seed=3)
+    out = ops.groupnorm_nhwc(x, gm, bt, G, 1e-6, silu)
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.float().permute(0, 3, 1, 2), G, gm.float(), bt.float(), 1e-6)
+    if silu:
+        ref = F.silu(ref)
+    return _report(f"groupnorm_C{C}_silu{int(silu)}_mean{mean}", out, ref.permute(0, 2, 3, 1), atol=2e-2, rtol=1e-2)
+
+
+def check_softmax_rows(rows=300, cols=1024, scale=0.0442):
+    s = _rand(rows, cols, scale=20.0, seed=1)
+    ref = torch.softmax(s.float() * scale, dim=-1)
+    ops.softmax_rows_(s, scale)
+    torch.cuda.synchronize()
+    return _report("softmax_rows", s, ref, atol=2e-3, rtol=1e-2)
+
+
+def check_gaussian_sample(B=2, L=16, h=12, w=20, shift=0.1159):
+    m = _rand(B, h, w, 2 * L, seed=1)
+    eps = _rand(B, L, h, w, seed=2)
+    out = ops.gaussian_sample_scale(m, eps, shift, 0.3611)
+    torch.cuda.synchronize()
+    mn = m.permute(0, 3, 1, 2)
+    mean, logvar = mn[:, :L], mn[:, L:]
+    z = mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * eps          # bf16 tensor ops, like diffusers
+    ref = (z - shift) * 0.3611 if shift is not None else z * 0.3611
+    r = _report("gaussian_sample_scale", out, ref, atol=0.0, rtol=0.0)
+    if not r["ok"]:  # exp() ulp differences may move a bf16 rounding; never more than 1 bf16 ulp
+        r2 = _report("gaussian_sample_scale", out, ref, atol=1e-3, rtol=2 ** -7)
+        r2["bit_exact"] = False
+        return r2
+    r["bit_exact"] = True
+    return r
+
+
+CHECKS.update({
+    "conv3x3_s1": lambda: check_conv3x3(),
+    "conv3x3_s1_res": lambda: check_conv3x3(Ci=128, Co=256, res=True),
+    "conv3x3_s1_wide": lambda: check_conv3x3(B=1, H=8, W=300, Ci=128, Co=128),
+    "conv3x3_s1_512": lambda: check_conv3x3(B=1, H=16, W=16, Ci=512, Co=512, res=True),
+    "conv3x3_out32": lambda: check_conv3x3(B=2, H=16, W=16, Ci=512, Co=32),
+    "conv3x3_s2": lambda: check_conv3x3(stride=2, Ci=128, Co=128),
+    "conv3x3_s2_wide": lambda: check_conv3x3(B=1, H=6, W=600, stride=2, Ci=64, Co=64),
+    "conv_in_3ch": lambda: check_conv_in(),
+    "groupnorm_silu": lambda: check_groupnorm(),
+    "groupnorm_plain_512": lambda: check_groupnorm(C=512, silu=False),
+    "groupnorm_256_offset": lambda: check_groupnorm(C=256, mean=3.0),
+    "softmax_rows": lambda: check_softmax_rows(),
+    "gaussian_sample": lambda: check_gaussian_sample(),
+    "gaussian_sample_noshift": lambda: check_gaussian_sample(shift=None),
+})
