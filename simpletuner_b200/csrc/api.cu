@@ -717,7 +717,7 @@ int stb_conv_in_3ch(const void* pixels, const void* w, const void* bias, void* o
 int stb_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, void* out, float* stats, int B, int HW,
                        int C, int G, float eps, int silu, void* stream) {
   if (int r = check_device()) return r;
-  if (C % 8 || C > 512 || G > 64 || C % G || ((C / G) != 4 && (C / G) % 8)) return fail(STB_ERR_ARG, "groupnorm_nhwc: unsupported C=%d G=%d", C, G);
+  if (C % 8 || C > 512 || G > 64 || C % G || (8 % (C / G) && (C / G) % 8)) return fail(STB_ERR_ARG, "groupnorm_nhwc: unsupported C=%d G=%d", C, G);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   STB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * G, st));
   const int chunks = std::max(1, std::min((HW + 255) / 256, (num_sms() * 4 + B - 1) / B));

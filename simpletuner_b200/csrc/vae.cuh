@@ -59,7 +59,7 @@ conv_in_3ch_kernel(const __nv_bfloat16* __restrict__ px, const __nv_bfloat16* __
 }
 
 // x: NHWC [B, HW, C]; stats: fp32 [B, G, 2] (zeroed by the caller).  grid = (chunks, B); each CTA reduces a
-// contiguous chunk of pixels for all channels; C <= 512, channels-per-group cpg = C / G (multiple of 2).
+// contiguous chunk of pixels for all channels; C <= 512, channels-per-group cpg = C / G in {1, 2, 4} or a multiple of 8.
 __global__ void __launch_bounds__(256)
 groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, int HW, int C, int G,
                        int pix_per_cta) {
@@ -77,26 +77,26 @@ groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ 
   const int r0 = threadIdx.x / vec_per_pix;
   if (r0 < rows_par) {
     const int v = threadIdx.x % vec_per_pix;
-    float f[8];
-    float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;  // two groups at most per 8-vector when cpg == 4
+    float f[8], a[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f, q[j] = 0.f;
     for (long long pix = p0 + r0; pix < p1; pix += rows_par) {
       unpack8(*reinterpret_cast<const uint4*>(xb + pix * C + v * 8), f);
-      if (cpg >= 8) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a0 += f[j], q0 += f[j] * f[j];
-      } else {  // cpg == 4: channels 0..3 -> group g, 4..7 -> group g + 1
-#pragma unroll
-        for (int j = 0; j < 4; ++j) a0 += f[j], q0 += f[j] * f[j];
-#pragma unroll
-        for (int j = 4; j < 8; ++j) a1 += f[j], q1 += f[j] * f[j];
-      }
+      for (int j = 0; j < 8; ++j) a[j] += f[j], q[j] += f[j] * f[j];
     }
-    const int g0 = (v * 8) / cpg;
-    atomicAdd(&s_sum[g0], a0);
-    atomicAdd(&s_sq[g0], q0);
-    if (cpg < 8) {
-      atomicAdd(&s_sum[g0 + 1], a1);
-      atomicAdd(&s_sq[g0 + 1], q1);
+    if (cpg >= 8) {  // the whole 8-vector belongs to one group
+      float sa = 0.f, sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sa += a[j], sq += q[j];
+      atomicAdd(&s_sum[(v * 8) / cpg], sa);
+      atomicAdd(&s_sq[(v * 8) / cpg], sq);
+    } else {  // cpg in {1, 2, 4}
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&s_sum[(v * 8 + j) / cpg], a[j]);
+        atomicAdd(&s_sq[(v * 8 + j) / cpg], q[j]);
+      }
     }
   }
   __syncthreads();

@@ -424,6 +424,7 @@ CHECKS.update({
     "groupnorm_silu": lambda: check_groupnorm(),
     "groupnorm_plain_512": lambda: check_groupnorm(C=512, silu=False),
     "groupnorm_256_offset": lambda: check_groupnorm(C=256, mean=3.0),
+    "groupnorm_c64": lambda: check_groupnorm(C=64),
     "softmax_rows": lambda: check_softmax_rows(),
     "gaussian_sample": lambda: check_gaussian_sample(),
     "gaussian_sample_noshift": lambda: check_gaussian_sample(shift=None),
