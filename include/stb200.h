@@ -151,6 +151,23 @@ int stb_flow_prep_pack(const void* latents, const void* noise, const float* sigm
 int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* noise, float* loss_out,
                       void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Epsilon / v-prediction families (PixArt, SDXL).
+ *   stb_ddpm_prep_pack  : noisy = (coef_a[b] * latents.float() + coef_b[b] * noise.float()).to(bf16), the
+ *                         DDPMScheduler.add_noise the reference calls in fp32 at common.py:5998-6002
+ *                         (coef_a = sqrt(alphas_cumprod[t]), coef_b = sqrt(1 - alphas_cumprod[t]), fp32 [B]);
+ *                         written unpacked [B,C,Hh,Ww] (optional) and 2x2-patchified [B, Hh/2*Ww/2, 4C]
+ *                         in (c, dy, dx) feature order = the flattened PatchEmbed conv weight (optional).
+ *   stb_target_mse_loss : mean_b [ w_b * mean_chw (pred.float() - target.float())^2 ]  (common.py:6376-6398,
+ *                         6426-6429; w = min-SNR weights or NULL) with pred in packed layout (layout as above:
+ *                         0 = (c,dy,dx), 1 = (dy,dx,c) "nhwpqc->nchpwq", pixart/transformer.py:763-782);
+ *                         target bf16 [B,C,Hh,Ww]; optional d loss / d pred (packed, bf16).
+ * ------------------------------------------------------------------------------------------- */
+int stb_ddpm_prep_pack(const void* latents, const void* noise, const float* coef_a, const float* coef_b, void* noisy,
+                       void* packed, int B, int C, int Hh, int Ww, void* stream);
+int stb_target_mse_loss(const void* pred_packed, const void* target, const float* weights, float* loss_out,
+                        void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, void* stream);
+
 /* y[b, s, :] = gate[b, :] * x[b, s, :]  — gradient of `gate * linear(...)` w.r.t. the linear output
  * (flux/transformer.py:464, 584, 652), applied before the dgrad GEMM. */
 int stb_gate_mul(const void* x, long long x_b, long long x_s, const void* gate, long long g_b, void* y,

@@ -530,6 +530,33 @@ int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* 
   return 0;
 }
 
+int stb_ddpm_prep_pack(const void* latents, const void* noise, const float* coef_a, const float* coef_b, void* noisy,
+                       void* packed, int B, int C, int Hh, int Ww, void* stream) {
+  if (int r = check_device()) return r;
+  if (packed && ((Hh & 1) || (Ww & 1))) return fail(STB_ERR_ARG, "latent H and W must be even for 2x2 patchify");
+  if (!noisy && !packed) return fail(STB_ERR_ARG, "ddpm_prep_pack: no output requested");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n = (long long)B * C * Hh * Ww;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 16);
+  stb::ddpm_prep_pack_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(latents), static_cast<const __nv_bfloat16*>(noise), coef_a, coef_b, static_cast<__nv_bfloat16*>(noisy), static_cast<__nv_bfloat16*>(packed), B, C, Hh, Ww);
+  STB_LAUNCH_CHECK("ddpm_prep_pack");
+  return 0;
+}
+
+int stb_target_mse_loss(const void* pred_packed, const void* target, const float* weights, float* loss_out,
+                        void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, void* stream) {
+  if (int r = check_device()) return r;
+  if (layout != 0 && layout != 1) return fail(STB_ERR_ARG, "target_mse_loss layout must be 0 (c,dy,dx) or 1 (dy,dx,c)");
+  if ((Hh & 1) || (Ww & 1)) return fail(STB_ERR_ARG, "latent H and W must be even for 2x2 patchify");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  STB_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  const long long n = (long long)B * C * Hh * Ww;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
+  stb::target_mse_loss_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pred_packed), static_cast<const __nv_bfloat16*>(target), weights, loss_out, static_cast<__nv_bfloat16*>(dpred_packed), grad_scale, B, C, Hh, Ww, layout);
+  STB_LAUNCH_CHECK("target_mse_loss");
+  return 0;
+}
+
 int stb_gate_mul(const void* x, long long x_b, long long x_s, const void* gate, long long g_b, void* y,
                  long long y_b, long long y_s, int B, int S, int D, void* stream) {
   if (int r = check_device()) return r;

@@ -469,6 +469,78 @@ flow_mse_loss_kernel(const __nv_bfloat16* __restrict__ pred_packed, const __nv_b
 }
 
 // ------------------------------------------------------------------------------------------------
+// epsilon / v-prediction families (PixArt, SDXL): DDPM forward-noising + 2x2 patchify, and the weighted MSE.
+// reference: common.py:5998-6002 — `noise_schedule.add_noise(latents.float(), input_noise.float(), timesteps)`
+// (diffusers DDPMScheduler.add_noise: sqrt(acp[t]) * x + sqrt(1 - acp[t]) * eps, fp32) `.to(weight_dtype)`.
+// coef_a / coef_b: fp32 [B] (the two gathered square roots).  Each fp32 op is rounded separately (no FMA
+// contraction) so the bf16 result is bit-identical to the eager chain.
+// packed feature order = (c, dy, dx): the flattened [D, C, 2, 2] PatchEmbed conv weight (diffusers PatchEmbed.proj).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ddpm_prep_pack_kernel(const __nv_bfloat16* __restrict__ lat, const __nv_bfloat16* __restrict__ noise,
+                      const float* __restrict__ coef_a, const float* __restrict__ coef_b,
+                      __nv_bfloat16* __restrict__ noisy, __nv_bfloat16* __restrict__ packed, int B, int C, int Hh,
+                      int Ww) {
+  const long long n = (long long)B * C * Hh * Ww;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int w = int(r % Ww); r /= Ww;
+    const int hh = int(r % Hh); r /= Hh;
+    const int c = int(r % C);
+    const int b = int(r / C);
+    const float v = __fadd_rn(__fmul_rn(coef_a[b], __bfloat162float(lat[i])),
+                              __fmul_rn(coef_b[b], __bfloat162float(noise[i])));
+    const __nv_bfloat16 vb = __float2bfloat16(v);
+    if (noisy) noisy[i] = vb;
+    if (packed) {
+      const int ph = hh >> 1, dy = hh & 1, pw = w >> 1, dx = w & 1;
+      const long long tok = (long long)ph * (Ww >> 1) + pw;
+      packed[((long long)b * ((Hh >> 1) * (Ww >> 1)) + tok) * (4 * C) + ((c * 2 + dy) * 2 + dx)] = vb;
+    }
+  }
+}
+
+// loss = mean_b [ w_b * mean_chw (pred.float() - target.float())^2 ]   (common.py:6376-6398, 6426-6429)
+// pred: packed tokens [B, (Hh/2)(Ww/2), 4C] (layout as flow_mse_loss_kernel); target: [B, C, Hh, Ww] bf16
+// (epsilon: the noise; v-prediction: get_velocity(...)); weights: fp32 [B] min-SNR weights or nullptr.
+__global__ void __launch_bounds__(256)
+target_mse_loss_kernel(const __nv_bfloat16* __restrict__ pred_packed, const __nv_bfloat16* __restrict__ target,
+                       const float* __restrict__ weights, float* __restrict__ loss_out,
+                       __nv_bfloat16* __restrict__ dpred_packed, float grad_scale, int B, int C, int Hh, int Ww,
+                       int layout) {
+  __shared__ float red[8];
+  const long long n = (long long)B * C * Hh * Ww;
+  const float inv = 1.f / float((long long)C * Hh * Ww) / float(B);
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int w = int(r % Ww); r /= Ww;
+    const int hh = int(r % Hh); r /= Hh;
+    const int c = int(r % C);
+    const int b = int(r / C);
+    const int ph = hh >> 1, dy = hh & 1, pw = w >> 1, dx = w & 1;
+    const long long tok = (long long)ph * (Ww >> 1) + pw;
+    const int feat = layout == 0 ? ((c * 2 + dy) * 2 + dx) : ((dy * 2 + dx) * C + c);
+    const long long pi = ((long long)b * ((Hh >> 1) * (Ww >> 1)) + tok) * (4 * C) + feat;
+    const float wgt = weights ? weights[b] : 1.f;
+    const float d = __bfloat162float(pred_packed[pi]) - __bfloat162float(target[i]);
+    acc += wgt * d * d;
+    if (dpred_packed) dpred_packed[pi] = __float2bfloat16(2.f * d * wgt * inv * grad_scale);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(loss_out, v * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LoRA weight gradients (rank r <= 64), reference: autograd through peft lora.Linear
 //   y = x W^T + s * (x A^T) B^T   =>   dA = s * (dY B)^T x ,  dB = s * dY^T (x A^T)
 // Generic "skinny" product:  Out[r, n] (+)= alpha * sum_m  L[m, r] * Rm[m, n]

@@ -79,11 +79,17 @@ class LoraPack:
     members: List[Optional[int]]  # index into the flat (A, B) parameter list, None = member not adapted
     n_out: int                    # rows per member
     rank_padded: int = 0          # per-member column block inside the stacks (rank rounded up to 8)
+    row_index: Optional[torch.Tensor] = None  # member-local output row -> row of the (head-dim padded) projection
+    col_index: Optional[torch.Tensor] = None  # input feature -> column of the (head-dim padded) activation
 
 
 def pack_lora(params: List[Optional[Tuple[torch.Tensor, torch.Tensor]]], n_out: int, k_in: int, scaling: float,
-              device, dtype=torch.bfloat16) -> Optional[LoraPack]:
-    """params[m] = (A [r, K], B [n_out, r]) or None for each member of the fused projection."""
+              device, dtype=torch.bfloat16, row_index: Optional[torch.Tensor] = None,
+              col_index: Optional[torch.Tensor] = None) -> Optional[LoraPack]:
+    """params[m] = (A [r, K], B [n_out, r]) or None for each member of the fused projection.
+
+    `n_out` / `k_in` are the sizes of the projection as the GEMM sees it; when heads are zero-padded (PixArt
+    head_dim 72 -> 128) `row_index` / `col_index` scatter the un-padded LoRA rows / columns into that layout."""
     present = [p for p in params if p is not None]
     if not present:
         return None
@@ -100,13 +106,17 @@ def pack_lora(params: List[Optional[Tuple[torch.Tensor, torch.Tensor]]], n_out: 
             members.append(None)
             continue
         a, b = p
-        a_stack[m * rp:m * rp + r].copy_(a.detach())
-        blk = b_ext[m * n_out:(m + 1) * n_out, m * rp:m * rp + r]
-        blk.copy_(b.detach())
-        if scaling != 1.0:
-            blk.mul_(scaling)
+        if col_index is None:
+            a_stack[m * rp:m * rp + r].copy_(a.detach())
+        else:
+            a_stack[m * rp:m * rp + r, col_index] = a.detach().to(dtype)
+        bs = b.detach().to(dtype) * scaling if scaling != 1.0 else b.detach().to(dtype)
+        if row_index is None:
+            b_ext[m * n_out:(m + 1) * n_out, m * rp:m * rp + r].copy_(bs)
+        else:
+            b_ext[m * n_out + row_index, m * rp:m * rp + r] = bs
         members.append(m)
-    return LoraPack(a_stack, _t(a_stack), b_ext, _t(b_ext), r, scaling, members, n_out, rp)
+    return LoraPack(a_stack, _t(a_stack), b_ext, _t(b_ext), r, scaling, members, n_out, rp, row_index, col_index)
 
 
 def _lora_down(x: torch.Tensor, pack: LoraPack) -> torch.Tensor:
@@ -127,6 +137,10 @@ def _lora_grads(pack: LoraPack, x: torch.Tensor, t_down: torch.Tensor, dy: torch
             continue
         da = d_a[m * rp:m * rp + r]
         dbt = d_bt[m * rp:m * rp + r, m * pack.n_out:(m + 1) * pack.n_out]
+        if pack.col_index is not None:
+            da = da[:, pack.col_index]
+        if pack.row_index is not None:
+            dbt = dbt[:, pack.row_index]
         db = dbt.t()
         if pack.scaling != 1.0:
             db = db * pack.scaling

@@ -243,6 +243,34 @@ def flow_mse_loss(pred_packed, latents, noise, want_grad: bool = True, grad_scal
     return loss, dpred
 
 
+def ddpm_prep_pack(latents, noise, coef_a, coef_b, want_unpacked: bool = True, want_packed: bool = True):
+    """noisy = (coef_a[b] * latents.float() + coef_b[b] * noise.float()).bf16 -> (noisy or None, packed (c,dy,dx) or None)."""
+    assert latents.is_contiguous() and noise.is_contiguous() and coef_a.dtype == torch.float32 and coef_b.dtype == torch.float32
+    _chk(latents, "latents"); _chk(noise, "noise")
+    B, Cc, Hh, Ww = latents.shape
+    noisy = torch.empty_like(latents) if want_unpacked else None
+    packed = torch.empty((B, (Hh // 2) * (Ww // 2), 4 * Cc), device=latents.device, dtype=torch.bfloat16) if want_packed else None
+    check(_lib.lib().stb_ddpm_prep_pack(latents.data_ptr(), noise.data_ptr(), coef_a.contiguous().data_ptr(),
+                                        coef_b.contiguous().data_ptr(), _ptr(noisy), _ptr(packed), B, Cc, Hh, Ww, _stream()))
+    return noisy, packed
+
+
+def target_mse_loss(pred_packed, target, weights=None, want_grad: bool = True, grad_scale: float = 1.0, layout: int = 1):
+    """mean_b[w_b * mean_chw (pred - target)^2]; pred packed [B, S, 4C], target [B,C,H,W] -> (loss [1] fp32, dpred or None)."""
+    assert pred_packed.is_contiguous() and target.is_contiguous()
+    _chk(pred_packed, "pred"); _chk(target, "target")
+    B, Cc, Hh, Ww = target.shape
+    assert pred_packed.shape[-1] == 4 * Cc
+    if weights is not None:
+        assert weights.dtype == torch.float32 and weights.numel() == B and weights.is_cuda
+        weights = weights.contiguous()
+    loss = torch.empty((1,), device=target.device, dtype=torch.float32)
+    dpred = torch.empty_like(pred_packed) if want_grad else None
+    check(_lib.lib().stb_target_mse_loss(pred_packed.data_ptr(), target.data_ptr(), _ptr(weights), loss.data_ptr(),
+                                         _ptr(dpred), grad_scale, B, Cc, Hh, Ww, layout, _stream()))
+    return loss, dpred
+
+
 def gate_mul(x, gate, out=None):
     """out[b, s, :] = gate[b, :] * x[b, s, :]."""
     _chk(x, "x"); _chk(gate, "gate")

@@ -429,3 +429,48 @@ CHECKS.update({
     "gaussian_sample": lambda: check_gaussian_sample(),
     "gaussian_sample_noshift": lambda: check_gaussian_sample(shift=None),
 })
+
+
+# --------------------------------------------------------------------------------------------- epsilon-family step kernels
+def check_ddpm_prep(B=3, C=4, Hh=16, Ww=24):
+    lat, noise = _rand(B, C, Hh, Ww, seed=1), _rand(B, C, Hh, Ww, seed=2)
+    ac = torch.cumprod(1 - torch.linspace(1e-4, 0.02, 1000), 0).to(DEV)
+    t = torch.tensor([3, 500, 999], device=DEV)[:B]
+    ca, cb = (ac[t] ** 0.5).contiguous(), ((1 - ac[t]) ** 0.5).contiguous()
+    noisy, packed = ops.ddpm_prep_pack(lat, noise, ca, cb)
+    torch.cuda.synchronize()
+    ref = (ca.view(-1, 1, 1, 1) * lat.float() + cb.view(-1, 1, 1, 1) * noise.float()).bfloat16()   # eager fp32 chain
+    refp = ref.view(B, C, Hh // 2, 2, Ww // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, -1, C * 4)
+    r = _report("ddpm_prep_pack", noisy, ref, atol=0.0, rtol=0.0)
+    r["packed_exact"] = bool(torch.equal(packed, refp))
+    r["ok"] = r["ok"] and r["packed_exact"]
+    return r
+
+
+def check_target_mse(B=3, C=4, Hh=16, Ww=24, weighted=True):
+    S = (Hh // 2) * (Ww // 2)
+    pred = _rand(B, S, 4 * C, seed=1).requires_grad_(False)
+    tgt = _rand(B, C, Hh, Ww, seed=2)
+    w = torch.tensor([0.5, 1.0, 2.5], device=DEV)[:B] if weighted else None
+    loss, dpred = ops.target_mse_loss(pred, tgt, w, layout=1)
+    torch.cuda.synchronize()
+    p32 = pred.float().requires_grad_(True)
+    un = torch.einsum("nhwpqc->nchpwq", p32.reshape(B, Hh // 2, Ww // 2, 2, 2, C)).reshape(B, C, Hh, Ww)
+    l = (un - tgt.float()) ** 2
+    if weighted:
+        l = l * w.view(-1, 1, 1, 1)
+    lref = l.mean(dim=[1, 2, 3]).mean()
+    lref.backward()
+    r = _report("target_mse_dpred", dpred, p32.grad, atol=1e-6, rtol=1e-2)
+    r["loss"], r["loss_ref"] = float(loss.item()), float(lref.item())
+    r["ok"] = r["ok"] and abs(r["loss"] - r["loss_ref"]) <= 1e-5 * abs(r["loss_ref"])
+    return r
+
+
+CHECKS.update({
+    "ddpm_prep_pack": lambda: check_ddpm_prep(),
+    "target_mse_weighted": lambda: check_target_mse(),
+    "target_mse_plain": lambda: check_target_mse(weighted=False),
+    "attn_fwd_cross_300": lambda: check_attn_fwd(2, 4, 1024, 300),
+    "attn_bwd_cross_300": lambda: check_attn_bwd(2, 4, 1024, 300),
+})
