@@ -145,11 +145,15 @@ int stb_qk_rmsnorm_rope_bwd(const void* dq, const void* dk, long long d_b, long 
  *                        (layout 0: Flux unpack_latents order, flux/__init__.py:33-44; layout 1: SD3
  *                        unpatchify order "nhwpqc->nchpwq", sd3/transformer.py:894); optional d loss/d pred.
  * latents/noise: bf16 [B, C, Hh, Ww] contiguous; sigmas fp32 [B]; loss_out fp32 [1] (zeroed here).
+ * loss_type (both loss entry points): 0 = l2, 1 = huber, 2 = smooth_l1 as `conditional_loss` defines them
+ * (common.py:6132-6166): huber = 2c(sqrt(d^2+c^2)-c), smooth_l1 = 2(sqrt(d^2+c^2)-c); huber_c = fp32 [B]
+ * per-sample c (constant or the scheduled value of common.py:6168-6215), may be NULL for l2.
  * ------------------------------------------------------------------------------------------- */
 int stb_flow_prep_pack(const void* latents, const void* noise, const float* sigmas, void* noisy,
                        void* packed, int B, int C, int Hh, int Ww, void* stream);
 int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* noise, float* loss_out,
-                      void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, void* stream);
+                      void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, int loss_type,
+                      const float* huber_c, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Epsilon / v-prediction families (PixArt, SDXL).
@@ -166,7 +170,8 @@ int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* 
 int stb_ddpm_prep_pack(const void* latents, const void* noise, const float* coef_a, const float* coef_b, void* noisy,
                        void* packed, int B, int C, int Hh, int Ww, void* stream);
 int stb_target_mse_loss(const void* pred_packed, const void* target, const float* weights, float* loss_out,
-                        void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, void* stream);
+                        void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, int loss_type,
+                        const float* huber_c, void* stream);
 
 /* y[b, s, :] = gate[b, :] * x[b, s, :]  — gradient of `gate * linear(...)` w.r.t. the linear output
  * (flux/transformer.py:464, 584, 652), applied before the dgrad GEMM. */

@@ -418,3 +418,47 @@ def flux_train_step_loss(P, cfg, batch, lora=None, lora_scale=1.0):
     pred = flux_model_predict(P, cfg, noisy, timesteps, batch["prompt_embeds"], batch["pooled"],
                               batch.get("guidance", 1.0), lora, lora_scale)
     return flow_loss(pred, flow_target(batch["latents"], batch["noise"])), pred
+
+
+# --------------------------------------------------------------------------------------------------
+# loss family (reference common.py:6132-6215, 6217-6430) — pinned against the reference's own `loss` executed
+# verbatim: tests/golden/loss_golden.pt (oracle/make_golden_loss.py), tests/test_loss_golden.py
+# --------------------------------------------------------------------------------------------------
+def conditional_loss(pred: Tensor, target: Tensor, loss_type: str = "l2", huber_c=0.1) -> Tensor:
+    """common.py:6132-6166 with reduction="none"; `huber_c` scalar or [B] (broadcast over the sample)."""
+    if loss_type == "l2":
+        return F.mse_loss(pred, target, reduction="none")
+    c = huber_c if not torch.is_tensor(huber_c) else huber_c.view(-1, *([1] * (pred.dim() - 1)))
+    k = 2 * c if loss_type == "huber" else 2.0
+    if loss_type not in ("huber", "smooth_l1"):
+        raise NotImplementedError(loss_type)
+    return k * (torch.sqrt((pred - target) ** 2 + c ** 2) - c)
+
+
+def scheduled_huber_c(timesteps: Tensor, base: float, schedule: str, prediction_type: str,
+                      alphas_cumprod: Optional[Tensor] = None, num_train_timesteps: int = 1000) -> Tensor:
+    """common.py:6168-6215."""
+    if schedule == "constant":
+        return torch.full((timesteps.numel(),), base)
+    if schedule == "exponential":
+        return torch.exp(-(-math.log(base) / num_train_timesteps) * timesteps).float()
+    if schedule == "snr":
+        if prediction_type == "flow_matching":
+            sig = timesteps / 1000
+            sig = ((1.0 - sig) / (sig + 0.0001)) ** 0.5
+        else:
+            sig = ((1.0 - alphas_cumprod[timesteps]) / alphas_cumprod[timesteps]) ** 0.5
+        return ((1 - base) / (1 + sig) ** 2 + base).float()
+    raise NotImplementedError(schedule)
+
+
+def model_loss(pred: Tensor, target: Tensor, loss_type: str = "l2", huber_c=0.1, weights: Optional[Tensor] = None,
+               snr_weight: float = 1.0) -> Tensor:
+    """common.py:6286 / 6376-6398 / 6426-6429: pointwise loss in fp32, optional per-sample (min-SNR) weights,
+    mean over (C, H, W) then over the batch."""
+    l = conditional_loss(pred.float(), target.float(), loss_type, huber_c)
+    if weights is not None:
+        l = l * weights.view(-1, 1, 1, 1)
+    elif loss_type == "l2":
+        l = snr_weight * l
+    return l.mean(dim=list(range(1, l.dim()))).mean()

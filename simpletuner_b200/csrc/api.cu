@@ -517,15 +517,23 @@ int stb_flow_prep_pack(const void* latents, const void* noise, const float* sigm
   return 0;
 }
 
+static int check_loss_type(int loss_type, const float* huber_c) {
+  if (loss_type < 0 || loss_type > 2) return fail(STB_ERR_ARG, "loss_type must be 0 (l2), 1 (huber) or 2 (smooth_l1)");
+  if (loss_type != 0 && !huber_c) return fail(STB_ERR_ARG, "huber / smooth_l1 need the per-sample huber_c array");
+  return 0;
+}
+
 int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* noise, float* loss_out,
-                      void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, void* stream) {
+                      void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, int loss_type,
+                      const float* huber_c, void* stream) {
   if (int r = check_device()) return r;
+  if (int r = check_loss_type(loss_type, huber_c)) return r;
   if (layout != 0 && layout != 1) return fail(STB_ERR_ARG, "flow_mse_loss layout must be 0 (Flux) or 1 (SD3)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   STB_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
   const long long n = (long long)B * C * Hh * Ww;
   const int grid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
-  stb::flow_mse_loss_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pred_packed), static_cast<const __nv_bfloat16*>(latents), static_cast<const __nv_bfloat16*>(noise), loss_out, static_cast<__nv_bfloat16*>(dpred_packed), grad_scale, B, C, Hh, Ww, layout);
+  stb::flow_mse_loss_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pred_packed), static_cast<const __nv_bfloat16*>(latents), static_cast<const __nv_bfloat16*>(noise), loss_out, static_cast<__nv_bfloat16*>(dpred_packed), grad_scale, B, C, Hh, Ww, layout, loss_type, huber_c);
   STB_LAUNCH_CHECK("flow_mse_loss");
   return 0;
 }
@@ -544,15 +552,17 @@ int stb_ddpm_prep_pack(const void* latents, const void* noise, const float* coef
 }
 
 int stb_target_mse_loss(const void* pred_packed, const void* target, const float* weights, float* loss_out,
-                        void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, void* stream) {
+                        void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, int loss_type,
+                        const float* huber_c, void* stream) {
   if (int r = check_device()) return r;
+  if (int r = check_loss_type(loss_type, huber_c)) return r;
   if (layout != 0 && layout != 1) return fail(STB_ERR_ARG, "target_mse_loss layout must be 0 (c,dy,dx) or 1 (dy,dx,c)");
   if ((Hh & 1) || (Ww & 1)) return fail(STB_ERR_ARG, "latent H and W must be even for 2x2 patchify");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   STB_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
   const long long n = (long long)B * C * Hh * Ww;
   const int grid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
-  stb::target_mse_loss_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pred_packed), static_cast<const __nv_bfloat16*>(target), weights, loss_out, static_cast<__nv_bfloat16*>(dpred_packed), grad_scale, B, C, Hh, Ww, layout);
+  stb::target_mse_loss_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pred_packed), static_cast<const __nv_bfloat16*>(target), weights, loss_out, static_cast<__nv_bfloat16*>(dpred_packed), grad_scale, B, C, Hh, Ww, layout, loss_type, huber_c);
   STB_LAUNCH_CHECK("target_mse_loss");
   return 0;
 }

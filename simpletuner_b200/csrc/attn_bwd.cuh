@@ -100,6 +100,10 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, __nv_bfloat16* gro
 // ------------------------------------------------------------------------------------------------
 // dK / dV
 // ------------------------------------------------------------------------------------------------
+// TMEM column (relative to the score buffer) of the packed bf16 operand chunk kk (16 of the 64 streamed rows):
+// chunks 0-1 are written by compute warpgroup 0 at columns 0-15, chunks 2-3 by warpgroup 1 at columns 32-47.
+#define PK_COL(kk) (uint32_t((kk) < 2 ? 8 * (kk) : 32 + 8 * ((kk) - 2)))
+
 template <int HD>
 __global__ void __launch_bounds__(384, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams p) {
@@ -152,7 +156,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
     for (int w = 0; w < 2; ++w) {
       mbar_init(st_full(w), 1);
       mbar_init(dpt_full(w), 1);
-      mbar_init(p_full(w), 128);
+      mbar_init(p_full(w), 256);   // both compute warpgroups contribute half the columns of every tile
       mbar_init(ds_full(w), 128);
     }
     mbar_init(acc_done, 1);
@@ -241,12 +245,12 @@ attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {  // contraction over the 64 query rows of the tile
           const uint64_t bd = sdesc_mn(do_smem(stg), kk * 2048, ATOM64);
-          mma_ts(DV, X(w) + 8 * kk, bd, idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
+          mma_ts(DV, X(w) + PK_COL(kk), bd, idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
         }
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t bd = sdesc_mn(q_smem(stg), kk * 2048, ATOM64);
-          mma_ts(DK, Y(w) + 8 * kk, bd, idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
+          mma_ts(DK, Y(w) + PK_COL(kk), bd, idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
         }
         tc_commit(qdo_empty(stg));
       }
@@ -257,42 +261,49 @@ attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
     __syncwarp();
   } else if (warp < 8) {
     // ===================== compute warpgroups =====================
-    const int w = warp >> 2;                       // warpgroup == TMEM score buffer
+    // Warpgroup w owns the 32-column half [32 w, 32 w + 32) of EVERY 64-wide score tile, so one tile's
+    // exp / dS phase is spread over all 8 compute warps (half the latency of a whole tile per warpgroup) and
+    // finishes inside the two MMA groups the tensor pipe has queued behind it.  Each half packs its bf16
+    // P^T / dS^T into the first 16 columns of its own fp32 range (PK_COL), never into the other half's.
+    const int w = warp >> 2;
     const int r = (warp & 3) * 32 + lane;          // key row within tile == TMEM lane
     const int wt = threadIdx.x & 127;              // thread within warpgroup
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const float sl2 = p.scale * 1.4426950408889634f;
     const float l2e = 1.4426950408889634f;
     const long long stat_base = ((long long)b * p.H + h) * p.Sq;
-    float* my_stat = stat_ptr + w * 256;           // [2 stages][lse 64 | delta 64]
-    auto load_stat = [&](int tile) -> float {
-      const int qi = tile * 64 + (wt & 63);
+    float* my_stat = stat_ptr + w * 256;           // [2 tile parities][lse 32 | delta 32 | unused 64]
+    auto load_stat = [&](int tile) -> float {      // threads 0-31: lse, 32-63: delta of this warpgroup's 32 queries
+      const int qi = tile * 64 + 32 * w + (wt & 31);
       const bool ok = qi < p.Sq;
-      return (wt < 64) ? (ok ? p.lse[stat_base + qi] * l2e : INFINITY) : (ok ? p.delta[stat_base + qi] : 0.f);
+      return (wt < 32) ? (ok ? p.lse[stat_base + qi] : INFINITY) : (ok ? p.delta[stat_base + qi] : 0.f);
     };
-    if (w < n_q) my_stat[wt] = load_stat(w);
+    if (wt < 64) {
+      if (0 < n_q) my_stat[wt] = load_stat(0) * (wt < 32 ? l2e : 1.f);
+      if (1 < n_q) my_stat[128 + wt] = load_stat(1) * (wt < 32 ? l2e : 1.f);
+    }
     named_bar_sync(1 + w, 128);
-    int it = 0;
-    for (int i = w; i < n_q; i += 2, ++it) {
-      const float* lse_s = my_stat + (it & 1) * 128;
-      const float* del_s = lse_s + 64;
-      const float nxt = (i + 2 < n_q) ? load_stat(i + 2) : 0.f;
-      mbar_wait(st_full(w), it & 1, 46);
-      mbar_wait(dpt_full(w), it & 1, 47);
+    for (int i = 0; i < n_q; ++i) {
+      const int buf = i & 1;
+      const float* lse_s = my_stat + buf * 128;
+      const float* del_s = lse_s + 32;
+      const bool pre = (i + 2 < n_q) && wt < 64;
+      const float nxt = pre ? load_stat(i + 2) : 0.f;   // consumed only after this tile's math (latency hidden)
+      mbar_wait(st_full(buf), (i >> 1) & 1, 46);
+      mbar_wait(dpt_full(buf), (i >> 1) & 1, 47);
       tc_fence_after();
       // one pass: P^T = exp2(S^T*sl2 - lse), dS^T = P^T o (dP^T - Delta)  (the softmax scale of dS is
       // applied once to the dK accumulator in the epilogue)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t sv[32], dv[32];
-        tmem_ld_32x32b_x32(X(w) + lane_off + 32 * c, sv);
-        tmem_ld_32x32b_x32(Y(w) + lane_off + 32 * c, dv);
+        tmem_ld_32x32b_x32(X(buf) + lane_off + 32 * w, sv);
+        tmem_ld_32x32b_x32(Y(buf) + lane_off + 32 * w, dv);
         tc_wait_ld();
         uint32_t pk[16], dk_[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(lse_s + 32 * c + j);   // smem broadcast
-          const float4 d4 = *reinterpret_cast<const float4*>(del_s + 32 * c + j);
+          const float4 l4 = *reinterpret_cast<const float4*>(lse_s + j);   // smem broadcast
+          const float4 d4 = *reinterpret_cast<const float4*>(del_s + j);
           const float x0 = ex2f(fmaf(__uint_as_float(sv[j + 0]), sl2, -l4.x));
           const float x1 = ex2f(fmaf(__uint_as_float(sv[j + 1]), sl2, -l4.y));
           const float x2 = ex2f(fmaf(__uint_as_float(sv[j + 2]), sl2, -l4.z));
@@ -302,14 +313,14 @@ attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
           dk_[j / 2] = pack_bf16x2(x0 * (__uint_as_float(dv[j + 0]) - d4.x), x1 * (__uint_as_float(dv[j + 1]) - d4.y));
           dk_[j / 2 + 1] = pack_bf16x2(x2 * (__uint_as_float(dv[j + 2]) - d4.z), x3 * (__uint_as_float(dv[j + 3]) - d4.w));
         }
-        tmem_st_32x32b_x16(X(w) + lane_off + 16 * c, pk);
-        tmem_st_32x32b_x16(Y(w) + lane_off + 16 * c, dk_);
+        tmem_st_32x32b_x16(X(buf) + lane_off + 32 * w, pk);
+        tmem_st_32x32b_x16(Y(buf) + lane_off + 32 * w, dk_);
       }
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(p_full(w));
-      if (i + 2 < n_q) my_stat[((it + 1) & 1) * 128 + wt] = nxt;
-      named_bar_sync(1 + w, 128);
+      mbar_arrive(p_full(buf));
+      named_bar_sync(1 + w, 128);                      // every thread of the warpgroup is done with this parity's stats
+      if (pre) my_stat[buf * 128 + wt] = nxt * (wt < 32 ? l2e : 1.f);   // tile i + 2 reuses parity buf; read after the next sync
     }
     // ---- epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK
     mbar_wait(acc_done, 0, 48);
@@ -382,7 +393,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
     for (int w = 0; w < 2; ++w) {
       mbar_init(s_full(w), 1);
       mbar_init(dp_full(w), 1);
-      mbar_init(ds_full(w), 128);
+      mbar_init(ds_full(w), 256);   // both compute warpgroups contribute half the columns of every tile
     }
     mbar_init(dq_done, 1);
     fence_mbar_init();
@@ -468,7 +479,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {  // contraction over the 64 keys of the tile
           const uint64_t bd = sdesc_mn(k_smem(stg), kk * 2048, ATOM64);
-          mma_ts(DQ, Yb(w) + 8 * kk, bd, idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
+          mma_ts(DQ, Yb(w) + PK_COL(kk), bd, idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
         }
         tc_commit(kv_empty(stg));
       }
@@ -487,22 +498,22 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
     const long long stat_idx = ((long long)b * p.H + h) * p.Sq + qrow;
     const float lse2 = row_ok ? p.lse[stat_idx] * 1.4426950408889634f : INFINITY;
     const float delta = row_ok ? p.delta[stat_idx] : 0.f;
-    int it = 0;
-    for (int j = w; j < n_kv; j += 2, ++it) {
-      const int kv_valid = p.Sk - j * 64;  // < 64 only on the ragged last tile
-      mbar_wait(s_full(w), it & 1, 55);
-      mbar_wait(dp_full(w), it & 1, 56);
+    // warpgroup w owns key columns [32 w, 32 w + 32) of EVERY 64-key tile (see attn_bwd_dkdv_kernel)
+    for (int j = 0; j < n_kv; ++j) {
+      const int buf = j & 1;
+      const int kv_valid = p.Sk - j * 64 - 32 * w;  // < 32 only on the ragged last tile
+      mbar_wait(s_full(buf), (j >> 1) & 1, 55);
+      mbar_wait(dp_full(buf), (j >> 1) & 1, 56);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t sv[32], dv[32];
-        tmem_ld_32x32b_x32(Sb(w) + lane_off + 32 * c, sv);
-        tmem_ld_32x32b_x32(Yb(w) + lane_off + 32 * c, dv);
+        tmem_ld_32x32b_x32(Sb(buf) + lane_off + 32 * w, sv);
+        tmem_ld_32x32b_x32(Yb(buf) + lane_off + 32 * w, dv);
         tc_wait_ld();
-        if (kv_valid < 64) {
+        if (kv_valid < 32) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (32 * c + i >= kv_valid) sv[i] = 0xff800000u;  // -inf -> P = 0
+            if (i >= kv_valid) sv[i] = 0xff800000u;  // -inf -> P = 0
         }
         uint32_t pk[16];
 #pragma unroll
@@ -513,11 +524,11 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
           const float d1 = p1 * (__uint_as_float(dv[i + 1]) - delta);
           pk[i / 2] = pack_bf16x2(d0, d1);
         }
-        tmem_st_32x32b_x16(Yb(w) + lane_off + 16 * c, pk);
+        tmem_st_32x32b_x16(Yb(buf) + lane_off + 32 * w, pk);
       }
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(ds_full(w));
+      mbar_arrive(ds_full(buf));
     }
     mbar_wait(dq_done, 0, 57);
     tc_fence_after();

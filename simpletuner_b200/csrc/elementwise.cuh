@@ -424,6 +424,27 @@ flow_prep_pack_kernel(const __nv_bfloat16* __restrict__ lat, const __nv_bfloat16
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pointwise loss of reference `conditional_loss` (common.py:6132-6166) on d = pred - target (fp32):
+//   l2        : d^2                                   grad 2 d
+//   huber     : 2 c (sqrt(d^2 + c^2) - c)             grad 2 c d / sqrt(d^2 + c^2)
+//   smooth_l1 : 2   (sqrt(d^2 + c^2) - c)             grad 2   d / sqrt(d^2 + c^2)
+// c = huber_c of the sample (constant or scheduled per timestep, common.py:6168-6215).
+// ------------------------------------------------------------------------------------------------
+enum LossType : int { LOSS_L2 = 0, LOSS_HUBER = 1, LOSS_SMOOTH_L1 = 2 };
+
+__device__ __forceinline__ void pointwise_loss(float d, int loss_type, float c, float& val, float& grad) {
+  if (loss_type == LOSS_L2) {
+    val = d * d;
+    grad = 2.f * d;
+    return;
+  }
+  const float k = loss_type == LOSS_HUBER ? 2.f * c : 2.f;
+  const float r = sqrtf(d * d + c * c);
+  val = k * (r - c);
+  grad = k * d / r;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Loss: mean over batch of mean over (C,H,W) of (pred.float() - target.float())^2 with
 // target = noise - latents (flow matching, common.py:4610-4611, 6286, 6426-6429), where pred arrives
 // in the packed token layout (unpack_latents, flux/__init__.py:33-44, folded into the index math).
@@ -434,7 +455,7 @@ __global__ void __launch_bounds__(256)
 flow_mse_loss_kernel(const __nv_bfloat16* __restrict__ pred_packed, const __nv_bfloat16* __restrict__ lat,
                      const __nv_bfloat16* __restrict__ noise, float* __restrict__ loss_out,
                      __nv_bfloat16* __restrict__ dpred_packed, float grad_scale, int B, int C, int Hh,
-                     int Ww, int layout) {
+                     int Ww, int layout, int loss_type, const float* __restrict__ huber_c) {
   __shared__ float red[8];
   const long long n = (long long)B * C * Hh * Ww;
   const float inv = 1.f / float((long long)C * Hh * Ww) / float(B);
@@ -454,8 +475,10 @@ flow_mse_loss_kernel(const __nv_bfloat16* __restrict__ pred_packed, const __nv_b
     // target = noise - latents computed in the latent dtype (bf16 tensor), then .float()
     const float tgt = bf16r(__bfloat162float(noise[i]) - __bfloat162float(lat[i]));
     const float d = __bfloat162float(pred_packed[pi]) - tgt;
-    acc += d * d;
-    if (dpred_packed) dpred_packed[pi] = __float2bfloat16(2.f * d * inv * grad_scale);
+    float lv, lg;
+    pointwise_loss(d, loss_type, huber_c ? huber_c[b] : 0.f, lv, lg);
+    acc += lv;
+    if (dpred_packed) dpred_packed[pi] = __float2bfloat16(lg * inv * grad_scale);
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -508,7 +531,7 @@ __global__ void __launch_bounds__(256)
 target_mse_loss_kernel(const __nv_bfloat16* __restrict__ pred_packed, const __nv_bfloat16* __restrict__ target,
                        const float* __restrict__ weights, float* __restrict__ loss_out,
                        __nv_bfloat16* __restrict__ dpred_packed, float grad_scale, int B, int C, int Hh, int Ww,
-                       int layout) {
+                       int layout, int loss_type, const float* __restrict__ huber_c) {
   __shared__ float red[8];
   const long long n = (long long)B * C * Hh * Ww;
   const float inv = 1.f / float((long long)C * Hh * Ww) / float(B);
@@ -526,8 +549,10 @@ target_mse_loss_kernel(const __nv_bfloat16* __restrict__ pred_packed, const __nv
     const long long pi = ((long long)b * ((Hh >> 1) * (Ww >> 1)) + tok) * (4 * C) + feat;
     const float wgt = weights ? weights[b] : 1.f;
     const float d = __bfloat162float(pred_packed[pi]) - __bfloat162float(target[i]);
-    acc += wgt * d * d;
-    if (dpred_packed) dpred_packed[pi] = __float2bfloat16(2.f * d * wgt * inv * grad_scale);
+    float lv, lg;
+    pointwise_loss(d, loss_type, huber_c ? huber_c[b] : 0.f, lv, lg);
+    acc += wgt * lv;
+    if (dpred_packed) dpred_packed[pi] = __float2bfloat16(lg * wgt * inv * grad_scale);
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;

@@ -513,8 +513,9 @@ class FlowLossFn(torch.autograd.Function):
     """loss = mean_b mean_chw (unpack(pred) - (noise - latents))^2 ; backward = precomputed d loss/d pred."""
 
     @staticmethod
-    def forward(ctx, pred_packed, latents, noise, layout=0):
-        loss, dpred = ops.flow_mse_loss(pred_packed.contiguous(), latents, noise, want_grad=True, layout=layout)
+    def forward(ctx, pred_packed, latents, noise, layout=0, loss_type="l2", huber_c=None):
+        loss, dpred = ops.flow_mse_loss(pred_packed.contiguous(), latents, noise, want_grad=True, layout=layout,
+                                        loss_type=loss_type, huber_c=huber_c)
         ctx.save_for_backward(dpred)
         return loss[0]
 
@@ -522,4 +523,4 @@ class FlowLossFn(torch.autograd.Function):
     def backward(ctx, g):
         (dpred,) = ctx.saved_tensors
         # g is the scalar upstream gradient (1.0 for loss.backward()); keep it on-device
-        return (dpred * g.to(dpred.dtype)), None, None, None
+        return (dpred * g.to(dpred.dtype)), None, None, None, None, None

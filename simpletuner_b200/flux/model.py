@@ -33,7 +33,7 @@ def default_config(**over) -> SimpleNamespace:
         flow_matching=True, flow_schedule_shift=3.0, flow_schedule_auto_shift=False, flow_sigmoid_scale=1.0,
         flow_use_uniform_schedule=False, flow_use_beta_schedule=False, flux_fast_schedule=False,
         flux_guidance_mode="constant", flux_guidance_value=1.0,
-        input_perturbation=0.0, offset_noise=False, loss_type="l2", snr_gamma=None,
+        input_perturbation=0.0, offset_noise=False, loss_type="l2", huber_c=0.1, huber_schedule="constant", snr_gamma=None,
         lora_rank=16, lora_alpha=None, lora_dropout=0.0, flux_lora_target="all",
         flux_attention_masked_training=False,
     )
@@ -153,10 +153,24 @@ class Flux:
     def loss(self, prepared_batch: Dict[str, Any], model_output: Dict[str, Any], apply_conditioning_mask: bool = True):
         """common.py:6217-6430, flow-matching / l2 branch: target = noise - latents (common.py:4610-4611),
         mse in fp32, mean over (C,H,W) then over the batch."""
+        return FlowLossFn.apply(model_output["model_prediction"], prepared_batch["latents"], prepared_batch["noise"],
+                                self.LOSS_LAYOUT, *self._loss_kind(prepared_batch))
+
+    LOSS_LAYOUT = 0   # packed prediction feature order: 0 = (c, dy, dx) Flux, 1 = (dy, dx, c) SD3 / PixArt
+
+    def _loss_kind(self, prepared_batch):
+        """loss_type / per-sample huber_c (common.py:6230-6284).  For flow matching the reference ignores snr_gamma."""
         c = self.config
-        if c.loss_type != "l2" or c.snr_gamma:
-            raise NotImplementedError("only loss_type='l2' without SNR weighting is implemented (reference defaults)")
-        return FlowLossFn.apply(model_output["model_prediction"], prepared_batch["latents"], prepared_batch["noise"])
+        lt = getattr(c, "loss_type", "l2")
+        if lt == "l2":
+            return "l2", None
+        if lt not in ("huber", "smooth_l1"):
+            raise NotImplementedError(f"Unsupported Loss Type {lt}")
+        from ..training.noise import compute_scheduled_huber_c
+        # NB: Flux.model_predict has overwritten `timesteps` with t / 1000 (flux/model.py:739-745) before loss() runs; the
+        # reference feeds those scaled values to compute_scheduled_huber_c as they are, and so does this mirror.
+        t = prepared_batch["timesteps"]
+        return lt, compute_scheduled_huber_c(c, self.noise_schedule, t.to(self.accelerator.device), self.PREDICTION_TYPE)
 
     def loss_with_logs(self, prepared_batch, model_output, apply_conditioning_mask: bool = True):
         return self.loss(prepared_batch, model_output, apply_conditioning_mask), None

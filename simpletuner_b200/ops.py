@@ -232,14 +232,34 @@ def flow_prep_pack(latents, noise, sigmas, want_unpacked: bool = True):
     return noisy, packed
 
 
-def flow_mse_loss(pred_packed, latents, noise, want_grad: bool = True, grad_scale: float = 1.0, layout: int = 0):
-    """Returns (loss fp32 scalar tensor [1], dpred_packed or None)."""
+LOSS_TYPES = {"l2": 0, "huber": 1, "smooth_l1": 2}
+
+
+def _huber_arg(loss_type, huber_c, B, device):
+    lt = LOSS_TYPES[loss_type] if isinstance(loss_type, str) else int(loss_type)
+    if lt == 0:
+        return lt, None
+    if huber_c is None:
+        raise ValueError("huber / smooth_l1 need huber_c")
+    if not torch.is_tensor(huber_c):
+        huber_c = torch.full((B,), float(huber_c), dtype=torch.float32)
+    huber_c = huber_c.to(device=device, dtype=torch.float32).reshape(-1)
+    if huber_c.numel() == 1:
+        huber_c = huber_c.expand(B)
+    assert huber_c.numel() == B
+    return lt, huber_c.contiguous()
+
+
+def flow_mse_loss(pred_packed, latents, noise, want_grad: bool = True, grad_scale: float = 1.0, layout: int = 0,
+                  loss_type="l2", huber_c=None):
+    """Returns (loss fp32 scalar tensor [1], dpred_packed or None).  loss_type: "l2" | "huber" | "smooth_l1"."""
     assert pred_packed.is_contiguous() and latents.is_contiguous() and noise.is_contiguous()
     B, Cc, Hh, Ww = latents.shape
+    lt, hc = _huber_arg(loss_type, huber_c, B, latents.device)
     loss = torch.empty((1,), device=latents.device, dtype=torch.float32)
     dpred = torch.empty_like(pred_packed) if want_grad else None
     check(_lib.lib().stb_flow_mse_loss(pred_packed.data_ptr(), latents.data_ptr(), noise.data_ptr(),
-                                       loss.data_ptr(), _ptr(dpred), grad_scale, B, Cc, Hh, Ww, layout, _stream()))
+                                       loss.data_ptr(), _ptr(dpred), grad_scale, B, Cc, Hh, Ww, layout, lt, _ptr(hc), _stream()))
     return loss, dpred
 
 
@@ -255,7 +275,8 @@ def ddpm_prep_pack(latents, noise, coef_a, coef_b, want_unpacked: bool = True, w
     return noisy, packed
 
 
-def target_mse_loss(pred_packed, target, weights=None, want_grad: bool = True, grad_scale: float = 1.0, layout: int = 1):
+def target_mse_loss(pred_packed, target, weights=None, want_grad: bool = True, grad_scale: float = 1.0, layout: int = 1,
+                    loss_type="l2", huber_c=None):
     """mean_b[w_b * mean_chw (pred - target)^2]; pred packed [B, S, 4C], target [B,C,H,W] -> (loss [1] fp32, dpred or None)."""
     assert pred_packed.is_contiguous() and target.is_contiguous()
     _chk(pred_packed, "pred"); _chk(target, "target")
@@ -264,10 +285,11 @@ def target_mse_loss(pred_packed, target, weights=None, want_grad: bool = True, g
     if weights is not None:
         assert weights.dtype == torch.float32 and weights.numel() == B and weights.is_cuda
         weights = weights.contiguous()
+    lt, hc = _huber_arg(loss_type, huber_c, B, target.device)
     loss = torch.empty((1,), device=target.device, dtype=torch.float32)
     dpred = torch.empty_like(pred_packed) if want_grad else None
     check(_lib.lib().stb_target_mse_loss(pred_packed.data_ptr(), target.data_ptr(), _ptr(weights), loss.data_ptr(),
-                                         _ptr(dpred), grad_scale, B, Cc, Hh, Ww, layout, _stream()))
+                                         _ptr(dpred), grad_scale, B, Cc, Hh, Ww, layout, lt, _ptr(hc), _stream()))
     return loss, dpred
 
 

@@ -41,15 +41,16 @@ def default_config(**over) -> SimpleNamespace:
 
 class _TargetLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred_packed, target, weights, snr_weight):
-        loss, dpred = ops.target_mse_loss(pred_packed.contiguous(), target, weights, want_grad=True, grad_scale=snr_weight, layout=1)
+    def forward(ctx, pred_packed, target, weights, snr_weight, loss_type="l2", huber_c=None):
+        loss, dpred = ops.target_mse_loss(pred_packed.contiguous(), target, weights, want_grad=True, grad_scale=snr_weight,
+                                          layout=1, loss_type=loss_type, huber_c=huber_c)
         ctx.save_for_backward(dpred)
         return loss[0] * snr_weight if snr_weight != 1.0 else loss[0]
 
     @staticmethod
     def backward(ctx, g):
         (dpred,) = ctx.saved_tensors
-        return dpred * g.to(dpred.dtype), None, None, None
+        return dpred * g.to(dpred.dtype), None, None, None, None, None
 
 
 class PixartSigma(Flux):
@@ -57,6 +58,7 @@ class PixartSigma(Flux):
     PREDICTION_TYPE = "epsilon"
     LATENT_CHANNEL_COUNT = 4
     DEFAULT_LORA_TARGET = PIXART_LORA_TARGETS
+    LOSS_LAYOUT = 1
 
     def __init__(self, config: Optional[SimpleNamespace] = None, transformer: Optional[PixArtTransformer2DModel] = None,
                  device: Optional[torch.device] = None, **transformer_kwargs):
@@ -163,10 +165,12 @@ class PixartSigma(Flux):
 
     def loss(self, prepared_batch, model_output, apply_conditioning_mask: bool = True):
         c = self.config
-        if c.loss_type != "l2":
-            raise NotImplementedError("only loss_type='l2' is implemented (reference default)")
+        lt, hc = self._loss_kind(prepared_batch)
+        # common.py:6376-6398: `snr_weight` multiplies the plain-l2 branch only; huber / smooth_l1 and the min-SNR
+        # branch do not apply it
+        snr_w = float(c.snr_weight) if (lt == "l2" and not c.snr_gamma) else 1.0
         weights = None
         if c.snr_gamma:
             weights = min_snr_loss_weights(prepared_batch["timesteps"].to(self.accelerator.device), self.noise_schedule,
                                            c.snr_gamma, self.PREDICTION_TYPE).float()
-        return _TargetLossFn.apply(model_output["model_prediction"], prepared_batch["noise"], weights, float(c.snr_weight))
+        return _TargetLossFn.apply(model_output["model_prediction"], prepared_batch["noise"], weights, snr_w, lt, hc)

@@ -57,8 +57,4 @@ class SD3(Flux):
         o = model_output["model_prediction"].reshape(B, Hh // 2, Ww // 2, 2, 2, Cc)
         return torch.einsum("nhwpqc->nchpwq", o).reshape(B, Cc, Hh, Ww)
 
-    def loss(self, prepared_batch, model_output, apply_conditioning_mask: bool = True):
-        c = self.config
-        if c.loss_type != "l2" or c.snr_gamma:
-            raise NotImplementedError("only loss_type='l2' without SNR weighting is implemented (reference defaults)")
-        return FlowLossFn.apply(model_output["model_prediction"], prepared_batch["latents"], prepared_batch["noise"], 1)
+    LOSS_LAYOUT = 1

@@ -9,6 +9,7 @@ that live in the reference repo bit-exactly against its own source (tests/golden
 """
 from __future__ import annotations
 
+import math
 from types import SimpleNamespace
 from typing import Optional, Sequence
 
@@ -52,6 +53,29 @@ def min_snr_loss_weights(timesteps: torch.Tensor, noise_scheduler, snr_gamma: fl
     if prediction_type == "v_prediction":
         return w / (snr + 1)
     return w / snr
+
+
+def compute_scheduled_huber_c(config, noise_scheduler, timesteps: torch.Tensor, prediction_type: str) -> torch.Tensor:
+    """common.py:6168-6215, vectorised over the batch: per-sample `huber_c` (fp32 [B]) for loss_type huber / smooth_l1.
+    The reference evaluates it one sample at a time (`timesteps[i:i+1]` -> `.item()`, common.py:6262-6266, 6334-6338);
+    the values are identical, the B host syncs are not reproduced."""
+    base = float(getattr(config, "huber_c", 0.1))
+    schedule = getattr(config, "huber_schedule", "constant")
+    t = timesteps.reshape(-1)
+    if schedule == "constant":
+        return torch.full((t.numel(),), base, dtype=torch.float32, device=t.device)
+    if schedule == "exponential":
+        alpha = -math.log(base) / noise_scheduler.config.num_train_timesteps
+        return torch.exp(-alpha * t).float()
+    if schedule == "snr":
+        if prediction_type == "flow_matching":
+            sig = t / 1000
+            sig = ((1.0 - sig) / (sig + 0.0001)) ** 0.5
+        else:
+            ac = noise_scheduler.alphas_cumprod.to(t.device)[t]
+            sig = ((1.0 - ac) / ac) ** 0.5
+        return ((1 - base) / (1 + sig) ** 2 + base).float()
+    raise NotImplementedError(f"Unknown Huber loss schedule {schedule}")
 
 
 def add_noise(noise_scheduler, original: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
