@@ -15,7 +15,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 CSRC = _HERE / "csrc"
 LIB_DIR = _HERE / "_C"
-LIB_PATH = LIB_DIR / "libstb200.so"
+LIB_PATH = Path(os.environ["STB200_LIB"]) if os.environ.get("STB200_LIB") else LIB_DIR / "libstb200.so"  # override: experiments only
 INCLUDE = _HERE.parent / "include" / "stb200.h"
 
 NVCC_FLAGS = [

@@ -180,9 +180,9 @@ int set_smem(K kernel, int bytes) {
 }
 
 // ---------------------------------------------------------------- GEMM
-template <int MT, int BN>
+template <int MT, int BN, bool PAIR = false>
 int launch_gemm(const stb_gemm_args* a, cudaStream_t st) {
-  using Cfg = stb::GemmCfg<MT, BN>;
+  using Cfg = typename std::conditional<PAIR, stb::GemmPairCfg<BN>, stb::GemmCfg<MT, BN>>::type;
   stb::GemmMaps maps;
   std::memset(&maps, 0, sizeof maps);
   stb::GemmParams p;
@@ -198,7 +198,7 @@ int launch_gemm(const stb_gemm_args* a, cudaStream_t st) {
     if (int r = make_map(&maps.a[s], g.a, 3, ad, as, ab)) return r;
     unsigned long long wd[2] = {(unsigned long long)g.K, (unsigned long long)a->N};
     unsigned long long ws[1] = {(unsigned long long)g.w_row_stride * 2ull};
-    unsigned wb[2] = {64, (unsigned)BN};
+    unsigned wb[2] = {64, (unsigned)(PAIR ? BN / 2 : BN)};   // pair: each CTA stages half of the W rows
     if (int r = make_map(&maps.w[s], g.w, 2, wd, ws, wb)) return r;
     p.kblocks[s] = (g.K + 63) / 64;
     int rem = g.K - (p.kblocks[s] - 1) * 64;
@@ -223,7 +223,7 @@ int launch_gemm(const stb_gemm_args* a, cudaStream_t st) {
   p.aux_batch_stride = a->aux_batch_stride;
   p.aux_row_stride = a->aux_row_stride;
 
-  auto kernel = stb::gemm_bf16_tn_kernel<MT, BN>;
+  auto kernel = stb::gemm_bf16_tn_kernel<MT, BN, false, PAIR>;
   static bool configured = false;
   if (!configured) {
     if (int r = set_smem(kernel, Cfg::SMEM_BYTES)) return r;
@@ -232,10 +232,31 @@ int launch_gemm(const stb_gemm_args* a, cudaStream_t st) {
   const int tiles_m = ((a->rows_per_batch + Cfg::BM - 1) / Cfg::BM) * a->num_batches;
   const int tiles_n = (a->N + BN - 1) / BN;
   const long long tiles = (long long)tiles_m * tiles_n;
-  const int grid = (int)std::min<long long>(tiles, num_sms());
-  kernel<<<grid, 256, Cfg::SMEM_BYTES, st>>>(maps, p);
-  STB_LAUNCH_CHECK("gemm_bf16_tn");
-  return 0;
+  if constexpr (PAIR) {
+    // one 2-CTA cluster (a TPC's two SMs) per 256 x BN tile stream
+    const int clusters = (int)std::min<long long>(tiles, num_sms() / 2);
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    STB_CUDA(cudaLaunchKernelEx(&cfg, kernel, maps, p));
+    g_launches.fetch_add(1);
+    return 0;
+  } else {
+    const int grid = (int)std::min<long long>(tiles, num_sms());
+    kernel<<<grid, 256, Cfg::SMEM_BYTES, st>>>(maps, p);
+    STB_LAUNCH_CHECK("gemm_bf16_tn");
+    return 0;
+  }
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -312,6 +333,7 @@ int stb_gemm_bf16(const stb_gemm_args* a, void* stream) {
     const long long t2 = (long long)((a->rows_per_batch + 255) / 256) * a->num_batches * ((a->N + bn - 1) / bn);
     mt = (bn >= 128 && t2 >= 2ll * num_sms() && fill(2) >= 0.98 * fill(1)) ? 2 : 1;
   }
+  if (mt == 3 && bn == 256) return launch_gemm<1, 256, true>(a, st);   // CTA-pair (cta_group::2) 256 x 256 tile
   if (mt == 1 && bn == 256) return launch_gemm<1, 256>(a, st);
   if (mt == 2 && bn == 256) return launch_gemm<2, 256>(a, st);
   if (mt == 1 && bn == 128) return launch_gemm<1, 128>(a, st);
@@ -404,6 +426,10 @@ int stb_attn_bwd(const stb_attn_bwd_args* a, void* stream) {
   p.dq_b = a->dq_b; p.dq_s = a->dq_s; p.dq_h = a->dq_h;
   p.dk_b = a->dk_b; p.dk_s = a->dk_s; p.dk_h = a->dk_h;
   p.dv_b = a->dv_b; p.dv_s = a->dv_s; p.dv_h = a->dv_h;
+  p.q = static_cast<const __nv_bfloat16*>(a->q);
+  p.d_o = static_cast<const __nv_bfloat16*>(a->d_o);
+  p.q_b = a->q_b; p.q_s = a->q_s; p.q_h = a->q_h;
+  p.do_b = a->do_b; p.do_s = a->do_s; p.do_h = a->do_h;
   if (a->HD == 128) return launch_attn_bwd<128>(a, maps, p, st);
   return launch_attn_bwd<64>(a, maps, p, st);
 }

@@ -20,6 +20,11 @@
 #include "../../include/stb200.h"
 #include "common.cuh"
 
+// timing experiments only (never defined in the shipped build): 1 = skip the exp / dS math, 2 = also skip the TMEM traffic
+#ifndef STB_ATTN_DEBUG_SKIP
+#define STB_ATTN_DEBUG_SKIP 0
+#endif
+
 namespace stb {
 
 struct AttnBwdParams {
@@ -29,6 +34,9 @@ struct AttnBwdParams {
   const float* delta;  // [B, H, Sq]
   __nv_bfloat16 *dq, *dk, *dv;
   long long dq_b, dq_s, dq_h, dk_b, dk_s, dk_h, dv_b, dv_s, dv_h;
+  // raw views of the operands the dq kernel stages into TMEM itself (everything else goes through the TMA maps)
+  const __nv_bfloat16 *q, *d_o;
+  long long q_b, q_s, q_h, do_b, do_s, do_h;
 };
 
 struct AttnBwdMaps {
@@ -294,12 +302,17 @@ attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
       tc_fence_after();
       // one pass: P^T = exp2(S^T*sl2 - lse), dS^T = P^T o (dP^T - Delta)  (the softmax scale of dS is
       // applied once to the dK accumulator in the epilogue)
+#if STB_ATTN_DEBUG_SKIP < 2
       {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32b_x32(X(buf) + lane_off + 32 * w, sv);
         tmem_ld_32x32b_x32(Y(buf) + lane_off + 32 * w, dv);
         tc_wait_ld();
         uint32_t pk[16], dk_[16];
+#if STB_ATTN_DEBUG_SKIP == 1
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = sv[j] ^ sv[j + 16], dk_[j] = dv[j] ^ dv[j + 16];
+#else
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 l4 = *reinterpret_cast<const float4*>(lse_s + j);   // smem broadcast
@@ -313,9 +326,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
           dk_[j / 2] = pack_bf16x2(x0 * (__uint_as_float(dv[j + 0]) - d4.x), x1 * (__uint_as_float(dv[j + 1]) - d4.y));
           dk_[j / 2 + 1] = pack_bf16x2(x2 * (__uint_as_float(dv[j + 2]) - d4.z), x3 * (__uint_as_float(dv[j + 3]) - d4.w));
         }
+#endif
         tmem_st_32x32b_x16(X(buf) + lane_off + 32 * w, pk);
         tmem_st_32x32b_x16(Y(buf) + lane_off + 32 * w, dk_);
       }
+#endif
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(p_full(buf));
@@ -385,7 +400,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
     tma_prefetch_desc(&maps.do128);
   }
   if (warp == 9 && lane == 0) {
-    mbar_init(qdo_full, 1);
+    mbar_init(qdo_full, 256);   // Q / dO rows written to TMEM by the 256 compute threads
     for (int s = 0; s < NSTG; ++s) {
       mbar_init(kv_full(s), 1);
       mbar_init(kv_empty(s), 1);
@@ -409,16 +424,13 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
   auto Sb = [&](int w) { return tmem_base + uint32_t(w) * 64; };
   auto Yb = [&](int w) { return tmem_base + 128 + uint32_t(w) * 64; };  // dP (dS packed in place)
   const uint32_t DQ = tmem_base + 256;
+  // The resident operands live in TMEM (bf16 pairs per column, lane = query row) and feed the score MMAs as the
+  // TS-form A operand: S = Q K^T and dP = dO V^T then fetch only their 64-key B slices from shared memory
+  // (2 KB per MMA instead of 6 KB), which takes the kernel off the shared-memory bandwidth limit.
+  const uint32_t QT = tmem_base + 384;             // Q  [128 x HD] bf16 : HD / 2 columns
+  const uint32_t DOT = tmem_base + 384 + HD / 2;   // dO [128 x HD] bf16
 
   if (warp == 8) {
-    if (elect_one()) {
-      mbar_arrive_expect_tx(qdo_full, 2 * BIG);
-      for (int a = 0; a < ATOMS; ++a) {
-        tma_load_4d(q_smem + a * ATOM128, &maps.q128, qdo_full, a * 64, h, q0, b);
-        tma_load_4d(do_smem + a * ATOM128, &maps.do128, qdo_full, a * 64, h, q0, b);
-      }
-    }
-    __syncwarp();
     int stg = 0;
     uint32_t ph = 0;
     for (int j = 0; j < n_kv; ++j) {
@@ -442,16 +454,14 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
     auto issue_scores = [&](int w, int stg) {
 #pragma unroll
       for (int kk = 0; kk < HD / 16; ++kk) {
-        const uint64_t ad = sdesc_k(q_smem, (kk / 4) * ATOM128 + (kk % 4) * 32);
         const uint64_t bd = sdesc_k(k_smem(stg), (kk / 4) * ATOM64 + (kk % 4) * 32);
-        mma_ss(Sb(w), ad, bd, idesc_s, kk > 0);
+        mma_ts(Sb(w), QT + 8 * kk, bd, idesc_s, kk > 0);
       }
       tc_commit(s_full(w));
 #pragma unroll
       for (int kk = 0; kk < HD / 16; ++kk) {
-        const uint64_t ad = sdesc_k(do_smem, (kk / 4) * ATOM128 + (kk % 4) * 32);
         const uint64_t bd = sdesc_k(v_smem(stg), (kk / 4) * ATOM64 + (kk % 4) * 32);
-        mma_ss(Yb(w), ad, bd, idesc_s, kk > 0);
+        mma_ts(Yb(w), DOT + 8 * kk, bd, idesc_s, kk > 0);
       }
       tc_commit(dp_full(w));
     };
@@ -498,6 +508,25 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
     const long long stat_idx = ((long long)b * p.H + h) * p.Sq + qrow;
     const float lse2 = row_ok ? p.lse[stat_idx] * 1.4426950408889634f : INFINITY;
     const float delta = row_ok ? p.delta[stat_idx] : 0.f;
+    {  // warpgroup 0 stages this thread's Q row, warpgroup 1 its dO row (global -> registers -> TMEM)
+      const __nv_bfloat16* src = (w == 0)
+          ? p.q + (long long)b * p.q_b + (long long)qrow * p.q_s + (long long)h * p.q_h
+          : p.d_o + (long long)b * p.do_b + (long long)qrow * p.do_s + (long long)h * p.do_h;
+      const uint32_t dst = (w == 0 ? QT : DOT) + lane_off;
+#pragma unroll
+      for (int c = 0; c < HD / 2; c += 32) {           // 32 columns = 64 bf16 = 128 bytes per chunk
+        uint32_t v[32];
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const uint4 u = row_ok ? __ldg(reinterpret_cast<const uint4*>(src + 2 * c) + q4) : make_uint4(0u, 0u, 0u, 0u);
+          v[4 * q4 + 0] = u.x, v[4 * q4 + 1] = u.y, v[4 * q4 + 2] = u.z, v[4 * q4 + 3] = u.w;
+        }
+        tmem_st_32x32b_x32(dst + c, v);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(qdo_full);
+    }
     // warpgroup w owns key columns [32 w, 32 w + 32) of EVERY 64-key tile (see attn_bwd_dkdv_kernel)
     for (int j = 0; j < n_kv; ++j) {
       const int buf = j & 1;
@@ -505,6 +534,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
       mbar_wait(s_full(buf), (j >> 1) & 1, 55);
       mbar_wait(dp_full(buf), (j >> 1) & 1, 56);
       tc_fence_after();
+#if STB_ATTN_DEBUG_SKIP < 2
       {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32b_x32(Sb(buf) + lane_off + 32 * w, sv);
@@ -516,6 +546,10 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
             if (i >= kv_valid) sv[i] = 0xff800000u;  // -inf -> P = 0
         }
         uint32_t pk[16];
+#if STB_ATTN_DEBUG_SKIP == 1
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = sv[i] ^ dv[i + 16];
+#else
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const float p0 = ex2f(fmaf(__uint_as_float(sv[i]), sl2, -lse2));
@@ -524,8 +558,10 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
           const float d1 = p1 * (__uint_as_float(dv[i + 1]) - delta);
           pk[i / 2] = pack_bf16x2(d0, d1);
         }
+#endif
         tmem_st_32x32b_x16(Yb(buf) + lane_off + 32 * w, pk);
       }
+#endif
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(ds_full(buf));

@@ -13,6 +13,7 @@
 // A CTA owns MT x 128 rows and BN columns of D per tile; TMEM holds 512/(MT*BN) accumulator
 // stages so the epilogue of tile i overlaps the mainloop of tile i+1 when there are >= 2.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace stb {
@@ -72,6 +73,21 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// CTA-pair tile: 256 x BN per 2-CTA cluster; per CTA 128 rows of A + BN/2 rows of W per stage, 128 x BN accumulator
+template <int BN>
+struct GemmPairCfg {
+  static constexpr int BM = 256;
+  static constexpr int BK = 64;
+  static constexpr int A_BYTES = 128 * BK * 2;
+  static constexpr int W_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int ACC_COLS = BN;
+  static constexpr int ACC_STAGES = (512 / ACC_COLS) >= 2 ? 2 : 1;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
 __device__ __forceinline__ void gemm_tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
   // grouped rasterisation: bands of 8 m-tiles sweep all n-tiles -> square-ish L2 footprint
   constexpr int GM = 8;
@@ -84,10 +100,18 @@ __device__ __forceinline__ void gemm_tile_coords(int tile, int tiles_m, int tile
   tn = within / gsize;
 }
 
-template <int MT, int BN, bool CONV = false>
+// PAIR = true: cta_group::2 kernel (launch with cluster dims (2,1,1), MT must be 1).  The cluster owns a 256 x BN
+// tile: CTA rank r stages A rows [128 r, 128 r + 128) and W rows [BN/2 r, BN/2 r + BN/2) of every k-block in its own
+// shared memory (6 KB -> 4 KB of operand fetch per SM per MMA k-step at BN = 256), the leader issues one M = 256
+// tcgen05.mma per k-step for both SMs, and each CTA drains its own 128 accumulator lanes.
+template <int MT, int BN, bool CONV = false, bool PAIR = false>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
-  using Cfg = GemmCfg<MT, BN>;
+  using Cfg = typename std::conditional<PAIR, GemmPairCfg<BN>, GemmCfg<MT, BN>>::type;
+  static_assert(!PAIR || (MT == 1 && !CONV), "pair kernel: MT = 1, no CONV");
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int tile0 = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int tile_step = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
 
@@ -125,16 +149,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(accf_bar(s), 1);
-      mbar_init(acce_bar(s), 4);
+      mbar_init(acce_bar(s), PAIR ? 8 : 4);   // pair: the leader's barrier collects both CTAs' epilogue warps
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -143,7 +172,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         int tm, tn;
         gemm_tile_coords(tile, tiles_m, tiles_n, tm, tn);
         const int b = tm / tiles_per_batch;
@@ -154,6 +183,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             mbar_wait(empty_bar(stage), phase ^ 1u, 1);
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
             if (elect_one()) {
+              if constexpr (PAIR) {
+                // both CTAs' bytes are accounted on the leader's barrier (the MMA issuer waits there)
+                if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+                tma_load_3d_pair(sa, &maps.a[seg], full_bar(stage), kb * 64, s0 + int(rank) * 128, b);
+                tma_load_2d_pair(sa + Cfg::A_BYTES, &maps.w[seg], full_bar(stage), kb * 64, n0 + int(rank) * (BN / 2));
+              } else {
               mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
               if constexpr (CONV) {
                 // implicit-GEMM 3x3 conv: shifted input window; TMA zero-fills the halo (x / y out of range)
@@ -169,6 +204,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                   tma_load_3d(sa + mt * Cfg::A_BYTES, &maps.a[seg], full_bar(stage), kb * 64, s0 + mt * 128, b);
               }
               tma_load_2d(sa + MT * Cfg::A_BYTES, &maps.w[seg], full_bar(stage), kb * 64, n0);
+              }
             }
             __syncwarp();
             if (++stage == STAGES) {
@@ -179,15 +215,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(acce_bar(acc), acc_phase ^ 1u, 2);
         tc_fence_after();
         const uint32_t d_base = tmem_base + acc * Cfg::ACC_COLS;
@@ -202,14 +238,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             if (elect_one()) {
               for (int kk = 0; kk < nk; ++kk) {
                 const uint64_t bdesc = sdesc_k(sw, kk * 32);
+                if constexpr (PAIR) {
+                  mma_ss2(d_base, sdesc_k(sa, kk * 32), bdesc, idesc, accumulate);
+                } else {
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                  const uint64_t adesc = sdesc_k(sa, mt * Cfg::A_BYTES + kk * 32);
-                  mma_ss(d_base + mt * BN, adesc, bdesc, idesc, accumulate);
+                  for (int mt = 0; mt < MT; ++mt) {
+                    const uint64_t adesc = sdesc_k(sa, mt * Cfg::A_BYTES + kk * 32);
+                    mma_ss(d_base + mt * BN, adesc, bdesc, idesc, accumulate);
+                  }
                 }
                 accumulate = 1;
               }
-              tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+              // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+              if constexpr (PAIR) tc_commit2(empty_bar(stage)); else tc_commit(empty_bar(stage));
             }
             __syncwarp();
             accumulate = 1;
@@ -219,7 +260,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             }
           }
         }
-        if (elect_one()) tc_commit(accf_bar(acc));  // accumulator complete -> epilogue
+        if (elect_one()) {  // accumulator complete -> epilogue (of both CTAs of a pair)
+          if constexpr (PAIR) tc_commit2(accf_bar(acc)); else tc_commit(accf_bar(acc));
+        }
         __syncwarp();
         if (++acc == ACC_STAGES) {
           acc = 0;
@@ -232,11 +275,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       int tm, tn;
       gemm_tile_coords(tile, tiles_m, tiles_n, tm, tn);
       const int b = tm / tiles_per_batch;
-      const int s0 = (tm - b * tiles_per_batch) * Cfg::BM;
+      const int s0 = (tm - b * tiles_per_batch) * Cfg::BM + (PAIR ? int(rank) * 128 : 0);
       const int n0 = tn * BN;
       mbar_wait(accf_bar(acc), acc_phase, 4);
       tc_fence_after();
@@ -397,7 +440,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acce_bar(acc));
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_remote(acce_bar(acc), 0u); else mbar_arrive(acce_bar(acc));
+      }
       if (++acc == ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1u;
@@ -406,10 +451,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();   // pair: the peer may still touch our smem / barriers / TMEM
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

@@ -69,6 +69,12 @@ class PixartSigma(Flux):
         self.noise_schedule = make_ddpm_schedule(1000, 0.0001, 0.02, "linear")
         self.model = transformer if transformer is not None else PixArtTransformer2DModel(**transformer_kwargs)
         self._sched_dev: Dict[Any, Any] = {}
+        pt = getattr(self.config, "prediction_type", None)      # pixart/model.py:698-700
+        if pt is not None:
+            if pt not in ("epsilon", "v_prediction"):
+                raise NotImplementedError(f"prediction_type {pt} is not implemented for the B200 PixArt step")
+            self.PREDICTION_TYPE = pt
+            self.noise_schedule.config.prediction_type = pt
 
     def add_lora_adapter(self):
         c = self.config
@@ -173,4 +179,10 @@ class PixartSigma(Flux):
         if c.snr_gamma:
             weights = min_snr_loss_weights(prepared_batch["timesteps"].to(self.accelerator.device), self.noise_schedule,
                                            c.snr_gamma, self.PREDICTION_TYPE).float()
-        return _TargetLossFn.apply(model_output["model_prediction"], prepared_batch["noise"], weights, snr_w, lt, hc)
+        if self.PREDICTION_TYPE == "v_prediction":              # common.py:4648-4653 (DDPMScheduler.get_velocity, latent dtype)
+            from ..training.noise import get_velocity
+            target = get_velocity(self.noise_schedule, prepared_batch["latents"], prepared_batch["noise"],
+                                  prepared_batch["timesteps"]).contiguous()
+        else:
+            target = prepared_batch["noise"]
+        return _TargetLossFn.apply(model_output["model_prediction"], target, weights, snr_w, lt, hc)

@@ -474,3 +474,17 @@ CHECKS.update({
     "attn_fwd_cross_300": lambda: check_attn_fwd(2, 4, 1024, 300),
     "attn_bwd_cross_300": lambda: check_attn_bwd(2, 4, 1024, 300),
 })
+
+
+# --------------------------------------------------------------------------------------------- CTA-pair (cta_group::2) GEMM
+CHECKS.update({
+    "gemm_pair_basic": lambda: check_gemm(512, 512, 256, tile=(3, 256)),
+    "gemm_pair_one_tile": lambda: check_gemm(256, 256, 64, tile=(3, 256)),
+    "gemm_pair_tails": lambda: check_gemm(200, 328, 200, B=2, tile=(3, 256)),
+    "gemm_pair_half_empty": lambda: check_gemm(100, 256, 128, B=3, tile=(3, 256)),
+    "gemm_pair_seg3_lora": lambda: check_gemm(512, 512, 256, segs=[128, 16], bias=True, tile=(3, 256)),
+    "gemm_pair_gate_res": lambda: check_gemm(512, 256, 128, B=2, bias=True, epi=E.EPI_GATE_RES, nan_to_num=True, tile=(3, 256)),
+    "gemm_pair_gelu": lambda: check_gemm(256, 512, 128, bias=True, epi=E.EPI_GELU, tile=(3, 256)),
+    "gemm_pair_persistent": lambda: check_gemm(4096, 3072, 512, tile=(3, 256)),
+    "gemm_pair_flux_shape": lambda: check_gemm(4608, 3072, 3072, B=2, bias=True, tile=(3, 256)),
+})

@@ -78,7 +78,7 @@ def main():
     which = sys.argv[1:] or ["gemm", "attn"]
     if "gemm" in which:
         for (M, N, K) in [(16384, 3072, 3072), (16384, 12288, 3072), (16384, 3072, 12288), (2048, 3072, 3072), (16384, 9216, 3072)]:
-            for tile in [(1, 256), (2, 256), (1, 128), (2, 128)]:
+            for tile in [(1, 256), (2, 256), (3, 256)]:
                 try:
                     r = bench_gemm(M, N, K, tile)
                 except Exception as e:  # noqa
