@@ -332,6 +332,15 @@ int stb_gemm_bf16(const stb_gemm_args* a, void* stream) {
     };
     const long long t2 = (long long)((a->rows_per_batch + 255) / 256) * a->num_batches * ((a->N + bn - 1) / bn);
     mt = (bn >= 128 && t2 >= 2ll * num_sms() && fill(2) >= 0.98 * fill(1)) ? 2 : 1;
+    // CTA-pair kernel (cta_group::2, one 256 x 256 tile per TPC): operand fetch per SM drops from 12 KB to 8 KB per
+    // k-step, which lifts the MMA rate from ~75 % to ~100 % of the tensor-pipe floor (profiles/r01/mma_probe.log);
+    // measured 1.49-1.57 PFLOP/s vs 1.28-1.41 for the single-CTA tiles.  Needs enough tiles to occupy every TPC.
+    if (bn == 256) {
+      const int clusters = num_sms() / 2;
+      const long long waves2 = (t2 + clusters - 1) / clusters;
+      const double fill_pair = double(t2) / double(waves2 * clusters);
+      if (t2 >= clusters && fill_pair >= 0.85 * std::max(fill(1), fill(2))) mt = 3;
+    }
   }
   if (mt == 3 && bn == 256) return launch_gemm<1, 256, true>(a, st);   // CTA-pair (cta_group::2) 256 x 256 tile
   if (mt == 1 && bn == 256) return launch_gemm<1, 256>(a, st);
