@@ -435,6 +435,21 @@ int stb_attn_bwd(const stb_attn_bwd_args* a, void* stream) {
   p.dq_b = a->dq_b; p.dq_s = a->dq_s; p.dq_h = a->dq_h;
   p.dk_b = a->dk_b; p.dk_s = a->dk_s; p.dk_h = a->dk_h;
   p.dv_b = a->dv_b; p.dv_s = a->dv_s; p.dv_h = a->dv_h;
+  p.fuse_prep = 0;
+  if (const stb_qk_prep* f = a->qk_prep) {
+    if (a->Sq != a->Sk) return fail(STB_ERR_ARG, "qk_prep fusion needs self-attention (Sq == Sk)");
+    if (!f->src || !aligned16(f->src) || (f->src_b & 7) || (f->src_s & 7) || (f->k_off & 7))
+      return fail(STB_ERR_ARG, "qk_prep.src must be 16-byte aligned with strides / k_off multiple of 8 elements");
+    if ((f->cos_t == nullptr) != (f->sin_t == nullptr)) return fail(STB_ERR_ARG, "qk_prep: give both cos_t and sin_t or neither");
+    p.fuse_prep = 1;
+    p.src = static_cast<const __nv_bfloat16*>(f->src);
+    p.src_b = f->src_b; p.src_s = f->src_s; p.k_off = f->k_off;
+    p.wq0 = static_cast<const __nv_bfloat16*>(f->wq); p.wk0 = static_cast<const __nv_bfloat16*>(f->wk);
+    p.wq1 = static_cast<const __nv_bfloat16*>(f->wq_added); p.wk1 = static_cast<const __nv_bfloat16*>(f->wk_added);
+    p.s_split = f->s_split;
+    p.cosT = f->cos_t; p.sinT = f->sin_t;
+    p.eps = f->eps;
+  }
   p.q = static_cast<const __nv_bfloat16*>(a->q);
   p.d_o = static_cast<const __nv_bfloat16*>(a->d_o);
   p.q_b = a->q_b; p.q_s = a->q_s; p.q_h = a->q_h;

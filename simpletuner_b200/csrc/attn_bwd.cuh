@@ -19,6 +19,7 @@
 #pragma once
 #include "../../include/stb200.h"
 #include "common.cuh"
+#include "elementwise.cuh"
 
 // timing experiments only (never defined in the shipped build): 1 = skip the exp / dS math, 2 = also skip the TMEM traffic
 #ifndef STB_ATTN_DEBUG_SKIP
@@ -37,6 +38,16 @@ struct AttnBwdParams {
   // raw views of the operands the dq kernel stages into TMEM itself (everything else goes through the TMA maps)
   const __nv_bfloat16 *q, *d_o;
   long long q_b, q_s, q_h, do_b, do_s, do_h;
+  // optional fused backward of the q / k pre-processing (per-head RMSNorm -> RoPE, qk_rmsnorm_rope_fwd_kernel):
+  // dq / dk then receive the gradient w.r.t. the PROJECTION outputs (self-attention only: token index == row index)
+  int fuse_prep;
+  const __nv_bfloat16* src;          // pre-norm projection output [B, S, C]: q at column 0, k at column k_off
+  long long src_b, src_s;
+  int k_off;
+  const __nv_bfloat16 *wq0, *wk0, *wq1, *wk1;   // RMSNorm weights (image stream | tokens s < s_split), may be null
+  int s_split;
+  const float *cosT, *sinT;          // [S, HD] or null
+  float eps;
 };
 
 struct AttnBwdMaps {
@@ -100,6 +111,73 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, __nv_bfloat16* gro
         u.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * mul, __uint_as_float(v[q * 8 + 5]) * mul);
         u.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * mul, __uint_as_float(v[q * 8 + 7]) * mul);
         dp[q] = u;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused epilogue: backward of RoPE(RMSNorm(x) * w) for one (token, head) row held in this thread's TMEM lane.
+//   go = acc * scale (gradient w.r.t. the post-RoPE q or k);  dy = R^T go;  g = dy * w;
+//   dx = rstd * (g - xhat * mean(g * xhat)),  xhat = x * rstd        (same math as qk_rmsnorm_rope_bwd_kernel)
+// pass 1 turns the accumulator columns [0, NC) at `taddr` into g in place and returns the partial sums;
+// pass 2 reads g back and writes dx (bf16).  x / w / cos / sin pointers are already offset to the first column.
+// ------------------------------------------------------------------------------------------------
+template <int NC>
+__device__ __forceinline__ void qk_grad_pass1(uint32_t taddr, float scale, bool row_ok, const __nv_bfloat16* xrow,
+                                              const __nv_bfloat16* w, const float* cs, const float* sn, float& ss,
+                                              float& sgx) {
+#pragma unroll 1
+  for (int c = 0; c < NC; c += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + c, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {   // 8 columns at a time
+      float x[8], wv[8];
+      const uint4 ux = row_ok ? __ldg(reinterpret_cast<const uint4*>(xrow + c) + q4) : make_uint4(0u, 0u, 0u, 0u);
+      unpack8(ux, x);
+      if (w) unpack8(__ldg(reinterpret_cast<const uint4*>(w + c) + q4), wv);
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const int j = q4 * 8 + i;
+        const float go0 = __uint_as_float(v[j]) * scale, go1 = __uint_as_float(v[j + 1]) * scale;
+        float dy0 = go0, dy1 = go1;
+        if (cs && row_ok) {
+          const float2 c2 = __ldg(reinterpret_cast<const float2*>(cs + c + j));
+          const float2 s2 = __ldg(reinterpret_cast<const float2*>(sn + c + j));
+          // o[i] = y[i] c[i] - y[i+1] s[i];  o[i+1] = y[i+1] c[i+1] + y[i] s[i+1]
+          dy0 = go0 * c2.x + go1 * s2.y;
+          dy1 = go1 * c2.y - go0 * s2.x;
+        }
+        const float g0 = w ? dy0 * wv[i] : dy0, g1 = w ? dy1 * wv[i + 1] : dy1;
+        ss += x[i] * x[i] + x[i + 1] * x[i + 1];
+        sgx += g0 * x[i] + g1 * x[i + 1];
+        v[j] = __float_as_uint(g0);
+        v[j + 1] = __float_as_uint(g1);
+      }
+    }
+    tmem_st_32x32b_x32(taddr + c, v);
+  }
+  tc_wait_st();
+}
+
+template <int NC>
+__device__ __forceinline__ void qk_grad_pass2(uint32_t taddr, bool row_ok, const __nv_bfloat16* xrow, float rstd, float m,
+                                              __nv_bfloat16* orow) {
+#pragma unroll 1
+  for (int c = 0; c < NC; c += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + c, v);
+    tc_wait_ld();
+    if (row_ok) {
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        float x[8], o[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xrow + c) + q4), x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rstd * (__uint_as_float(v[q4 * 8 + i]) - (x[i] * rstd) * m);
+        reinterpret_cast<uint4*>(orow + c)[q4] = pack8(o);
       }
     }
   }
@@ -344,8 +422,20 @@ attn_bwd_dkdv_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
     const bool row_ok = kv < p.Sk;
     if (w == 0)
       store_acc_row<HD>(DV + lane_off, p.dv + (long long)b * p.dv_b + (long long)kv * p.dv_s + (long long)h * p.dv_h, row_ok);
-    else
+    else if (!p.fuse_prep)
       store_acc_row<HD>(DK + lane_off, p.dk + (long long)b * p.dk_b + (long long)kv * p.dk_s + (long long)h * p.dk_h, row_ok, p.scale);
+    else {
+      // dK row -> gradient of the k projection output (RoPE^T, RMSNorm backward), token index == key index
+      const __nv_bfloat16* xrow = p.src + (long long)b * p.src_b + (long long)kv * p.src_s + p.k_off + h * HD;
+      const __nv_bfloat16* wk = (kv < p.s_split) ? p.wk1 : p.wk0;
+      const float* cs = p.cosT ? p.cosT + (long long)kv * HD : nullptr;
+      const float* sn = p.sinT ? p.sinT + (long long)kv * HD : nullptr;
+      float ss = 0.f, sgx = 0.f;
+      qk_grad_pass1<HD>(DK + lane_off, p.scale, row_ok, xrow, wk, cs, sn, ss, sgx);
+      const float rstd = rsqrtf(ss / HD + p.eps);
+      qk_grad_pass2<HD>(DK + lane_off, row_ok, xrow, rstd, sgx * rstd / HD,
+                        p.dk + (long long)b * p.dk_b + (long long)kv * p.dk_s + (long long)h * p.dk_h);
+    }
   }
 
   tc_fence_before();
@@ -569,7 +659,27 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams
     mbar_wait(dq_done, 0, 57);
     tc_fence_after();
     // both warpgroups cover all 128 lanes: split the HD columns between them
-    {
+    if (p.fuse_prep) {
+      // dQ row -> gradient of the q projection output; each warpgroup owns HD/2 columns, the two partial
+      // (sum x^2, sum g x) pairs meet in shared memory (the Q tile area is free: Q lives in TMEM)
+      constexpr int NC = HD / 2;
+      const int col = w * NC;
+      const __nv_bfloat16* xrow = p.src + (long long)b * p.src_b + (long long)qrow * p.src_s + h * HD + col;
+      const __nv_bfloat16* wq = (qrow < p.s_split) ? p.wq1 : p.wq0;
+      const float* cs = p.cosT ? p.cosT + (long long)qrow * HD + col : nullptr;
+      const float* sn = p.sinT ? p.sinT + (long long)qrow * HD + col : nullptr;
+      float ss = 0.f, sgx = 0.f;
+      qk_grad_pass1<NC>(DQ + lane_off + col, p.scale, row_ok, xrow, wq ? wq + col : nullptr, cs, sn, ss, sgx);
+      float2* part = reinterpret_cast<float2*>(smem_raw + (q_smem - smem_u32(smem_raw)));   // [2][128]
+      part[w * 128 + r] = make_float2(ss, sgx);
+      named_bar_sync(3, 256);
+      const float2 other = part[(w ^ 1) * 128 + r];
+      ss += other.x;
+      sgx += other.y;
+      const float rstd = rsqrtf(ss / HD + p.eps);
+      qk_grad_pass2<NC>(DQ + lane_off + col, row_ok, xrow, rstd, sgx * rstd / HD,
+                        p.dq + (long long)b * p.dq_b + (long long)qrow * p.dq_s + (long long)h * p.dq_h + col);
+    } else {
       __nv_bfloat16* dqrow = p.dq + (long long)b * p.dq_b + (long long)qrow * p.dq_s + (long long)h * p.dq_h;
 #pragma unroll 1
       for (int c = 0; c < HD / 2; c += 32) {

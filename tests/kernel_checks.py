@@ -488,3 +488,37 @@ CHECKS.update({
     "gemm_pair_persistent": lambda: check_gemm(4096, 3072, 512, tile=(3, 256)),
     "gemm_pair_flux_shape": lambda: check_gemm(4608, 3072, 3072, B=2, bias=True, tile=(3, 256)),
 })
+
+
+# --------------------------------------------------------------------------------------------- fused q/k-prep backward epilogue
+def check_attn_bwd_fused_prep(B=2, S=333, H=3, HD=128, s_split=77, rope=True, norm_w=True):
+    """attn_bwd(qk_prep=...) == attn_bwd -> qk_rmsnorm_rope_bwd (the two-kernel path) on the same inputs."""
+    D = H * HD
+    qkv = _rand(B, S, 3 * D, seed=1)
+    d_o = _rand(B, S, H, HD, seed=2)
+    mk = lambda sd: (1.0 + 0.1 * _rand(HD, seed=sd).float()).bfloat16() if norm_w else None
+    wq, wk, wqa, wka = mk(3), mk(4), mk(5), mk(6)
+    cos, sin = _rope_tables(S, HD) if rope else (None, None)
+    q, k = ops.qk_rmsnorm_rope_fwd(qkv, D, H, HD, wq, wk, wqa, wka, s_split, cos, sin, 1e-6)
+    v = qkv[:, :, 2 * D:].unflatten(-1, (H, HD))
+    o, lse = ops.attn_fwd(q, k, v)
+    # reference: two kernels
+    dq, dk, dv = ops.attn_bwd(q, k, v, o, d_o, lse)
+    ref = torch.zeros_like(qkv)
+    ops.qk_rmsnorm_rope_bwd(dq, dk, qkv, D, H, HD, wq, wk, wqa, wka, s_split, cos, sin, 1e-6, dsrc=ref)
+    ref[:, :, 2 * D:] = dv.reshape(B, S, D)
+    got = torch.zeros_like(qkv)
+    ops.attn_bwd(q, k, v, o, d_o, lse, dq=got[:, :, 0:D].unflatten(-1, (H, HD)), dk=got[:, :, D:2 * D].unflatten(-1, (H, HD)),
+                 dv=got[:, :, 2 * D:].unflatten(-1, (H, HD)),
+                 qk_prep=dict(src=qkv, k_off=D, wq=wq, wk=wk, wq_added=wqa, wk_added=wka, s_split=s_split, cos=cos, sin=sin, eps=1e-6))
+    torch.cuda.synchronize()
+    # the two-kernel path rounds dq / dk to bf16 before the norm backward, the fused one does not
+    return _report(f"attn_bwd_fused_prep_S{S}_HD{HD}_rope{int(rope)}_w{int(norm_w)}", got, ref,
+                   atol=2e-2 * float(ref.float().abs().max()), rtol=2e-2)
+
+
+CHECKS.update({
+    "attn_bwd_fused_prep": lambda: check_attn_bwd_fused_prep(),
+    "attn_bwd_fused_prep_hd64_norope": lambda: check_attn_bwd_fused_prep(B=1, S=320, H=4, HD=64, s_split=0, rope=False),
+    "attn_bwd_fused_prep_now": lambda: check_attn_bwd_fused_prep(B=1, S=256, H=2, HD=128, s_split=0, rope=True, norm_w=False),
+})
