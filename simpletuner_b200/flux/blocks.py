@@ -189,14 +189,17 @@ def _attn_core_bwd(qkv, o, d_o, lse, D, H, hd, img_plan, txt_plan, S_txt, cos, s
         ops.attn_bwd(q, k, v, o.view(B, S, H, hd), d_o.view(B, S, H, hd), lse,
                      dq=d_qkv[:, :, 0:D].unflatten(-1, (H, hd)), dk=d_qkv[:, :, D:2 * D].unflatten(-1, (H, hd)), dv=dv)
         return d_qkv
+    # The backward of RMSNorm + RoPE stays a separate HBM-bound pass.  libstb200 can also run it inside the
+    # attention-backward epilogues (ops.attn_bwd(qk_prep=...), tests: attn_bwd_fused_prep*), but with one CTA per
+    # SM the longer, latency-bound epilogue is not overlapped by anything: measured +38 ms of attention backward
+    # against 14 ms saved per Flux step (profiles/r01/bench_n1_v4.json vs v3), so it is not used here.
+    dq = torch.empty_like(q)
+    dk = torch.empty_like(k)
+    ops.attn_bwd(q, k, v, o.view(B, S, H, hd), d_o.view(B, S, H, hd), lse, dq=dq, dk=dk, dv=dv)
+    del q, k
     tq = txt_plan.norm_q if txt_plan is not None else None
     tk = txt_plan.norm_k if txt_plan is not None else None
-    # RoPE^T and the RMSNorm backward run in the attention-backward epilogues (thread = token row, whole head in
-    # registers / TMEM): d_qkv's q and k column ranges are written directly, no post-RoPE dq / dk round trip
-    ops.attn_bwd(q, k, v, o.view(B, S, H, hd), d_o.view(B, S, H, hd), lse,
-                 dq=d_qkv[:, :, 0:D].unflatten(-1, (H, hd)), dk=d_qkv[:, :, D:2 * D].unflatten(-1, (H, hd)), dv=dv,
-                 qk_prep=dict(src=qkv, k_off=D, wq=img_plan.norm_q, wk=img_plan.norm_k, wq_added=tq, wk_added=tk,
-                              s_split=S_txt, cos=cos, sin=sin, eps=EPS))
+    ops.qk_rmsnorm_rope_bwd(dq, dk, qkv, D, H, hd, img_plan.norm_q, img_plan.norm_k, tq, tk, S_txt, cos, sin, EPS, dsrc=d_qkv)
     return d_qkv
 
 
