@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -15,6 +16,7 @@
 #include "../../include/stb200.h"
 #include "attn_bwd.cuh"
 #include "attn_fwd.cuh"
+#include "attn_fwd_pair.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "vae.cuh"
@@ -375,6 +377,46 @@ int stb_attn_fwd(const stb_attn_fwd_args* a, void* stream) {
   p.o_b = a->o_b; p.o_s = a->o_s; p.o_h = a->o_h;
   p.lse = a->lse;
   dim3 grid((a->Sq + 255) / 256, a->H, a->B);
+  static const bool use_pair = [] { const char* e = std::getenv("STB_ATTN_FWD_PAIR"); return !(e && e[0] == '0'); }();
+  if (a->HD == 128 && use_pair) {
+    // CTA-pair kernel (cta_group::2): Q in TMEM, K split by rows / V by columns across the two SMs of a TPC
+    stb::AttnFwdPairMaps pm;
+    {
+      unsigned long long d[4] = {(unsigned long long)a->HD, (unsigned long long)a->H, (unsigned long long)a->Sk, (unsigned long long)a->B};
+      unsigned long long sk[3] = {(unsigned long long)a->k_h * 2ull, (unsigned long long)a->k_s * 2ull, (unsigned long long)a->k_b * 2ull};
+      unsigned long long sv[3] = {(unsigned long long)a->v_h * 2ull, (unsigned long long)a->v_s * 2ull, (unsigned long long)a->v_b * 2ull};
+      unsigned bk[4] = {64, 1, 64, 1}, bv[4] = {64, 1, 128, 1};
+      if (int r = make_map(&pm.k64, a->k, 4, d, sk, bk)) return r;
+      if (int r = make_map(&pm.v128, a->v, 4, d, sv, bv)) return r;
+    }
+    if (!aligned16(a->q) || (a->q_s & 7) || (a->q_h & 7) || (a->q_b & 7)) return fail(STB_ERR_ARG, "Q alignment");
+    stb::AttnFwdPairParams pp;
+    pp.base = p;
+    pp.q = static_cast<const __nv_bfloat16*>(a->q);
+    pp.q_b = a->q_b; pp.q_s = a->q_s; pp.q_h = a->q_h;
+    auto kernel = stb::attn_fwd_pair_kernel;
+    static bool configured = false;
+    if (!configured) {
+      if (int r = set_smem(kernel, stb::AttnFwdPairCfg::SMEM_BYTES)) return r;
+      configured = true;
+    }
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(2 * ((a->Sq + 255) / 256), a->H, a->B);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = stb::AttnFwdPairCfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    STB_CUDA(cudaLaunchKernelEx(&cfg, kernel, pm, pp));
+    g_launches.fetch_add(1);
+    return 0;
+  }
   if (a->HD == 128) {
     auto kernel = stb::attn_fwd_kernel<128>;
     static bool configured = false;
