@@ -377,7 +377,9 @@ int stb_attn_fwd(const stb_attn_fwd_args* a, void* stream) {
   p.o_b = a->o_b; p.o_s = a->o_s; p.o_h = a->o_h;
   p.lse = a->lse;
   dim3 grid((a->Sq + 255) / 256, a->H, a->B);
-  static const bool use_pair = [] { const char* e = std::getenv("STB_ATTN_FWD_PAIR"); return !(e && e[0] == '0'); }();
+  // opt-in (STB_ATTN_FWD_PAIR=1): measured at parity with the single-CTA kernel so far (0.99 vs 0.95 ms at the Flux
+  // shape): its MMA path is 1.5x cheaper, but both warpgroups now share every key tile and run in lockstep
+  static const bool use_pair = [] { const char* e = std::getenv("STB_ATTN_FWD_PAIR"); return e && e[0] == '1'; }();
   if (a->HD == 128 && use_pair) {
     // CTA-pair kernel (cta_group::2): Q in TMEM, K split by rows / V by columns across the two SMs of a TPC
     stb::AttnFwdPairMaps pm;

@@ -19,6 +19,10 @@
 #pragma once
 #include "attn_fwd.cuh"
 
+#ifndef STB_ATTN_DEBUG_SKIP
+#define STB_ATTN_DEBUG_SKIP 0
+#endif
+
 namespace stb {
 
 struct AttnFwdPairMaps {
@@ -141,8 +145,8 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
       for (int kk = 0; kk < 8; ++kk)   // 128 keys / 16
         mma_ts2(O_col, S_col(u) + P_col(kk), sdesc_mn(v_smem(stg), kk * 2048, 128 * 64 * 2), idesc_o, (acc || kk > 0) ? 1u : 0u);
     };
-    mbar_wait_cluster(q_ready, 0, 20);
-    mbar_wait_cluster(k_full(0), 0, 21);
+    mbar_wait(q_ready, 0, 20);
+    mbar_wait(k_full(0), 0, 21);
     tc_fence_after();
     if (elect_one()) {
       issue_S(0, 0);
@@ -155,7 +159,7 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
       const uint32_t par = (j / NSTG) & 1;
       if (j + 1 < n_kv) {
         const int stg_n = (j + 1) % NSTG;
-        mbar_wait_cluster(k_full(stg_n), ((j + 1) / NSTG) & 1, 23);
+        mbar_wait(k_full(stg_n), ((j + 1) / NSTG) & 1, 23);
         tc_fence_after();
         if (elect_one()) {   // S_{j+1} into the other buffer (its P_{j-1} was consumed by the PV issued last iteration)
           issue_S((j + 1) & 1, stg_n);
@@ -164,8 +168,8 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
         }
         __syncwarp();
       }
-      mbar_wait_cluster(v_full(stg), par, 22);
-      mbar_wait_cluster(p_full(j & 1), (j >> 1) & 1, 24);   // both CTAs' P_j is in TMEM
+      mbar_wait(v_full(stg), par, 22);
+      mbar_wait(p_full(j & 1), (j >> 1) & 1, 24);   // both CTAs' P_j is in TMEM
       tc_fence_after();
       if (elect_one()) {
         issue_PV(j & 1, stg, j > 0);
@@ -209,6 +213,10 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
       tc_fence_after();
       const int kv_valid = p.Sk - j * 128 - 64 * w;  // valid columns of this half; < 64 only on the ragged last tile
       const bool ragged = kv_valid < 64;
+#if STB_ATTN_DEBUG_SKIP >= 2
+      l += 1.f;
+      if (kv_valid < -1000000 && ragged) m_used = 0.f;
+#else
       // ---- pass 1: max over this half, then exchange with the other warpgroup
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
@@ -280,6 +288,7 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
         tmem_st_32x32b_x16(s_t + c / 2, pk);
       }
       l += l0 + l1;
+#endif
       tc_wait_st();
       tc_fence_before();
       __syncwarp();

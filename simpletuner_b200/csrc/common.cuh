@@ -279,13 +279,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
   while (!mbar_try_wait_cluster(bar, parity)) {}
 #endif
 }
-// arrive on the barrier at offset `bar` of cluster CTA `rank`
+// arrive on the barrier at offset `bar` of cluster CTA `rank`.  Default (.release.cta) semantics on purpose: what these
+// barriers order is TMEM traffic (tcgen05.fence::before/after_thread_sync around them); a cluster-scope release /
+// acquire makes ptxas emit CCTL.IVALL (L1 flush) on every arrive / poll, which costs ~1000 cycles per key tile.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}\n"
       ::"r"(bar), "r"(rank)
       : "memory");

@@ -117,6 +117,61 @@ __global__ void __launch_bounds__(128, 1) probe_mix(int mix, int iters, long lon
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tm, 512); }
 }
 
+// CTA-pair (cta_group::2) mixes, cluster (2,1,1): the leader issues M = 256 MMAs; operands zeroed.
+//   pmix 1: fwd pair tile: 8 TS2 N=128 (Q in TMEM x K half, K-major) + 8 TS2 N=128 (P x V half, MN-major)
+//   pmix 2: 8 SS2 N=128 (A smem 128 rows, B half) + 8 TS2 MN-major
+//   pmix 3: 16 TS2 N=128 K-major only
+//   pmix 4: GEMM k-block: 4 SS2 N=256
+__global__ void __launch_bounds__(128, 1) probe_pair(int pmix, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_smem = base, b_smem = base + 32768, b2_smem = base + 65536;
+  const uint32_t bar = base + 98304;
+  const uint32_t slot = bar + 16;
+  for (int i = threadIdx.x; i < 98304 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (threadIdx.x < 32) { tmem_alloc2(slot, 512); tmem_relinquish2(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tm = *reinterpret_cast<volatile uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x < 32 && rank == 0) {
+    constexpr uint32_t i128 = make_idesc_bf16(256, 128, 0, 0), i128mn = make_idesc_bf16(256, 128, 0, 1), i256 = make_idesc_bf16(256, 256, 0, 0);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t u = it & 1;
+      if (elect_one()) {
+        if (pmix == 4) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) mma_ss2(tm + u * 256, sdesc_k(a_smem, kk * 32), sdesc_k(b_smem, kk * 32), i256, 1u);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t bd = sdesc_k(b_smem, (kk / 4) * 8192 + (kk % 4) * 32);
+            if (pmix == 2) mma_ss2(tm + u * 128, sdesc_k(a_smem, (kk / 4) * 16384 + (kk % 4) * 32), bd, i128, kk > 0);
+            else mma_ts2(tm + u * 128, tm + 384 + 8 * kk, bd, i128, kk > 0);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            if (pmix == 3) mma_ts2(tm + u * 128, tm + 384 + 8 * kk, sdesc_k(b2_smem, (kk / 4) * 8192 + (kk % 4) * 32), i128, 1u);
+            else mma_ts2(tm + 256, tm + (u ^ 1) * 128 + (kk < 4 ? 8 * kk : 64 + 8 * (kk - 4)), sdesc_mn(b2_smem, kk * 2048, 16384), i128mn, 1u);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) tc_commit2(bar);
+    __syncwarp();
+    mbar_wait(bar, 0, 97);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x >> 1] = t1 - t0;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc2(tm, 512); }
+}
+
 int main() {
   int nsm = 0;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
@@ -161,6 +216,31 @@ int main() {
     for (int i = 0; i < nsm; ++i) avg += double(out[i]);
     avg /= nsm * 512.0;
     printf("grid %3d  mix %d %-28s %8.1f cyc/tile  (MMA floor %6.0f, eff %5.1f%%)\n", nsm, mix, names[mix], avg, floors[mix], 100.0 * floors[mix] / avg);
+  }
+  {
+    const int smem3 = 98304 + 1024 + 64;
+    cudaFuncSetAttribute(probe_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3);
+    const char* pn[] = {"", "fwd pair: 8 TS2 K-major + 8 TS2 MN-major (N=128)", "8 SS2 + 8 TS2 MN-major (N=128)", "16 TS2 K-major (N=128)", "GEMM k-block: 4 SS2 N=256"};
+    const double pf[] = {0, 1024, 1024, 1024, 512};
+    for (int pmix = 1; pmix <= 4; ++pmix) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(nsm);
+      cfg.blockDim = dim3(128);
+      cfg.dynamicSmemBytes = smem3;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      for (int rep = 0; rep < 2; ++rep) {
+        cudaLaunchKernelEx(&cfg, probe_pair, pmix, 512, out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("pmix %d: %s\n", pmix, cudaGetErrorString(e)); return 1; }
+      }
+      double avg = 0;
+      for (int i = 0; i < nsm / 2; ++i) avg += double(out[i]);
+      avg /= (nsm / 2) * 512.0;
+      printf("pairs %3d  pmix %d %-52s %8.1f cyc/iter  (MMA floor %6.0f, eff %5.1f%%)\n", nsm / 2, pmix, pn[pmix], avg, pf[pmix], 100.0 * pf[pmix] / avg);
+    }
   }
   return 0;
 }
