@@ -755,10 +755,10 @@ int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, l
 }  // extern "C"
 
 // ---------------------------------------------------------------- VAE latent encode
-template <int BN>
+template <int BN, bool PAIR = false>
 static int launch_conv3x3(const void* x, const void* w, const void* bias, const void* res, void* out, int B, int H,
                           int W, int C_in, int C_out, int stride, cudaStream_t st) {
-  using Cfg = stb::GemmCfg<1, BN>;
+  using Cfg = typename std::conditional<PAIR, stb::GemmPairCfg<BN>, stb::GemmCfg<1, BN>>::type;
   const int H_out = stride == 1 ? H : H / 2, W_out = stride == 1 ? W : W / 2;
   stb::GemmMaps maps;
   std::memset(&maps, 0, sizeof maps);
@@ -773,11 +773,12 @@ static int launch_conv3x3(const void* x, const void* w, const void* bias, const 
   {
     unsigned long long d[2] = {(unsigned long long)9 * C_in, (unsigned long long)C_out};
     unsigned long long sb[1] = {(unsigned long long)9 * C_in * 2ull};
-    unsigned bx[2] = {64, (unsigned)BN};
+    unsigned bx[2] = {64, (unsigned)(PAIR ? BN / 2 : BN)};
     if (int r = make_map(&maps.w[0], w, 2, d, sb, bx)) return r;
   }
   stb::GemmParams p;
   std::memset(&p, 0, sizeof p);
+  p.conv_pair_rows = W_out > 128 ? 1 : 2;
   p.rows_per_batch = W_out;
   p.num_batches = B * H_out;
   p.N = C_out;
@@ -796,17 +797,39 @@ static int launch_conv3x3(const void* x, const void* w, const void* bias, const 
   p.conv_stride = stride;
   p.conv_pad = stride == 1 ? 1 : 0;
   p.conv_cblocks = C_in / 64;
-  auto kernel = stb::gemm_bf16_tn_kernel<1, BN, true>;
+  auto kernel = stb::gemm_bf16_tn_kernel<1, BN, true, PAIR>;
   static bool configured = false;
   if (!configured) {
     if (int r = set_smem(kernel, Cfg::SMEM_BYTES)) return r;
     configured = true;
   }
-  const long long tiles = (long long)((W_out + 127) / 128) * p.num_batches * ((C_out + BN - 1) / BN);
-  const int grid = (int)std::min<long long>(tiles, num_sms());
-  kernel<<<grid, 256, Cfg::SMEM_BYTES, st>>>(maps, p);
-  STB_LAUNCH_CHECK("conv3x3_nhwc");
-  return 0;
+  if constexpr (PAIR) {
+    const long long tiles_m = p.conv_pair_rows == 2 ? (p.num_batches + 1) / 2 : (long long)((W_out + 255) / 256) * p.num_batches;
+    const long long tiles = tiles_m * ((C_out + BN - 1) / BN);
+    const int clusters = (int)std::min<long long>(tiles, num_sms() / 2);
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    STB_CUDA(cudaLaunchKernelEx(&cfg, kernel, maps, p));
+    g_launches.fetch_add(1);
+    return 0;
+  } else {
+    const long long tiles = (long long)((W_out + 127) / 128) * p.num_batches * ((C_out + BN - 1) / BN);
+    const int grid = (int)std::min<long long>(tiles, num_sms());
+    kernel<<<grid, 256, Cfg::SMEM_BYTES, st>>>(maps, p);
+    STB_LAUNCH_CHECK("conv3x3_nhwc");
+    return 0;
+  }
 }
 
 extern "C" {
@@ -820,6 +843,17 @@ int stb_conv3x3_nhwc(const void* x, const void* w, const void* bias, const void*
   if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (res && !aligned16(res)) || (bias && !aligned16(bias)))
     return fail(STB_ERR_ARG, "conv3x3_nhwc alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    // CTA-pair implicit GEMM (two half-rows or two rows of output pixels per TPC) once there is a tile per TPC
+    const int H_out = stride == 1 ? H : H / 2, W_out = stride == 1 ? W : W / 2;
+    const long long rows = (long long)B * H_out;
+    const long long tiles_m = W_out > 128 ? (long long)((W_out + 255) / 256) * rows : (rows + 1) / 2;
+    static const bool no_pair = [] { const char* e = std::getenv("STB_CONV_PAIR"); return e && e[0] == '0'; }();
+    if (!no_pair && C_out >= 128 && (C_out % 16) == 0 && tiles_m * ((C_out + 255) / 256) >= num_sms() / 2) {
+      if (C_out > 128) return launch_conv3x3<256, true>(x, w, bias, res, out, B, H, W, C_in, C_out, stride, st);
+      return launch_conv3x3<128, true>(x, w, bias, res, out, B, H, W, C_in, C_out, stride, st);
+    }
+  }
   if (C_out > 128) return launch_conv3x3<256>(x, w, bias, res, out, B, H, W, C_in, C_out, stride, st);
   if (C_out > 64) return launch_conv3x3<128>(x, w, bias, res, out, B, H, W, C_in, C_out, stride, st);
   return launch_conv3x3<64>(x, w, bias, res, out, B, H, W, C_in, C_out, stride, st);

@@ -48,6 +48,9 @@ struct GemmParams {
   // maps.a[0] is then a 4-D map (c, x, y, img) with box (64, 128, 1, 1) and x element-stride = conv_stride;
   // k-block kb covers tap kb / conv_cblocks (dy = tap / 3, dx = tap % 3) and channels (kb % conv_cblocks) * 64.
   int conv_h_out, conv_stride, conv_pad, conv_cblocks;
+  // CONV + pair: 1 = the two CTAs take pixels [s0, s0+128) and [s0+128, s0+256) of one output row (W_out > 128);
+  //              2 = they take two consecutive output rows of <= 128 pixels each
+  int conv_pair_rows;
 };
 
 struct GemmMaps {
@@ -108,7 +111,7 @@ template <int MT, int BN, bool CONV = false, bool PAIR = false>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   using Cfg = typename std::conditional<PAIR, GemmPairCfg<BN>, GemmCfg<MT, BN>>::type;
-  static_assert(!PAIR || (MT == 1 && !CONV), "pair kernel: MT = 1, no CONV");
+  static_assert(!PAIR || MT == 1, "pair kernel: MT = 1");
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const int tile0 = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
   const int tile_step = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
@@ -129,8 +132,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_per_batch = (p.rows_per_batch + Cfg::BM - 1) / Cfg::BM;
-  const int tiles_m = tiles_per_batch * p.num_batches;
+  const bool row_pairs = PAIR && CONV && p.conv_pair_rows == 2;
+  const int tiles_per_batch = row_pairs ? 1 : (p.rows_per_batch + Cfg::BM - 1) / Cfg::BM;
+  const int tiles_m = row_pairs ? (p.num_batches + 1) / 2 : tiles_per_batch * p.num_batches;
+  // (batch, first row) of this CTA's 128-row half of m-tile `tm`
+  auto tile_origin = [&](int tm, int& b, int& s0) {
+    if (row_pairs) {
+      b = 2 * tm + int(rank);
+      s0 = 0;
+    } else {
+      b = tm / tiles_per_batch;
+      s0 = (tm - b * tiles_per_batch) * Cfg::BM + (PAIR ? int(rank) * 128 : 0);
+    }
+  };
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   int kb_total = 0;
@@ -175,8 +189,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         int tm, tn;
         gemm_tile_coords(tile, tiles_m, tiles_n, tm, tn);
-        const int b = tm / tiles_per_batch;
-        const int s0 = (tm - b * tiles_per_batch) * Cfg::BM;
+        int b, s0;
+        tile_origin(tm, b, s0);
         const int n0 = tn * BN;
         for (int seg = 0; seg < p.nseg; ++seg) {
           for (int kb = 0; kb < p.kblocks[seg]; ++kb) {
@@ -186,7 +200,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               if constexpr (PAIR) {
                 // both CTAs' bytes are accounted on the leader's barrier (the MMA issuer waits there)
                 if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
-                tma_load_3d_pair(sa, &maps.a[seg], full_bar(stage), kb * 64, s0 + int(rank) * 128, b);
+                if constexpr (CONV) {
+                  const int tap = kb / p.conv_cblocks;
+                  const int c0 = (kb - tap * p.conv_cblocks) * 64;
+                  const int img = b / p.conv_h_out, yo = b - img * p.conv_h_out;   // b past the last row -> img out of range -> zeros
+                  const int dy = tap / 3, dx = tap - dy * 3;
+                  tma_load_4d_pair(sa, &maps.a[0], full_bar(stage), c0, s0 * p.conv_stride + dx - p.conv_pad,
+                                   yo * p.conv_stride + dy - p.conv_pad, img);
+                } else {
+                  tma_load_3d_pair(sa, &maps.a[seg], full_bar(stage), kb * 64, s0, b);
+                }
                 tma_load_2d_pair(sa + Cfg::A_BYTES, &maps.w[seg], full_bar(stage), kb * 64, n0 + int(rank) * (BN / 2));
               } else {
               mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
@@ -278,15 +301,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       int tm, tn;
       gemm_tile_coords(tile, tiles_m, tiles_n, tm, tn);
-      const int b = tm / tiles_per_batch;
-      const int s0 = (tm - b * tiles_per_batch) * Cfg::BM + (PAIR ? int(rank) * 128 : 0);
+      int b, s0;
+      tile_origin(tm, b, s0);
       const int n0 = tn * BN;
       mbar_wait(accf_bar(acc), acc_phase, 4);
       tc_fence_after();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const int s = s0 + mt * 128 + ew * 32 + lane;
-        const bool row_ok = s < p.rows_per_batch;
+        const bool row_ok = s < p.rows_per_batch && b < p.num_batches;
         __nv_bfloat16* drow = p.D + (long long)b * p.d_batch_stride + (long long)s * p.d_row_stride;
         const __nv_bfloat16* rrow =
             p.res ? p.res + (long long)b * p.res_batch_stride + (long long)s * p.res_row_stride : nullptr;

@@ -522,3 +522,14 @@ CHECKS.update({
     "attn_bwd_fused_prep_hd64_norope": lambda: check_attn_bwd_fused_prep(B=1, S=320, H=4, HD=64, s_split=0, rope=False),
     "attn_bwd_fused_prep_now": lambda: check_attn_bwd_fused_prep(B=1, S=256, H=2, HD=128, s_split=0, rope=True, norm_w=False),
 })
+
+
+# --------------------------------------------------------------------------------------------- CTA-pair implicit-GEMM conv
+CHECKS.update({
+    "conv3x3_pair_rows2": lambda: check_conv3x3(B=2, H=96, W=128, Ci=128, Co=128),
+    "conv3x3_pair_oddrows": lambda: check_conv3x3(B=1, H=149, W=120, Ci=128, Co=128, res=True),
+    "conv3x3_pair_wide": lambda: check_conv3x3(B=1, H=80, W=300, Ci=64, Co=256, res=True),
+    "conv3x3_pair_512": lambda: check_conv3x3(B=2, H=64, W=128, Ci=512, Co=512),
+    "conv3x3_pair_s2": lambda: check_conv3x3(B=2, H=160, W=256, stride=2, Ci=128, Co=128),
+    "conv3x3_pair_s2_wide": lambda: check_conv3x3(B=1, H=160, W=600, stride=2, Ci=64, Co=256),
+})
