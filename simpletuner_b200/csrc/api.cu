@@ -864,6 +864,23 @@ int stb_conv_in_3ch(const void* pixels, const void* w, const void* bias, void* o
   if (int r = check_device()) return r;
   if (C % 8 || C > 512) return fail(STB_ERR_ARG, "conv_in_3ch: C must be a multiple of 8, <= 512");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const bool no_mma = [] { const char* e = std::getenv("STB_CONV_IN_MMA"); return e && e[0] == '0'; }();
+  if (!no_mma && C % 16 == 0 && C <= 256 && aligned16(bias) && aligned16(out)) {
+    // tensor-core path: im2col tiles built in shared memory, K = 27 padded to 32
+    auto kernel = stb::conv_in_3ch_mma_kernel;
+    constexpr int SMEM = 65536 + 64 + 1024;
+    static bool configured = false;
+    if (!configured) {
+      if (int r = set_smem(kernel, SMEM)) return r;
+      configured = true;
+    }
+    const long long tiles = (long long)B * H * ((W + 127) / 128);
+    const int grid = (int)std::min<long long>(tiles, num_sms());
+    kernel<<<grid, 192, SMEM, st>>>(static_cast<const __nv_bfloat16*>(pixels), static_cast<const __nv_bfloat16*>(w),
+                                    static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(out), B, H, W, C);
+    STB_LAUNCH_CHECK("conv_in_3ch_mma");
+    return 0;
+  }
   const long long total = (long long)B * H * W * (C / 8);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
   const int smem = (C * 27 + C) * (int)sizeof(float);
@@ -889,10 +906,11 @@ int stb_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, void*
   const int ppc = (HW + chunks - 1) / chunks;
   stb::groupnorm_stats_kernel<<<dim3((HW + ppc - 1) / ppc, B), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), stats, HW, C, G, ppc);
   STB_LAUNCH_CHECK("groupnorm_stats");
-  const long long total = (long long)B * HW * (C / 8);
-  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
-  stb::groupnorm_apply_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), stats, static_cast<const __nv_bfloat16*>(gamma),
-                                                     static_cast<const __nv_bfloat16*>(beta), static_cast<__nv_bfloat16*>(out), B, HW, C, G, eps, silu);
+  const int achunks = std::max(1, std::min((HW + 63) / 64, (num_sms() * 16 + B - 1) / B));
+  const int appc = (HW + achunks - 1) / achunks;
+  stb::groupnorm_apply_kernel<<<dim3((HW + appc - 1) / appc, B), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), stats, static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta),
+      static_cast<__nv_bfloat16*>(out), B, HW, C, G, eps, silu, appc);
   STB_LAUNCH_CHECK("groupnorm_apply");
   return 0;
 }

@@ -58,6 +58,159 @@ conv_in_3ch_kernel(const __nv_bfloat16* __restrict__ px, const __nv_bfloat16* __
   }
 }
 
+// Tensor-core version of the RGB stem conv: per 128-pixel tile an im2col A tile [128 px x 32] (k = (c, dy, dx): 27
+// taps + 5 zeros) is built in shared memory in the SWIZZLE_128B K-major layout the UMMA descriptors expect, the padded
+// weights [C x 32] sit next to it, and two K = 16 tcgen05 MMAs produce the [128 x C] outputs in TMEM.
+// Persistent CTAs; A tiles and accumulators are double-buffered so building tile i+1 overlaps the MMA / drain of tile i.
+// warps 0-3: build A row (thread = pixel = TMEM lane) + epilogue; warp 4: MMA issuer; warp 5: TMEM allocator.
+__device__ __forceinline__ uint32_t sw128_row_chunk(uint32_t tile, int row, int chunk) {
+  return tile + uint32_t(row >> 3) * 1024u + uint32_t(row & 7) * 128u + uint32_t((chunk ^ (row & 7)) << 4);
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_in_3ch_mma_kernel(const __nv_bfloat16* __restrict__ px, const __nv_bfloat16* __restrict__ w,
+                       const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_smem = base;                       // [256 rows x 128 B]
+  auto a_smem = [&](int u) { return base + 32768u + uint32_t(u) * 16384u; };
+  const uint32_t bar_base = base + 65536u;
+  auto a_full = [&](int u) { return bar_base + 8u * u; };
+  auto acc_full = [&](int u) { return bar_base + 8u * (2 + u); };
+  auto acc_empty = [&](int u) { return bar_base + 8u * (4 + u); };
+  const uint32_t tmem_slot = bar_base + 48u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = (W + 127) / 128;
+  const long long num_tiles = (long long)B * H * tiles_x;
+
+  if (threadIdx.x == 0) {
+    for (int u = 0; u < 2; ++u) {
+      mbar_init(a_full(u), 128);
+      mbar_init(acc_full(u), 1);
+      mbar_init(acc_empty(u), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  // weights: row t = output channel, 27 taps then zeros up to k = 32, swizzled like a TMA box would be
+  for (int t = threadIdx.x; t < C; t += blockDim.x) {
+    const unsigned short* wr = reinterpret_cast<const unsigned short*>(w) + t * 27;
+    uint32_t v[16];
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+      const uint32_t lo = k < 27 ? uint32_t(wr[k]) : 0u, hi = (k + 1) < 27 ? uint32_t(wr[k + 1]) : 0u;
+      v[k / 2] = lo | (hi << 16);
+    }
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128_row_chunk(w_smem, t, c4)), "r"(v[c4 * 4 + 0]),
+                   "r"(v[c4 * 4 + 1]), "r"(v[c4 * 4 + 2]), "r"(v[c4 * 4 + 3]) : "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    const int r = threadIdx.x;   // pixel within the tile == TMEM lane
+    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    auto drain = [&](long long tile, int it) {
+      const int u = it & 1;
+      mbar_wait(acc_full(u), (it >> 1) & 1, 61);
+      tc_fence_after();
+      const int tx = int(tile % tiles_x);
+      const long long row = tile / tiles_x;          // b * H + y
+      const int x = tx * 128 + r;
+      __nv_bfloat16* orow = out + (row * W + x) * C;
+#pragma unroll 1
+      for (int c = 0; c < C; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + u * 256 + c, v);
+        tc_wait_ld();
+        if (x < W) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            if (c + q4 * 8 < C) {
+              float bv[8], o[8];
+              unpack8(__ldg(reinterpret_cast<const uint4*>(bias + c) + q4), bv);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[q4 * 8 + i]) + bv[i];
+              reinterpret_cast<uint4*>(orow + c)[q4] = pack8(o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(u));
+    };
+    int it = 0;
+    long long prev = -1;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int u = it & 1;
+      // A[u] was last read by the MMAs of tile it-2, whose accumulator this thread drained already (program order)
+      const int tx = int(tile % tiles_x);
+      const long long row = tile / tiles_x;
+      const int y = int(row % H);
+      const int b = int(row / H);
+      const int x = tx * 128 + r;
+      uint32_t pk[16];
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        float f2[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int kk = k + e;
+          float val = 0.f;
+          if (kk < 27) {
+            const int c = kk / 9, dy = (kk % 9) / 3, dx = kk % 3;
+            const int yy = y + dy - 1, xx = x + dx - 1;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __bfloat162float(px[(((long long)b * 3 + c) * H + yy) * W + xx]);
+          }
+          f2[e] = val;
+        }
+        pk[k / 2] = pack_bf16x2(f2[0], f2[1]);
+      }
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128_row_chunk(a_smem(u), r, c4)), "r"(pk[c4 * 4 + 0]),
+                     "r"(pk[c4 * 4 + 1]), "r"(pk[c4 * 4 + 2]), "r"(pk[c4 * 4 + 3]) : "memory");
+      fence_proxy_async_smem();
+      mbar_arrive(a_full(u));
+      if (prev >= 0) drain(prev, it - 1);
+      prev = tile;
+    }
+    if (prev >= 0) drain(prev, it - 1);
+  } else if (warp == 4) {
+    const uint32_t idesc = make_idesc_bf16(128, C, 0, 0);
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int u = it & 1;
+      mbar_wait(acc_empty(u), ((it >> 1) & 1) ^ 1u, 62);
+      mbar_wait(a_full(u), (it >> 1) & 1, 63);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+          mma_ss(tmem_base + u * 256, sdesc_k(a_smem(u), kk * 32), sdesc_k(w_smem, kk * 32), idesc, kk > 0);
+        tc_commit(acc_full(u));
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // x: NHWC [B, HW, C]; stats: fp32 [B, G, 2] (zeroed by the caller).  grid = (chunks, B); each CTA reduces a
 // contiguous chunk of pixels for all channels; C <= 512, channels-per-group cpg = C / G in {1, 2, 4} or a multiple of 8.
 __global__ void __launch_bounds__(256)
@@ -106,39 +259,53 @@ groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ 
   }
 }
 
+// grid = (chunks, B): like the stats kernel, a thread owns one fixed 8-channel vector column, so the per-channel
+// affine (a = rstd * gamma, b = beta - mean * a) is computed once per thread and the streaming loop is two loads-free
+// FMAs + SiLU per element — no integer division or rsqrt in the inner loop (the first version spent 4x the HBM time there).
 __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
                        const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
-                       __nv_bfloat16* __restrict__ out, int B, int HW, int C, int G, float eps, int silu) {
+                       __nv_bfloat16* __restrict__ out, int B, int HW, int C, int G, float eps, int silu,
+                       int pix_per_cta) {
+  const int b = blockIdx.y;
   const int vec_per_pix = C / 8;
   const int cpg = C / G;
+  const int rows_par = blockDim.x / vec_per_pix;
+  const int r0 = threadIdx.x / vec_per_pix;
+  if (r0 >= rows_par) return;
+  const int v = threadIdx.x - r0 * vec_per_pix;
   const float inv_n = 1.f / (float(HW) * float(cpg));
-  const long long total = (long long)B * HW * vec_per_pix;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = int(i % vec_per_pix);
-    const long long pix = i / vec_per_pix;
-    const int b = int(pix / HW);
-    float f[8], gm[8], bt[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + pix * C + v * 8), f);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + v * 8)), gm);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(beta + v * 8)), bt);
+  float sc[8], sh[8], gm[8], bt[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + v * 8)), gm);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(beta + v * 8)), bt);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (v * 8 + j) / cpg;
+    const float s1 = stats[((long long)b * G + g) * 2 + 0];
+    const float q1 = stats[((long long)b * G + g) * 2 + 1];
+    const float mean = s1 * inv_n;
+    const float var = fmaxf(q1 * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    sc[j] = rstd * gm[j];
+    sh[j] = bt[j] - mean * sc[j];
+  }
+  const long long p0 = (long long)blockIdx.x * pix_per_cta;
+  const long long p1 = min((long long)HW, p0 + pix_per_cta);
+  const __nv_bfloat16* xb = x + (long long)b * HW * C + v * 8;
+  __nv_bfloat16* ob = out + (long long)b * HW * C + v * 8;
+  for (long long pix = p0 + r0; pix < p1; pix += rows_par) {
+    float f[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(xb + pix * C), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (v * 8 + j) / cpg;
-      const float s = stats[((long long)b * G + g) * 2 + 0];
-      const float q = stats[((long long)b * G + g) * 2 + 1];
-      const float mean = s * inv_n;
-      const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + eps);
-      float y = (f[j] - mean) * rstd * gm[j] + bt[j];
+      float y = fmaf(f[j], sc[j], sh[j]);
       if (silu) {
         y = bf16r(y);                 // GroupNorm output tensor (bf16), then nn.SiLU
         y = y / (1.f + __expf(-y));
       }
       o[j] = y;
     }
-    *reinterpret_cast<uint4*>(out + pix * C + v * 8) = pack8(o);
+    *reinterpret_cast<uint4*>(ob + pix * C) = pack8(o);
   }
 }
 

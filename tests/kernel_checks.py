@@ -533,3 +533,9 @@ CHECKS.update({
     "conv3x3_pair_s2": lambda: check_conv3x3(B=2, H=160, W=256, stride=2, Ci=128, Co=128),
     "conv3x3_pair_s2_wide": lambda: check_conv3x3(B=1, H=160, W=600, stride=2, Ci=64, Co=256),
 })
+
+CHECKS.update({
+    "conv_in_3ch_wide": lambda: check_conv_in(B=2, H=9, W=300, C=128),     # tile tail (300 = 2 * 128 + 44), tensor-core path
+    "conv_in_3ch_c64": lambda: check_conv_in(B=1, H=33, W=130, C=64),
+    "conv_in_3ch_c8_cuda_core": lambda: check_conv_in(B=1, H=12, W=20, C=8),  # C % 16 != 0 -> CUDA-core fallback kernel
+})

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--torch", action="store_true")
+    ap.add_argument("--profile", action="store_true")
     a = ap.parse_args()
     from oracle import vae_oracle as O  # parameter initialiser only (tools/, not the product path)
     from tests.vae_parity import build_cuda_vae
@@ -58,6 +59,13 @@ def main():
     out = {"workload": f"flux_vae_encode_b{a.batch}_{a.res}", "ms": ms, "images_per_sec": a.batch / ms * 1e3,
            "tflops": fl / ms / 1e9, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
            "finite": bool(torch.isfinite(z).all())}
+    if a.profile:
+        prof = torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA])
+        with prof:
+            vae.encode_scaled(x, eps)
+            torch.cuda.synchronize()
+        rows = sorted(((e.device_time_total / 1e3, e.count, e.key) for e in prof.key_averages()), reverse=True)
+        out["kernels_ms"] = [[round(t, 3), c, k[:70]] for t, c, k in rows[:14]]
     if a.torch:
         import torch.nn.functional as F
         Pc = {k: v.cuda().bfloat16() for k, v in P.items()}
