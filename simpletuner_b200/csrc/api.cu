@@ -377,8 +377,7 @@ int stb_attn_fwd(const stb_attn_fwd_args* a, void* stream) {
   p.o_b = a->o_b; p.o_s = a->o_s; p.o_h = a->o_h;
   p.lse = a->lse;
   dim3 grid((a->Sq + 255) / 256, a->H, a->B);
-  // opt-in (STB_ATTN_FWD_PAIR=1): measured at parity with the single-CTA kernel so far (0.99 vs 0.95 ms at the Flux
-  // shape): its MMA path is 1.5x cheaper, but both warpgroups now share every key tile and run in lockstep
+  // opt-in (STB_ATTN_FWD_PAIR=1) until it has been measured faster inside the full step
   static const bool use_pair = [] { const char* e = std::getenv("STB_ATTN_FWD_PAIR"); return e && e[0] == '1'; }();
   if (a->HD == 128 && use_pair) {
     // CTA-pair kernel (cta_group::2): Q in TMEM, K split by rows / V by columns across the two SMs of a TPC
@@ -390,12 +389,12 @@ int stb_attn_fwd(const stb_attn_fwd_args* a, void* stream) {
       unsigned bk[4] = {64, 1, 64, 1}, bv[4] = {64, 1, 128, 1};
       if (int r = make_map(&pm.k64, a->k, 4, d, sk, bk)) return r;
       if (int r = make_map(&pm.v128, a->v, 4, d, sv, bv)) return r;
+      unsigned long long dq[4] = {(unsigned long long)a->HD, (unsigned long long)a->H, (unsigned long long)a->Sq, (unsigned long long)a->B};
+      unsigned long long sq[3] = {(unsigned long long)a->q_h * 2ull, (unsigned long long)a->q_s * 2ull, (unsigned long long)a->q_b * 2ull};
+      if (int r = make_map(&pm.q128, a->q, 4, dq, sq, bv)) return r;
     }
-    if (!aligned16(a->q) || (a->q_s & 7) || (a->q_h & 7) || (a->q_b & 7)) return fail(STB_ERR_ARG, "Q alignment");
     stb::AttnFwdPairParams pp;
     pp.base = p;
-    pp.q = static_cast<const __nv_bfloat16*>(a->q);
-    pp.q_b = a->q_b; pp.q_s = a->q_s; pp.q_h = a->q_h;
     auto kernel = stb::attn_fwd_pair_kernel;
     static bool configured = false;
     if (!configured) {

@@ -6,15 +6,17 @@
 // N = 128 MMAs run at 85-100 % of the floor, and in pair mode the B operand is split between the two SMs.
 //
 // A 2-CTA cluster (one TPC) owns 256 query rows of one (batch, head); CTA r owns rows [128 r, 128 r + 128):
-//   * Q lives in TMEM (bf16 pairs, staged once by the compute warps) and is the TS-form A operand of S = Q K^T;
 //   * every 128-key K tile is split by KEY ROWS (CTA r stages keys [64 r, +64)), every V tile by HEAD-DIM COLUMNS
 //     (CTA r stages columns [64 r, +64)): exactly the halves of the B operands the pair MMA reads from each SM,
-//     so each SM stages 32 KB per key tile (as the single-CTA kernel did for two Q tiles) and fetches 2 KB per MMA;
+//     so each SM stages 32 KB per key tile (as the single-CTA kernel did for two Q tiles);
 //   * the leader CTA issues M = 256 MMAs for both SMs; commits are multicast to both CTAs;
-//   * S is double-buffered in TMEM across key tiles (S_{j+1} is computed while the 8 compute warps run the softmax
-//     of tile j); both warpgroups work on every tile, each on 64 of its 128 columns, exchanging the row maxima
-//     through shared memory, and pack their bf16 P into the first 32 columns of their own half.
-// TMEM (per CTA): S0 [0,128)  S1 [128,256)  O [256,384)  Q [384,448).
+//   * S is double-buffered in TMEM across key tiles (S_{j+1} is computed while the compute warps run the softmax
+//     of tile j);
+//   * the two compute warpgroups are INDEPENDENT: warpgroup w owns the 64-key half w of every key tile with its own
+//     running max / row sum and its own output accumulator O_w (O = O_0 + O_1 are merged with the usual
+//     2^(m_w - M) weights in the epilogue).  No per-tile max exchange, so the warpgroups drift apart and one's
+//     MUFU-bound exp pass overlaps the other's TMEM reads / max pass; the leader issues PV_w as soon as P_w is ready.
+// TMEM (per CTA): S0 [0,128)  S1 [128,256)  O_0 [256,384)  O_1 [384,512).  Q stays in shared memory (SS-form S MMA).
 // warps 0-7 compute, warp 8 TMA producer, warp 9 MMA issuer (leader only), warp 10 TMEM allocator.
 #pragma once
 #include "attn_fwd.cuh"
@@ -26,23 +28,23 @@
 namespace stb {
 
 struct AttnFwdPairMaps {
-  CUtensorMap k64;   // 4-D (d, h, s, b), box (64, 1, 64, 1):  half of a key tile's rows, one 64-wide d atom
-  CUtensorMap v128;  // 4-D (d, h, s, b), box (64, 1, 128, 1): all keys of a tile, one 64-wide d atom (this CTA's half)
+  CUtensorMap q128;  // 4-D (d, h, s, b), box (64, 1, 128, 1): this CTA's 128 query rows, one 64-wide d atom
+  CUtensorMap k64;   // box (64, 1, 64, 1):  half of a key tile's rows, one 64-wide d atom
+  CUtensorMap v128;  // box (64, 1, 128, 1): all keys of a tile, one 64-wide d atom (this CTA's half of the columns)
 };
 
 struct AttnFwdPairParams {
   AttnFwdParams base;
-  const __nv_bfloat16* q;   // raw view: the compute warps stage their Q rows into TMEM themselves
-  long long q_b, q_s, q_h;
 };
 
 struct AttnFwdPairCfg {
   static constexpr int HD = 128;
+  static constexpr int Q_BYTES = 128 * HD * 2;   // this CTA's Q tile
   static constexpr int K_BYTES = 64 * HD * 2;    // this CTA's half of a key tile (64 keys x 128)
   static constexpr int V_BYTES = 128 * 64 * 2;   // this CTA's half of a value tile (128 keys x 64 columns)
   static constexpr int STAGES = 4;
-  static constexpr int SCRATCH = 2 * 2 * 128 * 4 + 2 * 128 * 4;   // row-max exchange (double-buffered) + row-sum exchange
-  static constexpr int SMEM_BYTES = STAGES * (K_BYTES + V_BYTES) + SCRATCH + 1024 + 256;
+  static constexpr int SCRATCH = 2 * 2 * 128 * 4;   // (m_w, l_w) exchange for the epilogue merge
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + SCRATCH + 1024 + 256;
 };
 
 __global__ void __launch_bounds__(384, 1)
@@ -54,19 +56,20 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  auto k_smem = [&](int s) { return smem_base + uint32_t(s) * Cfg::K_BYTES; };
-  auto v_smem = [&](int s) { return smem_base + NSTG * Cfg::K_BYTES + uint32_t(s) * Cfg::V_BYTES; };
-  const uint32_t scratch = smem_base + NSTG * (Cfg::K_BYTES + Cfg::V_BYTES);
+  const uint32_t q_smem = smem_base;
+  auto k_smem = [&](int s) { return smem_base + Cfg::Q_BYTES + uint32_t(s) * Cfg::K_BYTES; };
+  auto v_smem = [&](int s) { return smem_base + Cfg::Q_BYTES + NSTG * Cfg::K_BYTES + uint32_t(s) * Cfg::V_BYTES; };
+  const uint32_t scratch = smem_base + Cfg::Q_BYTES + NSTG * (Cfg::K_BYTES + Cfg::V_BYTES);
   const uint32_t bar_base = scratch + Cfg::SCRATCH;
   auto k_full = [&](int s) { return bar_base + 8u * s; };                 // leader's copy is the live one
   auto v_full = [&](int s) { return bar_base + 8u * (NSTG + s); };        // leader
   auto k_empty = [&](int s) { return bar_base + 8u * (2 * NSTG + s); };   // both CTAs (multicast commit)
   auto v_empty = [&](int s) { return bar_base + 8u * (3 * NSTG + s); };   // both
   auto s_full = [&](int u) { return bar_base + 8u * (4 * NSTG + u); };    // both
-  auto p_full = [&](int u) { return bar_base + 8u * (4 * NSTG + 2 + u); };  // leader: 8 warps x 2 CTAs
-  const uint32_t o_done = bar_base + 8u * (4 * NSTG + 4);                 // both
-  const uint32_t q_ready = bar_base + 8u * (4 * NSTG + 5);                // leader: 8 warps x 2 CTAs
-  const uint32_t tmem_slot = bar_base + 8u * (4 * NSTG + 6);
+  auto p_full = [&](int u, int w) { return bar_base + 8u * (4 * NSTG + 2 + 2 * u + w); };  // leader: 4 warps x 2 CTAs
+  auto o_done = [&](int w) { return bar_base + 8u * (4 * NSTG + 6 + w); };                 // both
+  const uint32_t q_full = bar_base + 8u * (4 * NSTG + 8);                 // leader
+  const uint32_t tmem_slot = bar_base + 8u * (4 * NSTG + 9);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* scratch_f = reinterpret_cast<float*>(smem_raw + (scratch - smem_u32(smem_raw)));
 
@@ -79,6 +82,7 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
   const int n_kv = (p.Sk + 127) / 128;
 
   if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&maps.q128);
     tma_prefetch_desc(&maps.k64);
     tma_prefetch_desc(&maps.v128);
   }
@@ -91,10 +95,11 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
     }
     for (int u = 0; u < 2; ++u) {
       mbar_init(s_full(u), 1);
-      mbar_init(p_full(u), 16);
+      mbar_init(p_full(u, 0), 8);
+      mbar_init(p_full(u, 1), 8);
+      mbar_init(o_done(u), 1);
     }
-    mbar_init(o_done, 1);
-    mbar_init(q_ready, 16);
+    mbar_init(q_full, 1);
     fence_mbar_init();
   }
   if (warp == 10) {
@@ -106,14 +111,16 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   auto S_col = [&](int u) { return tmem_base + uint32_t(u * 128); };
-  const uint32_t O_col = tmem_base + 256;
-  const uint32_t QT = tmem_base + 384;
-  // TMEM column of the packed bf16 P chunk kk (16 keys): chunks 0-3 belong to warpgroup 0 (S columns 0-63, packed
-  // at 0-31), chunks 4-7 to warpgroup 1 (S columns 64-127, packed at 64-95)
-  auto P_col = [&](int kk) { return uint32_t(kk < 4 ? 8 * kk : 64 + 8 * (kk - 4)); };
+  auto O_col = [&](int w) { return tmem_base + 256 + uint32_t(w * 128); };
 
   if (warp == 8) {
     // ===================== TMA producer (both CTAs; bytes are accounted on the leader's barriers) =====================
+    if (elect_one()) {
+      if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * Cfg::Q_BYTES);
+      for (int a = 0; a < HD / 64; ++a)
+        tma_load_4d_pair(q_smem + a * (128 * 64 * 2), &maps.q128, q_full, a * 64, h, q0, b);
+    }
+    __syncwarp();
     for (int j = 0; j < n_kv; ++j) {
       const int stg = j % NSTG;
       const uint32_t par = ((j / NSTG) & 1) ^ 1u;
@@ -133,19 +140,21 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
     }
   } else if (warp == 9 && rank == 0) {
     // ===================== MMA issuer (leader CTA, one elected lane) =====================
-    constexpr uint32_t idesc_s = make_idesc_bf16(256, 128, 0, 0);  // Q (TMEM)  x K (K-major halves)
-    constexpr uint32_t idesc_o = make_idesc_bf16(256, HD, 0, 1);   // P (TMEM)  x V (MN-major halves)
+    constexpr uint32_t idesc_s = make_idesc_bf16(256, 128, 0, 0);  // Q (K-major, own rows) x K (K-major halves)
+    constexpr uint32_t idesc_o = make_idesc_bf16(256, HD, 0, 1);   // P_w (TMEM)            x V (MN-major halves)
     auto issue_S = [&](int u, int stg) {
 #pragma unroll
       for (int kk = 0; kk < HD / 16; ++kk)
-        mma_ts2(S_col(u), QT + 8 * kk, sdesc_k(k_smem(stg), (kk / 4) * (64 * 64 * 2) + (kk % 4) * 32), idesc_s, kk > 0);
+        mma_ss2(S_col(u), sdesc_k(q_smem, (kk / 4) * (128 * 64 * 2) + (kk % 4) * 32),
+                sdesc_k(k_smem(stg), (kk / 4) * (64 * 64 * 2) + (kk % 4) * 32), idesc_s, kk > 0);
     };
-    auto issue_PV = [&](int u, int stg, bool acc) {
+    auto issue_PV = [&](int u, int w, int stg, bool acc) {
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk)   // 128 keys / 16
-        mma_ts2(O_col, S_col(u) + P_col(kk), sdesc_mn(v_smem(stg), kk * 2048, 128 * 64 * 2), idesc_o, (acc || kk > 0) ? 1u : 0u);
+      for (int kk = 0; kk < 4; ++kk)   // the 64 keys of half w: P_w packed at S columns [64 w, 64 w + 32)
+        mma_ts2(O_col(w), S_col(u) + 64 * w + 8 * kk, sdesc_mn(v_smem(stg), (4 * w + kk) * 2048, 128 * 64 * 2), idesc_o,
+                (acc || kk > 0) ? 1u : 0u);
     };
-    mbar_wait(q_ready, 0, 20);
+    mbar_wait(q_full, 0, 20);
     mbar_wait(k_full(0), 0, 21);
     tc_fence_after();
     if (elect_one()) {
@@ -157,54 +166,42 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
     for (int j = 0; j < n_kv; ++j) {
       const int stg = j % NSTG;
       const uint32_t par = (j / NSTG) & 1;
+      const int u = j & 1;
       if (j + 1 < n_kv) {
         const int stg_n = (j + 1) % NSTG;
         mbar_wait(k_full(stg_n), ((j + 1) / NSTG) & 1, 23);
         tc_fence_after();
-        if (elect_one()) {   // S_{j+1} into the other buffer (its P_{j-1} was consumed by the PV issued last iteration)
-          issue_S((j + 1) & 1, stg_n);
-          tc_commit2(s_full((j + 1) & 1));
+        if (elect_one()) {   // S_{j+1} into the other buffer (both halves of P_{j-1} were consumed by the PVs issued last iteration)
+          issue_S(u ^ 1, stg_n);
+          tc_commit2(s_full(u ^ 1));
           tc_commit2(k_empty(stg_n));
         }
         __syncwarp();
       }
       mbar_wait(v_full(stg), par, 22);
-      mbar_wait(p_full(j & 1), (j >> 1) & 1, 24);   // both CTAs' P_j is in TMEM
-      tc_fence_after();
-      if (elect_one()) {
-        issue_PV(j & 1, stg, j > 0);
-        tc_commit2(o_done);
-        tc_commit2(v_empty(stg));
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        mbar_wait(p_full(u, w), (j >> 1) & 1, 24 + w);   // both CTAs' P_{j, w} is in TMEM
+        tc_fence_after();
+        if (elect_one()) {
+          issue_PV(u, w, stg, j > 0);
+          tc_commit2(o_done(w));
+          if (w == 1) tc_commit2(v_empty(stg));
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp < 8) {
-    // ===================== compute warpgroups: both work on every key tile, 64 columns each =====================
+    // ===================== compute warpgroups: warpgroup w owns key half w of every tile, independently =====================
     const int w = warp >> 2;
     const int r = (warp & 3) * 32 + lane;    // row within this CTA's Q tile == TMEM lane
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const int s = q0 + r;
     const bool row_ok = s < p.Sq;
     const float sl2 = p.scale * 1.4426950408889634f;
-    {  // stage this row's Q half (head-dim columns [64 w, 64 w + 64)) into TMEM as packed bf16 pairs
-      const __nv_bfloat16* src = pp.q + (long long)b * pp.q_b + (long long)s * pp.q_s + (long long)h * pp.q_h + 64 * w;
-      uint32_t v[32];
-#pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        const uint4 u = row_ok ? __ldg(reinterpret_cast<const uint4*>(src) + q4) : make_uint4(0u, 0u, 0u, 0u);
-        v[4 * q4 + 0] = u.x, v[4 * q4 + 1] = u.y, v[4 * q4 + 2] = u.z, v[4 * q4 + 3] = u.w;
-      }
-      tmem_st_32x32b_x32(QT + lane_off + 32 * w, v);
-      tc_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(q_ready, 0u);
-    }
-    float* mx = scratch_f;                 // [2 (j parity)][2 (warpgroup)][128]
-    float* lx = scratch_f + 2 * 2 * 128;   // [2 (warpgroup)][128]
-    const uint32_t o_t = O_col + lane_off + 64 * w;   // this warpgroup rescales / stores O columns [64 w, +64)
-    float m_used = -INFINITY;  // raw-score max currently baked into O and l
-    float l = 0.f;             // this thread's partial row sum (its 64 columns of every tile)
+    const uint32_t o_t = O_col(w) + lane_off;
+    float m_used = -INFINITY;  // raw-score max currently baked into O_w and l
+    float l = 0.f;
 
     for (int j = 0; j < n_kv; ++j) {
       const int u = j & 1;
@@ -217,7 +214,7 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
       l += 1.f;
       if (kv_valid < -1000000 && ragged) m_used = 0.f;
 #else
-      // ---- pass 1: max over this half, then exchange with the other warpgroup
+      // ---- pass 1: max over this half
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
@@ -237,22 +234,19 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
           m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
         }
       }
-      float m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      mx[(u * 2 + w) * 128 + r] = m_tile;
-      named_bar_sync(2, 256);
-      m_tile = fmaxf(m_tile, mx[(u * 2 + (w ^ 1)) * 128 + r]);
-      // ---- lazy rescale (both warpgroups take the same decision for the same rows)
-      const bool need = (m_tile - m_used) * sl2 > 8.0f;  // true on the first tile (m_used = -inf)
+      const float m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      // ---- lazy rescale of this warpgroup's accumulator (warp-uniform decision; -inf - -inf = NaN compares false)
+      const bool need = (m_tile - m_used) * sl2 > 8.0f;
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = fmaxf(m_used, m_tile);
-        const float alpha = ex2f((m_used - m_new) * sl2);  // 0 on the first tile
+        const float alpha = (m_used == -INFINITY) ? 0.f : ex2f((m_used - m_new) * sl2);
         l *= alpha;
         m_used = m_new;
         if (j > 0) {
-          mbar_wait(o_done, (j - 1) & 1, 31);  // PV_{j-1} has landed in O
+          mbar_wait(o_done(w), (j - 1) & 1, 31);  // PV_{j-1, w} has landed in O_w
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < 64; c += 32) {
+          for (int c = 0; c < HD; c += 32) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(o_t + c, v);
             tc_wait_ld();
@@ -264,7 +258,7 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
         }
       }
       // ---- pass 2: P = exp2(s*sl2 - m*sl2) -> bf16, packed into the first 32 columns of this half
-      const float mb = m_used * sl2;
+      const float mb = (m_used == -INFINITY) ? 0.f : m_used * sl2;   // a half with no valid key so far: exp2(-inf) = 0
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
@@ -292,36 +286,42 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(p_full(u), 0u);
+      if (lane == 0) mbar_arrive_remote(p_full(u, w), 0u);
     }
 
-    // ---- epilogue: O / l -> bf16 -> global (this warpgroup's 64 columns); LSE
-    lx[w * 128 + r] = l;
+    // ---- epilogue: merge the two half-accumulators: O = (O_0 a_0 + O_1 a_1) / (l_0 a_0 + l_1 a_1), a_w = 2^((m_w - M) sl2)
+    scratch_f[(w * 2 + 0) * 128 + r] = m_used;
+    scratch_f[(w * 2 + 1) * 128 + r] = l;
     named_bar_sync(2, 256);
-    l += lx[(w ^ 1) * 128 + r];
-    mbar_wait(o_done, (n_kv - 1) & 1, 32);
+    const float m_o = scratch_f[((w ^ 1) * 2 + 0) * 128 + r], l_o = scratch_f[((w ^ 1) * 2 + 1) * 128 + r];
+    const float M = fmaxf(m_used, m_o);
+    const float a_me = (m_used == -INFINITY) ? 0.f : ex2f((m_used - M) * sl2);
+    const float a_ot = (m_o == -INFINITY) ? 0.f : ex2f((m_o - M) * sl2);
+    const float lsum = l * a_me + l_o * a_ot;
+    const float inv_l = 1.f / lsum;
+    const float a0 = (w == 0 ? a_me : a_ot) * inv_l, a1 = (w == 0 ? a_ot : a_me) * inv_l;
+    mbar_wait(o_done(0), (n_kv - 1) & 1, 32);
+    mbar_wait(o_done(1), (n_kv - 1) & 1, 33);
     tc_fence_after();
-    const float inv_l = 1.f / l;
     __nv_bfloat16* orow = p.O + (long long)b * p.o_b + (long long)s * p.o_s + (long long)h * p.o_h + 64 * w;
 #pragma unroll 1
-    for (int c = 0; c < 64; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(o_t + c, v);
+    for (int c = 0; c < 64; c += 32) {   // this warpgroup stores output columns [64 w, 64 w + 64)
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32b_x32(O_col(0) + lane_off + 64 * w + c, v0);
+      tmem_ld_32x32b_x32(O_col(1) + lane_off + 64 * w + c, v1);
       tc_wait_ld();
       if (row_ok) {
         uint4* dp = reinterpret_cast<uint4*>(orow + c);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          uint4 u4;
-          u4.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * inv_l, __uint_as_float(v[q * 8 + 1]) * inv_l);
-          u4.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * inv_l, __uint_as_float(v[q * 8 + 3]) * inv_l);
-          u4.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * inv_l, __uint_as_float(v[q * 8 + 5]) * inv_l);
-          u4.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * inv_l, __uint_as_float(v[q * 8 + 7]) * inv_l);
-          dp[q] = u4;
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v0[q * 8 + i]) * a0 + __uint_as_float(v1[q * 8 + i]) * a1;
+          dp[q] = pack8(o);
         }
       }
     }
-    if (w == 0 && row_ok && p.lse) p.lse[((long long)b * p.H + h) * p.Sq + s] = m_used * p.scale + logf(l);
+    if (w == 0 && row_ok && p.lse) p.lse[((long long)b * p.H + h) * p.Sq + s] = M * p.scale + logf(lsum);
   }
 
   tc_fence_before();
