@@ -214,25 +214,26 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
       l += 1.f;
       if (kv_valid < -1000000 && ragged) m_used = 0.f;
 #else
-      // ---- pass 1: max over this half
+      // ---- single TMEM read of this half (64 fp32 scores stay in registers): the forward is bound by the
+      // 64 B/clk TMEM read path, a second pass over S would double the per-tile time (attn_fwd.cuh reads it twice)
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32(s_t, va);
+      tmem_ld_32x32b_x32(s_t + 32, vb);
+      tc_wait_ld();
+      if (ragged) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= kv_valid) va[i] = 0xff800000u;       // -inf
+          if (32 + i >= kv_valid) vb[i] = 0xff800000u;
+        }
+      }
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(s_t + c, v);
-        tc_wait_ld();
-        if (ragged) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i >= kv_valid) v[i] = 0xff800000u;  // -inf
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          m0 = fmaxf(m0, __uint_as_float(v[i]));
-          m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
-          m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
-          m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
-        }
+      for (int i = 0; i < 32; i += 4) {
+        m0 = fmaxf(m0, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+        m1 = fmaxf(m1, fmaxf(__uint_as_float(va[i + 1]), __uint_as_float(vb[i + 1])));
+        m2 = fmaxf(m2, fmaxf(__uint_as_float(va[i + 2]), __uint_as_float(vb[i + 2])));
+        m3 = fmaxf(m3, fmaxf(__uint_as_float(va[i + 3]), __uint_as_float(vb[i + 3])));
       }
       const float m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       // ---- lazy rescale of this warpgroup's accumulator (warp-uniform decision; -inf - -inf = NaN compares false)
@@ -257,29 +258,29 @@ attn_fwd_pair_kernel(const __grid_constant__ AttnFwdPairMaps maps, const AttnFwd
           tc_wait_st();
         }
       }
-      // ---- pass 2: P = exp2(s*sl2 - m*sl2) -> bf16, packed into the first 32 columns of this half
+      // ---- P = exp2(s*sl2 - m*sl2) -> bf16, packed into the first 32 columns of this half
       const float mb = (m_used == -INFINITY) ? 0.f : m_used * sl2;   // a half with no valid key so far: exp2(-inf) = 0
       float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(s_t + c, v);
-        tc_wait_ld();
-        if (ragged) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i >= kv_valid) v[i] = 0xff800000u;  // exp2(-inf) = 0
-        }
+      {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float x0 = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mb));
-          const float x1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -mb));
+          const float x0 = ex2f(fmaf(__uint_as_float(va[i]), sl2, -mb));
+          const float x1 = ex2f(fmaf(__uint_as_float(va[i + 1]), sl2, -mb));
           l0 += x0;
           l1 += x1;
           pk[i / 2] = pack_bf16x2(x0, x1);
         }
-        tmem_st_32x32b_x16(s_t + c / 2, pk);
+        tmem_st_32x32b_x16(s_t, pk);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float x0 = ex2f(fmaf(__uint_as_float(vb[i]), sl2, -mb));
+          const float x1 = ex2f(fmaf(__uint_as_float(vb[i + 1]), sl2, -mb));
+          l0 += x0;
+          l1 += x1;
+          pk[i / 2] = pack_bf16x2(x0, x1);
+        }
+        tmem_st_32x32b_x16(s_t + 16, pk);
       }
       l += l0 + l1;
 #endif
