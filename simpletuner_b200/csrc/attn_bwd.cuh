@@ -11,10 +11,14 @@
 //       same smem bytes through MN-major descriptors).
 //   attn_bwd_dq_kernel   : one CTA per (b, h, 128-row query tile); streams 64-key tiles (lane = query
 //       row): S = Q K^T, dP = dO V^T, dS -> TMEM bf16, dQ += dS K.
+//       Q and dO (the resident operands) live in TMEM as bf16 pairs — staged once by the compute warps — and feed
+//       the score MMAs in TS form: 2 KB instead of 6 KB of shared-memory operand fetch per MMA.
 // Both use 64-wide streamed tiles so that the score buffers are DOUBLE-BUFFERED in TMEM
-// (2 x 64 S + 2 x 64 dP + 256 accumulator columns = 512): two compute warpgroups alternate tiles
-// (warpgroup w owns tiles i = w mod 2 and TMEM buffer w) while the tensor pipe already works on the
-// next tile's S / dP — the exp / dS math is off the MMA critical path.
+// (2 x 64 S + 2 x 64 dP + accumulators [+ Q / dO in dq] = 512 columns): while the compute warps turn tile i into
+// P / dS the tensor pipe already works on tile i+1's S / dP.  Both compute warpgroups work on every tile (warpgroup
+// w owns 32 of its 64 columns and packs its bf16 result into the first 16 columns of its own range, PK_COL).
+// What bounds them is the MMA path itself (SS / TS N = 64 instruction rates, tools/probe/mma_probe.cu), not the
+// exp / dS math: see DESIGN.md 3.3.
 // warps 0-3 / 4-7 = compute warpgroups, warp 8 = TMA producer, warp 9 = MMA issuer, warp 10 = TMEM alloc.
 #pragma once
 #include "../../include/stb200.h"

@@ -12,6 +12,9 @@
 // allocator, warps 4..7 = epilogue (TMEM -> registers -> fused epilogue -> global).
 // A CTA owns MT x 128 rows and BN columns of D per tile; TMEM holds 512/(MT*BN) accumulator
 // stages so the epilogue of tile i overlaps the mainloop of tile i+1 when there are >= 2.
+// PAIR = true is the default for large problems: a 2-CTA cluster (cta_group::2) owns a 256 x BN tile, each CTA
+// stages half of it, the leader issues M = 256 MMAs (see the comment at the kernel).  CONV = true turns the A
+// operand into the shifted NHWC window of a 3x3 convolution (implicit GEMM, VAE encoder).
 #pragma once
 #include <type_traits>
 #include "common.cuh"
