@@ -94,12 +94,11 @@ class Flux:
             raise ValueError("Received invalid value for latents.")
         batch["latents"] = latents.to(**kw, non_blocking=True).contiguous()
         # noise, then sigma draw — same order and generators as common.py:5938, 5068
-        noise = torch.randn_like(batch["latents"])
+        from ..training.noise import sample_noise
+        noise, input_noise = sample_noise(c, batch["latents"], state, flow_matching=True)
         bsz = batch["latents"].shape[0]
         batch["noise"] = noise
-        if c.input_perturbation != 0:
-            raise NotImplementedError("input_perturbation is not part of the B200 step (reference default 0.0)")
-        batch["input_noise"] = noise
+        batch["input_noise"] = input_noise.to(batch["latents"].dtype).contiguous()
         sigmas, timesteps = sample_flow_sigmas(c, self.noise_schedule, bsz, noise, dev)
         batch["timesteps"] = timesteps
         batch["sigmas"] = sigmas.view(-1, 1, 1, 1)  # expand_sigmas, common.py:6825-6828

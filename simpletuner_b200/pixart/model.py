@@ -108,11 +108,11 @@ class PixartSigma(Flux):
         mask = batch.get("encoder_attention_mask")
         if mask is not None and hasattr(mask, "to"):
             batch["encoder_attention_mask"] = mask.to(**kw)
-        noise = torch.randn_like(batch["latents"])                       # common.py:5938
+        from ..training.noise import sample_noise
+        noise, input_noise = sample_noise(c, batch["latents"], state, flow_matching=False)   # common.py:5936-5967
         bsz = batch["latents"].shape[0]
-        if c.offset_noise or c.input_perturbation != 0:
-            raise NotImplementedError("offset_noise / input_perturbation are not part of the B200 step (reference defaults off)")
-        batch["noise"] = batch["input_noise"] = noise
+        batch["noise"] = noise.to(batch["latents"].dtype).contiguous()
+        batch["input_noise"] = input_noise.to(batch["latents"].dtype).contiguous()
         n_t = self.noise_schedule.config.num_train_timesteps
         weights = generate_timestep_weights(c, n_t).to(dev)              # common.py:5982-5984
         if bsz > 1 and not c.disable_segmented_timestep_sampling:
@@ -120,7 +120,7 @@ class PixartSigma(Flux):
         else:
             batch["timesteps"] = torch.multinomial(weights, bsz, replacement=True).long()
         ca, cb = self._coefs(batch["timesteps"], dev)
-        noisy, packed = ops.ddpm_prep_pack(batch["latents"], noise, ca, cb, want_unpacked=True, want_packed=True)
+        noisy, packed = ops.ddpm_prep_pack(batch["latents"], batch["input_noise"], ca, cb, want_unpacked=True, want_packed=True)
         batch["noisy_latents"] = noisy
         batch["_packed_noisy_latents"] = packed
         return batch

@@ -55,6 +55,29 @@ def min_snr_loss_weights(timesteps: torch.Tensor, noise_scheduler, snr_gamma: fl
     return w / snr
 
 
+def sample_noise(config, latents: torch.Tensor, state, flow_matching: bool):
+    """common.py:5936-5967: `noise = randn_like(latents)`, optional offset noise (epsilon / v families only), optional
+    input perturbation of the noise that goes into the noisy latents (the loss target keeps the unperturbed `noise`).
+    Draw order — randn_like, [random.random() gate], [randn(B, C, 1, 1)], [randn_like] — is the reference's, so a seeded
+    run consumes the generators identically.  Returns (noise, input_noise)."""
+    import random
+
+    noise = torch.randn_like(latents)
+    if not flow_matching and getattr(config, "offset_noise", False):
+        prob = getattr(config, "noise_offset_probability", 0.25)
+        if prob == 1.0 or random.random() < prob:
+            noise = noise + getattr(config, "noise_offset", 0.1) * torch.randn(
+                latents.shape[0], latents.shape[1], 1, 1, device=latents.device)
+    input_noise = noise
+    pert = getattr(config, "input_perturbation", 0.0)
+    steps = getattr(config, "input_perturbation_steps", None)
+    if pert != 0 and (not steps or state["global_step"] < steps):
+        if steps:
+            pert = pert * (1.0 - (state["global_step"] / steps))
+        input_noise = noise + pert * torch.randn_like(latents)
+    return noise, input_noise
+
+
 def compute_scheduled_huber_c(config, noise_scheduler, timesteps: torch.Tensor, prediction_type: str) -> torch.Tensor:
     """common.py:6168-6215, vectorised over the batch: per-sample `huber_c` (fp32 [B]) for loss_type huber / smooth_l1.
     The reference evaluates it one sample at a time (`timesteps[i:i+1]` -> `.item()`, common.py:6262-6266, 6334-6338);

@@ -36,3 +36,32 @@ def test_add_noise_velocity_and_min_snr():
     torch.testing.assert_close(w, torch.minimum(snr, torch.tensor(5.0)) / snr)
     wv = N.min_snr_loss_weights(t, sched, 5.0, "v_prediction")
     torch.testing.assert_close(wv, torch.minimum(snr, torch.tensor(5.0)) / (snr + 1))
+
+
+def test_sample_noise_draw_order_and_options():
+    """common.py:5936-5967: randn_like -> [random() gate] -> [randn(B,C,1,1)] -> [randn_like]; the loss target keeps
+    the unperturbed noise, only `input_noise` carries the perturbation; flow matching never applies offset noise."""
+    import random
+    from types import SimpleNamespace
+
+    from simpletuner_b200.training.noise import sample_noise
+
+    lat = torch.zeros(3, 4, 5, 6)
+    cfg = SimpleNamespace(offset_noise=True, noise_offset=0.1, noise_offset_probability=1.0, input_perturbation=0.2,
+                          input_perturbation_steps=100)
+    torch.manual_seed(7)
+    random.seed(7)
+    noise, inp = sample_noise(cfg, lat, {"global_step": 25}, flow_matching=False)
+    torch.manual_seed(7)
+    n0 = torch.randn_like(lat)
+    n1 = n0 + 0.1 * torch.randn(3, 4, 1, 1)
+    i1 = n1 + 0.2 * (1.0 - 25 / 100) * torch.randn_like(lat)
+    assert torch.equal(noise, n1) and torch.equal(inp, i1)
+    torch.manual_seed(7)
+    noise_f, inp_f = sample_noise(cfg, lat, {"global_step": 250}, flow_matching=True)   # past the perturbation window
+    assert torch.equal(noise_f, n0) and inp_f is noise_f
+    cfg.noise_offset_probability = 0.0
+    torch.manual_seed(7)
+    random.seed(1)
+    noise_g, _ = sample_noise(cfg, lat, {"global_step": 250}, flow_matching=False)
+    assert torch.equal(noise_g, n0)
