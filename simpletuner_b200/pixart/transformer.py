@@ -348,7 +348,17 @@ class PixArtTransformer2DModel(nn.Module):
 
     # ---- reference-facing utilities -------------------------------------------------------------
     def enable_gradient_checkpointing(self):
+        """Re-run every transformer block in backward (torch.utils.checkpoint, as the reference does); off by default."""
         self.gradient_checkpointing = True
+
+    def disable_gradient_checkpointing(self):
+        self.gradient_checkpointing = False
+
+    def _run_block(self, blk, *args):
+        if self.gradient_checkpointing and torch.is_grad_enabled():
+            from torch.utils.checkpoint import checkpoint
+            return checkpoint(blk, *args, use_reentrant=False)
+        return blk(*args)
 
     def invalidate_plans(self):
         for blk in self.transformer_blocks:
@@ -484,7 +494,7 @@ class PixArtTransformer2DModel(nn.Module):
         if self._pad_index is None and hdp != hd:
             self._pad_index = (torch.arange(H, device=dev)[:, None] * hdp + torch.arange(hd, device=dev)[None, :]).reshape(-1)
         for blk in self.transformer_blocks:
-            h = blk(h, ctx, kbias, t6, self._lora_scaling, self._pad_index)
+            h = self._run_block(blk, h, ctx, kbias, t6, self._lora_scaling, self._pad_index)
         # 3. output: LN -> (scale_shift_table + embedded) modulate -> proj_out  (reference :749-760)
         mod = (self.scale_shift_table[None] + embedded[:, None].to(self.scale_shift_table.dtype)).to(dt)  # [B, 2, D] (shift | scale)
         mod = torch.cat([mod[:, 1], mod[:, 0]], dim=1).contiguous()                                         # TailFn wants (scale | shift)

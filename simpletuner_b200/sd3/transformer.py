@@ -178,7 +178,17 @@ class SD3Transformer2DModel(nn.Module):
 
     # ---- reference-facing utilities -------------------------------------------------------------
     def enable_gradient_checkpointing(self):
+        """Re-run every joint block in backward (torch.utils.checkpoint, as the reference does); off by default."""
         self.gradient_checkpointing = True
+
+    def disable_gradient_checkpointing(self):
+        self.gradient_checkpointing = False
+
+    def _run_block(self, blk, *args):
+        if self.gradient_checkpointing and torch.is_grad_enabled():
+            from torch.utils.checkpoint import checkpoint
+            return checkpoint(blk, *args, use_reentrant=False)
+        return blk(*args)
 
     def invalidate_plans(self):
         for blk in self.transformer_blocks:
@@ -292,7 +302,7 @@ class SD3Transformer2DModel(nn.Module):
         temb = tte.timestep_embedder(_sinusoid(timestep.to(dev).float()).to(dt)) + tte.text_embedder(pooled_projections.to(dt).contiguous())
         silu_temb = F.silu(temb).contiguous()
         for blk in self.transformer_blocks:
-            h = blk(h, silu_temb, S_txt, self._lora_scaling)
+            h = self._run_block(blk, h, silu_temb, S_txt, self._lora_scaling)
         if self._tail_plan is None:
             self._tail_plan = {"w_proj": self.proj_out.weight.detach(), "b_proj": self.proj_out.bias.detach(),
                                "w_proj_t": _t(self.proj_out.weight.detach())}

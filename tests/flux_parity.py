@@ -52,13 +52,17 @@ def build_cuda_model(cfg, P, lora, rank, device="cuda"):
     return wrapper
 
 
-def run_parity(cfg=None, B=2, Hh=16, Ww=16, S_txt=64, rank=16, seed=0, device="cuda"):
+def run_parity(cfg=None, B=2, Hh=16, Ww=16, S_txt=64, rank=16, seed=0, device="cuda", checkpoint=False, interval=None):
     """Returns a dict of measured deviations (and asserts nothing)."""
     cfg = cfg or small_config()
     P = {k: v.bfloat16().float() for k, v in O.init_flux_params(cfg, seed=seed).items()}
     L = {k: v.bfloat16().float() for k, v in O.init_lora_params(cfg, rank, seed=seed + 1, b_std=0.02).items()}
     batch = make_batch(B, Hh, Ww, S_txt, cfg, seed=seed + 2)
     w = build_cuda_model(cfg, P, L, rank, device)
+    if checkpoint:   # reference --gradient_checkpointing (+ interval): selected blocks are re-run in backward
+        w._denoiser().enable_gradient_checkpointing()
+        if interval:
+            w._denoiser().set_gradient_checkpointing_interval(interval)
     torch.manual_seed(1234)
     torch.cuda.manual_seed(1234)
     prepared = w.prepare_batch({k: v.clone() for k, v in batch.items()}, {"global_step": 0})

@@ -70,3 +70,13 @@ def test_lora_disabled_equals_base_model():
 def test_flux_step_parity_other_ranks(rank):
     # rank 4 is zero-padded to 8 inside the packed LoRA stacks; rank 32 -> a 96-wide fused q|k|v rank block
     _assert(FP.run_parity(cfg=FP.small_config(layers=1, single=1), rank=rank, seed=7))
+
+
+def test_flux_gradient_checkpointing_matches():
+    """enable_gradient_checkpointing(): blocks are re-run in backward (torch.utils.checkpoint around the block Functions);
+    the step result must stay inside the same tolerances, for every block and with an interval."""
+    from tests import flux_parity as FP
+    for kw in ({"checkpoint": True}, {"checkpoint": True, "interval": 2}):
+        res = FP.run_parity(**kw)
+        assert res["noisy_bit_exact"] and res["loss_rel_err"] <= FP.LOSS_RTOL and res["pred_cos"] >= FP.PRED_COS \
+            and res["grad_cos_min"] >= FP.GRAD_COS, (kw, res)
