@@ -287,6 +287,8 @@ def run_b200(args):
         cfg_over = dict(num_layers=1, num_single_layers=2, num_attention_heads=4, joint_attention_dim=256, pooled_projection_dim=64)
         hw, s_txt = 32, 64
     wrapper = build_model(device, cfg_over, rank=16, seed=0)
+    if args.gradient_checkpointing:   # non-default: the reference's --gradient_checkpointing memory / time trade-off
+        wrapper._denoiser().enable_gradient_checkpointing()
     if world > 1:
         wrap_ddp(wrapper, device_ids=[local_rank])
     params = wrapper._denoiser().trainable_parameters()
@@ -379,7 +381,8 @@ def run_b200(args):
             "config": {
                 "workload": "Flux.1-dev LoRA rank16 (flux_lora_target=all, 266 targets, 26.1M trainable) bf16, 1024^2 cached latents [B,16,128,128] + T5 [B,512,4096], train step = prepare_batch+fwd+loss+bwd+value-clip+AdamW",
                 "global_batch": B * world, "per_gpu_batch": B, "seq_len": S_IMG + S_TXT, "parallelism": f"dp{world}",
-                "activation_recompute": "none (block-native minimal saves; reference default would recompute every block)",
+                "activation_recompute": ("every block re-run in backward (--gradient-checkpointing)" if args.gradient_checkpointing else
+                                         "none (block-native minimal saves; reference default would recompute every block)"),
                 "host_syncs_in_step": 0, "l2_policy": "inputs larger than L2 (24 GB of weights + 16 MB fresh batch streamed every step)",
                 "lora_dropout": 0.0, "optimizer": "torch.optim.AdamW(fused) on bf16 LoRA params (reference adamw_bf16 is a §8f 'next' row)",
                 "tiny": bool(args.tiny),
@@ -416,6 +419,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--tiny", action="store_true", help="plumbing check on a toy config (not a benchmark value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gradient-checkpointing", action="store_true",
+                    help="re-run every block in backward like the reference's --gradient_checkpointing (not the headline config)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200" and not args.tiny:
         args.warmup = 3
