@@ -292,7 +292,11 @@ def run_b200(args):
     if world > 1:
         wrap_ddp(wrapper, device_ids=[local_rank])
     params = wrapper._denoiser().trainable_parameters()
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-2, fused=True)
+    if args.optimizer == "adamw_bf16":   # the reference's default optimizer, one libstb200 launch per step
+        from simpletuner_b200.training.optim import AdamWBF16
+        opt = AdamWBF16(params, lr=1e-4, weight_decay=1e-2, eps=1e-6, seed=1234 + rank)
+    else:
+        opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-2, fused=True)
     step = TrainStep(wrapper, opt, max_grad_norm=2.0, grad_clip_method="value")
     torch.manual_seed(42 + rank)  # seed_for_each_device=True (trainer.py:2554-2556)
     joint = cfg_over["joint_attention_dim"] if cfg_over else 4096
@@ -384,7 +388,8 @@ def run_b200(args):
                 "activation_recompute": ("every block re-run in backward (--gradient-checkpointing)" if args.gradient_checkpointing else
                                          "none (block-native minimal saves; reference default would recompute every block)"),
                 "host_syncs_in_step": 0, "l2_policy": "inputs larger than L2 (24 GB of weights + 16 MB fresh batch streamed every step)",
-                "lora_dropout": 0.0, "optimizer": "torch.optim.AdamW(fused) on bf16 LoRA params (reference adamw_bf16 is a §8f 'next' row)",
+                "lora_dropout": 0.0, "optimizer": ("adamw_bf16 (reference default; stochastic-rounding AdamW, one stb_adamw_bf16_multi launch)" if args.optimizer == "adamw_bf16"
+                              else "torch.optim.AdamW(fused) on bf16 LoRA params"),
                 "tiny": bool(args.tiny),
             },
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": batch_bytes(host_batches[0]), "d2h_bytes_per_step": 4,
@@ -419,6 +424,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--tiny", action="store_true", help="plumbing check on a toy config (not a benchmark value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="adamw", choices=["adamw", "adamw_bf16"])
     ap.add_argument("--gradient-checkpointing", action="store_true",
                     help="re-run every block in backward like the reference's --gradient_checkpointing (not the headline config)")
     args = ap.parse_args()

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -17,6 +18,7 @@
 #include "attn_bwd.cuh"
 #include "attn_fwd.cuh"
 #include "attn_fwd_pair.cuh"
+#include "optim.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "vae.cuh"
@@ -659,6 +661,24 @@ int stb_target_mse_loss(const void* pred_packed, const void* target, const float
   STB_LAUNCH_CHECK("target_mse_loss");
   return 0;
 }
+
+int stb_adamw_bf16_multi(const long long* ptrs, const long long* sizes, const float* decay, const int* blk_tensor,
+                         const long long* blk_off, int num_blocks, int T, float beta1, float beta2, float step, float lr,
+                         float eps, const int* rnd, const long long* rnd_off, long long rnd_plane, unsigned long long seed,
+                         void* stream) {
+  if (int r = check_device()) return r;
+  if (!ptrs || !sizes || !decay || !blk_tensor || !blk_off || num_blocks < 1 || T < 1) return fail(STB_ERR_ARG, "adamw_bf16_multi: bad tables");
+  if (!(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || eps < 0.f) return fail(STB_ERR_ARG, "adamw_bf16_multi: bad hyper-parameters");
+  // the Python floats of the reference (`1 - beta`, `-lr * (1 - beta2 ** step) ** 0.5`) are formed in double, then become fp32 kernel scalars
+  const float alpha1 = float(1.0 - double(beta1)), alpha2 = float(1.0 - double(beta2));
+  const float value = float(-double(lr) * std::sqrt(1.0 - std::pow(double(beta2), double(step))));
+  stb::adamw_bf16_multi_kernel<<<num_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ptrs, sizes, decay, blk_tensor, blk_off, T, beta1, beta2, alpha1, alpha2, value, eps, rnd, rnd_off, rnd_plane, seed);
+  STB_LAUNCH_CHECK("adamw_bf16_multi");
+  return 0;
+}
+
+int stb_adamw_bf16_chunk(void) { return stb::OPT_CHUNK; }
 
 int stb_gate_mul(const void* x, long long x_b, long long x_s, const void* gate, long long g_b, void* y,
                  long long y_b, long long y_s, int B, int S, int D, void* stream) {

@@ -1,0 +1,76 @@
+// simpletuner_b200 — multi-tensor AdamW-bf16 with stochastic rounding (the reference's default optimizer `adamw_bf16`),
+// one launch per optimizer step for every trainable tensor.
+// reference: helpers/training/optimizers/adamw_bfloat16/__init__.py:54-180 (`AdamWBF16.step`, `_make_step`) and
+//            .../stochastic/__init__.py:48-121 — ~25 tiny eager kernels per parameter tensor there.
+// Every rounding point of the eager chain is reproduced (bf16 tensors between ops, fp32 `result` buffers before each
+// stochastic rounding, CUDA scalar semantics: fp32 alpha / eps, addcdiv = fma(value, t1 / t2, self)); including the
+// reference's quirk that the first moment is `grad + (1 - beta1) * (beta1 * exp_avg)` (oracle/adamw_bf16_oracle.py).
+// Stochastic rounding: add a 16-bit random integer to the fp32 bit pattern, keep the upper 16 bits.  The integers come
+// either from a caller-supplied stream (parity tests) or from a counter-based hash of (seed, element, draw).
+#pragma once
+#include "common.cuh"
+#include "elementwise.cuh"
+
+namespace stb {
+
+__device__ __forceinline__ uint32_t hash_u32(uint64_t x) {   // splitmix64 finaliser -> upper bits
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return uint32_t((x ^ (x >> 31)) >> 32);
+}
+__device__ __forceinline__ float stochastic_bf16(float x, uint32_t rnd16) {
+  return __uint_as_float((__float_as_uint(x) + rnd16) & 0xFFFF0000u);
+}
+
+constexpr int OPT_CHUNK = 256 * 8;   // elements per block
+
+// ptrs: [5][T] device pointers (p, grad, exp_avg, exp_avg_sq, shift), all bf16 with sizes[t] elements
+__global__ void __launch_bounds__(256)
+adamw_bf16_multi_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ sizes, const float* __restrict__ decay,
+                        const int* __restrict__ blk_tensor, const long long* __restrict__ blk_off, int T, float beta1,
+                        float beta2, float alpha1, float alpha2, float value, float eps, const int* __restrict__ rnd,
+                        const long long* __restrict__ rnd_off, long long rnd_plane, unsigned long long seed) {
+  const int t = blk_tensor[blockIdx.x];
+  const long long n = sizes[t];
+  const long long i0 = blk_off[blockIdx.x];
+  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(ptrs[0 * T + t]);
+  const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(ptrs[1 * T + t]);
+  __nv_bfloat16* m = reinterpret_cast<__nv_bfloat16*>(ptrs[2 * T + t]);
+  __nv_bfloat16* v = reinterpret_cast<__nv_bfloat16*>(ptrs[3 * T + t]);
+  __nv_bfloat16* s = reinterpret_cast<__nv_bfloat16*>(ptrs[4 * T + t]);
+  const float dec = decay[t];
+  const long long roff = rnd_off ? rnd_off[t] : 0;
+  for (long long i = i0 + threadIdx.x; i < min(n, i0 + (long long)OPT_CHUNK); i += blockDim.x) {
+    uint32_t r0, r1, r2, r3;
+    if (rnd) {
+      r0 = uint32_t(rnd[0 * rnd_plane + roff + i]), r1 = uint32_t(rnd[1 * rnd_plane + roff + i]);
+      r2 = uint32_t(rnd[2 * rnd_plane + roff + i]), r3 = uint32_t(rnd[3 * rnd_plane + roff + i]);
+    } else {
+      const uint64_t key = (seed ^ (uint64_t(uint32_t(t)) << 40)) + uint64_t(i) * 4ull;
+      const uint32_t h0 = hash_u32(key), h1 = hash_u32(key + 2);
+      r0 = h0 & 0xFFFFu, r1 = h0 >> 16, r2 = h1 & 0xFFFFu, r3 = h1 >> 16;
+    }
+    const float gv = __bfloat162float(g[i]), pv = __bfloat162float(p[i]);
+    // exp_avg.mul_(beta1); add_stochastic_(exp_avg, grad, alpha = 1 - beta1)  ->  grad + alpha * exp_avg
+    const float m1 = bf16r(__bfloat162float(m[i]) * beta1);
+    const float m2 = stochastic_bf16(fmaf(alpha1, m1, gv), r0);
+    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+    const float v1 = bf16r(__bfloat162float(v[i]) * beta2);
+    const float v2 = bf16r(fmaf(__fmul_rn(alpha2, gv), gv, v1));
+    // addcdiv_stochastic_(shift, exp_avg, sqrt(exp_avg_sq) + eps, value = -lr * sqrt(1 - beta2^step))
+    const float den = bf16r(bf16r(sqrtf(v2)) + eps);
+    const float s1 = stochastic_bf16(fmaf(value, __fdiv_rn(m2, den), __bfloat162float(s[i])), r1);
+    // p += shift (stochastic); shift += (p_old - p_new) (stochastic): the part of the update bf16 could not hold
+    const float p1 = stochastic_bf16(__fadd_rn(s1, pv), r2);
+    const float diff = bf16r(__fsub_rn(pv, p1));
+    float s2 = stochastic_bf16(__fadd_rn(diff, s1), r3);
+    if (dec > 0.f) s2 = bf16r(fmaf(-dec, p1, s2));   // delayed weight decay goes into the remainder
+    p[i] = __float2bfloat16(p1);
+    m[i] = __float2bfloat16(m2);
+    v[i] = __float2bfloat16(v2);
+    s[i] = __float2bfloat16(s2);
+  }
+}
+
+}  // namespace stb
