@@ -178,13 +178,14 @@ int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* 
  *   ptrs      : device int64 [5][T] = pointers to p, grad, exp_avg, exp_avg_sq, shift (bf16, sizes[t] elements each)
  *   decay     : device fp32 [T] `decay_this_iteration` per tensor (0 = none; __init__.py:96-99 delayed weight decay)
  *   blk_tensor / blk_off : device [num_blocks] block -> (tensor, first element); a block covers stb_adamw_bf16_chunk() elements
- *   step, lr  : the reference's `state["step"]` (after the increment) and group lr; betas / eps as in the group
+ *   step, lr  : the reference's `state["step"]` (after the increment) and group lr; betas / eps as in the group — all as
+ *               doubles (Python floats): the derived fp32 scalars are formed exactly as the eager path forms them
  *   rnd       : optional device int32 [4][rnd_plane] 16-bit random integers in the reference's draw order (exp_avg, shift,
  *               p, shift) with per-tensor offsets rnd_off[T] — parity tests; NULL = counter-based generator keyed by `seed`
  * ------------------------------------------------------------------------------------------- */
 int stb_adamw_bf16_multi(const long long* ptrs, const long long* sizes, const float* decay, const int* blk_tensor,
-                         const long long* blk_off, int num_blocks, int T, float beta1, float beta2, float step, float lr,
-                         float eps, const int* rnd, const long long* rnd_off, long long rnd_plane, unsigned long long seed,
+                         const long long* blk_off, int num_blocks, int T, double beta1, double beta2, double step, double lr,
+                         double eps, const int* rnd, const long long* rnd_off, long long rnd_plane, unsigned long long seed,
                          void* stream);
 int stb_adamw_bf16_chunk(void);
 

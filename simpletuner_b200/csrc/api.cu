@@ -663,17 +663,18 @@ int stb_target_mse_loss(const void* pred_packed, const void* target, const float
 }
 
 int stb_adamw_bf16_multi(const long long* ptrs, const long long* sizes, const float* decay, const int* blk_tensor,
-                         const long long* blk_off, int num_blocks, int T, float beta1, float beta2, float step, float lr,
-                         float eps, const int* rnd, const long long* rnd_off, long long rnd_plane, unsigned long long seed,
+                         const long long* blk_off, int num_blocks, int T, double beta1, double beta2, double step, double lr,
+                         double eps, const int* rnd, const long long* rnd_off, long long rnd_plane, unsigned long long seed,
                          void* stream) {
   if (int r = check_device()) return r;
   if (!ptrs || !sizes || !decay || !blk_tensor || !blk_off || num_blocks < 1 || T < 1) return fail(STB_ERR_ARG, "adamw_bf16_multi: bad tables");
-  if (!(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || eps < 0.f) return fail(STB_ERR_ARG, "adamw_bf16_multi: bad hyper-parameters");
-  // the Python floats of the reference (`1 - beta`, `-lr * (1 - beta2 ** step) ** 0.5`) are formed in double, then become fp32 kernel scalars
-  const float alpha1 = float(1.0 - double(beta1)), alpha2 = float(1.0 - double(beta2));
-  const float value = float(-double(lr) * std::sqrt(1.0 - std::pow(double(beta2), double(step))));
+  if (!(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || eps < 0.0) return fail(STB_ERR_ARG, "adamw_bf16_multi: bad hyper-parameters");
+  // hyper-parameters arrive as the reference's Python floats (doubles): `1 - beta` and `-lr * (1 - beta2 ** step) ** 0.5`
+  // are formed in double there and only then become the fp32 scalars of the eager kernels
+  const float alpha1 = float(1.0 - beta1), alpha2 = float(1.0 - beta2);
+  const float value = float(-lr * std::sqrt(1.0 - std::pow(beta2, step)));
   stb::adamw_bf16_multi_kernel<<<num_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      ptrs, sizes, decay, blk_tensor, blk_off, T, beta1, beta2, alpha1, alpha2, value, eps, rnd, rnd_off, rnd_plane, seed);
+      ptrs, sizes, decay, blk_tensor, blk_off, T, float(beta1), float(beta2), alpha1, alpha2, value, float(eps), rnd, rnd_off, rnd_plane, seed);
   STB_LAUNCH_CHECK("adamw_bf16_multi");
   return 0;
 }
