@@ -424,7 +424,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--tiny", action="store_true", help="plumbing check on a toy config (not a benchmark value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--optimizer", default="adamw", choices=["adamw", "adamw_bf16"])
+    ap.add_argument("--optimizer", default="adamw_bf16", choices=["adamw", "adamw_bf16"],
+                    help="adamw_bf16 = the reference's default optimizer (one libstb200 launch); adamw = torch.optim.AdamW(fused)")
     ap.add_argument("--gradient-checkpointing", action="store_true",
                     help="re-run every block in backward like the reference's --gradient_checkpointing (not the headline config)")
     args = ap.parse_args()
