@@ -383,7 +383,7 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic (random-init Flux.1-dev architecture; seeded N(0,1) cached latents + T5/CLIP embeds)",
             "config": {
-                "workload": "Flux.1-dev LoRA rank16 (flux_lora_target=all, 266 targets, 26.1M trainable) bf16, 1024^2 cached latents [B,16,128,128] + T5 [B,512,4096], train step = prepare_batch+fwd+loss+bwd+value-clip+AdamW",
+                "workload": "Flux.1-dev LoRA rank16 (flux_lora_target=all, 266 targets, 26.1M trainable) bf16, 1024^2 cached latents [B,16,128,128] + T5 [B,512,4096], train step = prepare_batch+fwd+loss+bwd+value-clip+optimizer",
                 "global_batch": B * world, "per_gpu_batch": B, "seq_len": S_IMG + S_TXT, "parallelism": f"dp{world}",
                 "activation_recompute": ("every block re-run in backward (--gradient-checkpointing)" if args.gradient_checkpointing else
                                          "none (block-native minimal saves; reference default would recompute every block)"),
