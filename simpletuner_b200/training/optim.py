@@ -33,6 +33,7 @@ def build_block_map(sizes: List[int], chunk: int) -> Tuple[List[int], List[int]]
 
 class AdamWBF16(Optimizer):
     decay_threshold = 5e-3
+    _RING = 4   # pinned staging slots for the per-step pointer / decay tables
 
     def __init__(self, params, *, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, seed: Optional[int] = None):
         if not 0.0 <= eps:
@@ -62,8 +63,11 @@ class AdamWBF16(Optimizer):
                 "sizes": torch.tensor(sizes, dtype=torch.int64, device=dev),
                 "blk_tensor": torch.tensor(bt, dtype=torch.int32, device=dev),
                 "blk_off": torch.tensor(bo, dtype=torch.int64, device=dev),
-                "ptrs_host": torch.empty((5, T), dtype=torch.int64).pin_memory(),
-                "decay_host": torch.empty((T,), dtype=torch.float32).pin_memory(),
+                # pinned staging ring: the async H2D copy reads host memory when it EXECUTES, and the host thread may be
+                # several steps ahead of the GPU; a slot is rewritten only after the copy that last used it has completed
+                "ptrs_host": [torch.empty((5, T), dtype=torch.int64).pin_memory() for _ in range(self._RING)],
+                "decay_host": [torch.empty((T,), dtype=torch.float32).pin_memory() for _ in range(self._RING)],
+                "copied": [None] * self._RING, "slot": 0,
                 "ptrs": torch.empty((5, T), dtype=torch.int64, device=dev),
                 "decay": torch.empty((T,), dtype=torch.float32, device=dev),
                 "rnd_off": torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)[:-1].tolist()), dtype=torch.int64, device=dev),
@@ -108,7 +112,11 @@ class AdamWBF16(Optimizer):
             if len(steps) != 1:
                 raise NotImplementedError("parameters of one group with different step counts are not supported")
             pl = self._plan(ps)
-            ph, dh = pl["ptrs_host"], pl["decay_host"]
+            slot = pl["slot"]
+            pl["slot"] = (slot + 1) % self._RING
+            if pl["copied"][slot] is not None:
+                pl["copied"][slot].synchronize()     # normally long done (RING steps ago)
+            ph, dh = pl["ptrs_host"][slot], pl["decay_host"][slot]
             for t, p in enumerate(ps):
                 st = self.state[p]
                 ph[0, t], ph[1, t] = p.data_ptr(), p.grad.data_ptr()
@@ -116,6 +124,9 @@ class AdamWBF16(Optimizer):
                 dh[t] = decays[t]
             pl["ptrs"].copy_(ph, non_blocking=True)
             pl["decay"].copy_(dh, non_blocking=True)
+            ev = pl["copied"][slot] or torch.cuda.Event()
+            ev.record()
+            pl["copied"][slot] = ev
             stepf = float(next(iter(steps)))
             rnd_ptr, rnd_plane = None, 0
             if _rnd is not None:
