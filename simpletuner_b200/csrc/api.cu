@@ -343,7 +343,11 @@ int stb_gemm_bf16(const stb_gemm_args* a, void* stream) {
       const int clusters = num_sms() / 2;
       const long long waves2 = (t2 + clusters - 1) / clusters;
       const double fill_pair = double(t2) / double(waves2 * clusters);
-      if (t2 >= clusters && fill_pair >= 0.85 * std::max(fill(1), fill(2))) mt = 3;
+      // rows a 256-row pair tile actually uses, against the 128-row tiling (many short batches would leave one CTA of
+      // every pair idle)
+      const double u2 = double(a->rows_per_batch) / (256.0 * ((a->rows_per_batch + 255) / 256));
+      const double u1 = double(a->rows_per_batch) / (128.0 * ((a->rows_per_batch + 127) / 128));
+      if (t2 >= clusters && fill_pair >= 0.85 * std::max(fill(1), fill(2)) && u2 >= 0.85 * u1) mt = 3;
     }
   }
   if (mt == 3 && bn == 256) return launch_gemm<1, 256, true>(a, st);   // CTA-pair (cta_group::2) 256 x 256 tile
