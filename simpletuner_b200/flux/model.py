@@ -32,7 +32,7 @@ def default_config(**over) -> SimpleNamespace:
         weight_dtype=torch.bfloat16, base_weight_dtype=torch.bfloat16,
         flow_matching=True, flow_schedule_shift=3.0, flow_schedule_auto_shift=False, flow_sigmoid_scale=1.0,
         flow_use_uniform_schedule=False, flow_use_beta_schedule=False, flux_fast_schedule=False,
-        flux_guidance_mode="constant", flux_guidance_value=1.0,
+        flux_guidance_mode="constant", flux_guidance_value=1.0, flux_guidance_min=0.0, flux_guidance_max=4.0,
         input_perturbation=0.0, offset_noise=False, loss_type="l2", huber_c=0.1, huber_schedule="constant", snr_gamma=None,
         lora_rank=16, lora_alpha=None, lora_dropout=0.0, flux_lora_target="all",
         flux_attention_masked_training=False,
@@ -114,9 +114,14 @@ class Flux:
         if not self._denoiser().config.guidance_embeds:
             return None
         c = self.config
-        if c.flux_guidance_mode != "constant":
-            raise NotImplementedError("only flux_guidance_mode='constant' is implemented (reference default)")
-        return torch.full((bsz,), float(c.flux_guidance_value), device=device, dtype=torch.float32)
+        # flux/model.py:682-706 (`_flux_guidance_scales`): "constant" or one python `random.uniform` draw per sample
+        if c.flux_guidance_mode == "constant":
+            return torch.full((bsz,), float(c.flux_guidance_value), device=device, dtype=torch.float32)
+        if c.flux_guidance_mode == "random-range":
+            import random
+            scales = [random.uniform(c.flux_guidance_min, c.flux_guidance_max) for _ in range(bsz)]
+            return torch.tensor(scales, device=device, dtype=torch.float32)
+        raise ValueError(f"Unsupported Flux guidance mode: {c.flux_guidance_mode!r}.")
 
     def model_predict(self, prepared_batch: Dict[str, Any]) -> Dict[str, Any]:
         """flux/model.py:707-864.  Returns `model_prediction` in the PACKED token layout plus the

@@ -101,3 +101,24 @@ def test_rope_tables_product_equals_oracle():
     c2, s2 = O.rope_tables(ids, (16, 56, 56))
     assert torch.equal(c1, c2) and torch.equal(s1, s2)
     assert torch.all(c1[:5] == 1) and torch.all(s1[:5] == 0)  # text tokens: identity rotation (quirk Q9)
+
+
+def test_flux_guidance_modes_follow_reference_draws():
+    """flux/model.py:682-706: constant value, or `random.uniform(min, max)` once per sample from python's generator."""
+    import random
+    from types import SimpleNamespace
+
+    from simpletuner_b200.flux.model import Flux, default_config
+
+    w = Flux.__new__(Flux)
+    w.model = SimpleNamespace(config=SimpleNamespace(guidance_embeds=True))
+    w.config = default_config(flux_guidance_mode="random-range", flux_guidance_min=1.5, flux_guidance_max=3.5)
+    random.seed(11)
+    got = w._guidance(3, "cpu")
+    random.seed(11)
+    want = [random.uniform(1.5, 3.5) for _ in range(3)]
+    assert torch.allclose(got, torch.tensor(want, dtype=torch.float32))
+    w.config = default_config()
+    assert torch.equal(w._guidance(2, "cpu"), torch.ones(2))
+    w.model.config.guidance_embeds = False
+    assert w._guidance(2, "cpu") is None
