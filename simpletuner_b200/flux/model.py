@@ -99,7 +99,10 @@ class Flux:
         bsz = batch["latents"].shape[0]
         batch["noise"] = noise
         batch["input_noise"] = input_noise.to(batch["latents"].dtype).contiguous()
-        sigmas, timesteps = sample_flow_sigmas(c, self.noise_schedule, bsz, noise, dev)
+        if getattr(self, "_sigma_sampler", None) is None:   # keeps the round-robin cursor of custom timestep lists
+            from ..training.schedule import FlowSigmaSampler
+            self._sigma_sampler = FlowSigmaSampler(c, self.noise_schedule, dev)
+        sigmas, timesteps = self._sigma_sampler.sample(bsz, noise, state)
         batch["timesteps"] = timesteps
         batch["sigmas"] = sigmas.view(-1, 1, 1, 1)  # expand_sigmas, common.py:6825-6828
         # fused: noisy = (1 - s) x + s eps  AND  2x2 patchify  (common.py:4975-4992, flux/__init__.py:25-30)

@@ -118,3 +118,120 @@ def sample_flow_sigmas(config, noise_scheduler, bsz: int, noise: Optional[torch.
         sigmas = torch.sigmoid(getattr(config, "flow_sigmoid_scale", 1.0) * normal)
     sigmas = apply_flow_schedule_shift(config, noise_scheduler, sigmas, noise)
     return sigmas, sigmas * 1000.0
+
+
+# --------------------------------------------------------------------------------------------------
+# full `sample_flow_sigmas` (every branch except the cubic-spline schedule), with the round-robin cursor state
+# --------------------------------------------------------------------------------------------------
+def normalize_flow_custom_timesteps(raw_value, device=None) -> Optional[torch.Tensor]:
+    """common.py:4799-4838: comma/semicolon separated string, JSON list, array or tensor -> finite 1-D fp32 tensor."""
+    import json
+
+    if raw_value is None or (isinstance(raw_value, str) and raw_value in ("", "None")):
+        return None
+    candidate = raw_value
+    if isinstance(candidate, str):
+        stripped = candidate.strip()
+        if stripped == "":
+            return None
+        try:
+            candidate = json.loads(stripped)
+        except Exception:
+            segments = [seg for seg in stripped.replace(";", ",").split(",") if seg.strip()]
+            try:
+                candidate = [float(seg.strip()) for seg in segments]
+            except Exception:
+                return None
+    if hasattr(candidate, "tolist") and not torch.is_tensor(candidate):
+        candidate = candidate.tolist()
+    try:
+        tensor = torch.as_tensor(candidate, device=device, dtype=torch.float32).flatten()
+    except Exception:
+        return None
+    if tensor.numel() == 0:
+        return None
+    finite = torch.isfinite(tensor)
+    if not torch.all(finite):
+        tensor = tensor[finite]
+    return tensor if tensor.numel() else None
+
+
+class FlowSigmaSampler:
+    """Stateful mirror of `ModelFoundation.sample_flow_sigmas` (common.py:4994-5090) + the round-robin cursor helpers
+    (`reset_flow_custom_timestep_cursor`).  `layout_fn(bsz)` returns an object with `global_batch_size` and
+    `local_batch_offset` (training.dist.resolve_batch_layout by default), so ranks with different local batch sizes walk
+    disjoint slices of the custom list exactly like the reference (tests/test_flow_custom_timesteps.py)."""
+
+    def __init__(self, config, noise_scheduler, device, layout_fn=None):
+        self.config, self.noise_scheduler, self.device = config, noise_scheduler, device
+        if layout_fn is None:
+            from .dist import resolve_batch_layout
+            layout_fn = lambda bsz: resolve_batch_layout(bsz, device)
+        self._layout_fn = layout_fn
+        self._cursor: Optional[int] = None
+        self._resume_step: Optional[int] = None
+        self._warned = False
+
+    def reset_cursor(self, global_step: Optional[int] = None):
+        """common.py `reset_flow_custom_timestep_cursor`: forget the cursor; the next draw re-derives it from the step."""
+        self._cursor = None
+        self._resume_step = None if global_step is None else int(global_step)
+
+    def sample(self, bsz: int, noise: Optional[torch.Tensor], state: Optional[dict] = None, timestep_offset: float = 0.0):
+        import random
+
+        c, dev = self.config, self.device
+        state = state or {}
+        if getattr(c, "mixflow_enabled", False) is True:
+            sigmas = 1.0 - torch.sqrt(torch.rand((bsz,), device=dev))
+            sigmas = apply_flow_schedule_shift(c, self.noise_scheduler, sigmas, noise)
+            return sigmas, sigmas * 1000.0
+        custom = normalize_flow_custom_timesteps(getattr(c, "flow_custom_timesteps", None), dev)
+        if custom is not None:
+            mode = str(getattr(c, "flow_timesteps_mode", "fixed-list") or "fixed-list").replace("_", "-")
+            if mode not in {"fixed-list", "round-robin"}:
+                raise ValueError("flow_timesteps_mode must be either 'fixed-list' or 'round-robin'.")
+            if torch.max(custom) <= 1.0:     # values <= 1 are sigmas, otherwise timesteps in [0, 1000]
+                base_sigmas = custom.clamp(0.0, 1.0)
+                base_t = base_sigmas * 1000.0
+            else:
+                base_t = custom.clamp(0.0, 1000.0)
+                base_sigmas = (base_t / 1000.0).clamp(0.0, 1.0)
+            n = base_t.numel()
+            if n == 1:
+                return base_sigmas.expand(bsz), base_t.expand(bsz)
+            if mode == "round-robin":
+                layout = self._layout_fn(bsz)
+                g = int(layout.global_batch_size)
+                if n < g and not self._warned:
+                    self._warned = True   # the reference logs a warning once: ranks may reuse entries on the same step
+                if self._cursor is None:
+                    completed = int(self._resume_step if self._resume_step is not None else state.get("global_step", 0) or 0)
+                    self._cursor = (completed * g) % n
+                    self._resume_step = None
+                idx = (torch.arange(bsz, device=dev) + self._cursor + int(layout.local_batch_offset)) % n
+                self._cursor = (self._cursor + g) % n
+            else:
+                idx = torch.randint(0, n, (bsz,), device=dev)
+            return base_sigmas[idx], base_t[idx]
+        if getattr(c, "flow_cubic_schedule", None) or getattr(c, "flow_cubic_schedule_weights", None):
+            raise NotImplementedError("the cubic-spline flow schedule is not part of the B200 step")
+        fast = getattr(c, "flux_fast_schedule", False)
+        beta = getattr(c, "flow_use_beta_schedule", False)
+        uniform = getattr(c, "flow_use_uniform_schedule", False)
+        if not fast and not beta and not uniform:
+            normal = torch.randn((bsz,), device=dev)
+            if timestep_offset:
+                normal = normal + timestep_offset
+            sigmas = torch.sigmoid(getattr(c, "flow_sigmoid_scale", 1.0) * normal)
+            sigmas = apply_flow_schedule_shift(c, self.noise_scheduler, sigmas, noise)
+        elif uniform:
+            sigmas = torch.rand((bsz,), device=dev)
+            sigmas = apply_flow_schedule_shift(c, self.noise_scheduler, sigmas, noise)
+        elif beta:
+            from torch.distributions import Beta
+            sigmas = Beta(c.flow_beta_schedule_alpha, c.flow_beta_schedule_beta).sample((bsz,)).to(device=dev)
+            sigmas = apply_flow_schedule_shift(c, self.noise_scheduler, sigmas, noise)
+        else:
+            sigmas = torch.tensor(random.choices([1.0] * 7 + [0.75, 0.5, 0.25], k=bsz), device=dev)
+        return sigmas, sigmas * 1000.0

@@ -122,3 +122,82 @@ def test_flux_guidance_modes_follow_reference_draws():
     assert torch.equal(w._guidance(2, "cpu"), torch.ones(2))
     w.model.config.guidance_embeds = False
     assert w._guidance(2, "cpu") is None
+
+
+# ---- custom timestep lists: the reference's own known answers (reference tests/test_flow_custom_timesteps.py:33-118)
+def _sampler(custom, mode, world=(2,), rank=0):
+    from types import SimpleNamespace
+
+    from simpletuner_b200.training.schedule import FlowSigmaSampler
+
+    cfg = SimpleNamespace(flow_custom_timesteps=custom, flow_timesteps_mode=mode)
+    sizes = list(world)
+
+    def layout(bsz):
+        return SimpleNamespace(global_batch_size=sum(sizes), local_batch_offset=sum(sizes[:rank]))
+
+    return FlowSigmaSampler(cfg, None, "cpu", layout_fn=layout)
+
+
+def test_round_robin_cycles_custom_timesteps():
+    s = _sampler("100,200,300", "round-robin", world=(2,))
+    assert torch.equal(s.sample(2, None, {})[1], torch.tensor([100.0, 200.0]))
+    assert torch.equal(s.sample(2, None, {})[1], torch.tensor([300.0, 100.0]))
+
+
+def test_round_robin_offsets_distributed_ranks_and_varying_batch_sizes():
+    r0, r1 = _sampler("100,200,300,400,500", "round-robin", (2, 2), 0), _sampler("100,200,300,400,500", "round-robin", (2, 2), 1)
+    assert torch.equal(r0.sample(2, None, {"global_step": 0})[1], torch.tensor([100.0, 200.0]))
+    assert torch.equal(r1.sample(2, None, {"global_step": 0})[1], torch.tensor([300.0, 400.0]))
+    assert torch.equal(r0.sample(2, None, {"global_step": 0})[1], torch.tensor([500.0, 100.0]))
+    lst = "100,200,300,400,500,600,700,800"
+    r0, r1 = _sampler(lst, "round-robin", (1, 3), 0), _sampler(lst, "round-robin", (1, 3), 1)
+    assert torch.equal(r0.sample(1, None, {"global_step": 0})[1], torch.tensor([100.0]))
+    assert torch.equal(r1.sample(3, None, {"global_step": 0})[1], torch.tensor([200.0, 300.0, 400.0]))
+    assert torch.equal(r0.sample(1, None, {"global_step": 0})[1], torch.tensor([500.0]))
+
+
+def test_round_robin_resume_and_reset():
+    s = _sampler("100,200,300,400,500", "round-robin", (2, 2), 0)
+    assert torch.equal(s.sample(2, None, {"global_step": 1})[1], torch.tensor([500.0, 100.0]))    # cursor = 1 * 4 % 5
+    s = _sampler("100,200,300,400,500", "round-robin", (2, 2), 0)
+    s.sample(2, None, {"global_step": 0})
+    s.reset_cursor(global_step=1)
+    assert torch.equal(s.sample(2, None, {"global_step": 1})[1], torch.tensor([500.0, 100.0]))
+
+
+def test_custom_list_modes_and_sigma_interpretation():
+    import pytest as _pt
+    with _pt.raises(ValueError, match="flow_timesteps_mode"):
+        _sampler("100,200", "sequential").sample(1, None, {})
+    sig, t = _sampler("0.25;0.5", "fixed-list").sample(64, None, {})          # values <= 1 are sigmas
+    assert set(sig.tolist()) <= {0.25, 0.5} and torch.equal(t, sig * 1000.0)
+    sig, t = _sampler("[750]", "fixed-list").sample(3, None, {})               # JSON list, single entry
+    assert torch.equal(t, torch.full((3,), 750.0)) and torch.equal(sig, torch.full((3,), 0.75))
+
+
+def test_other_flow_schedules_draw_like_the_reference():
+    import random
+    from types import SimpleNamespace
+
+    from simpletuner_b200.training.schedule import FlowSigmaSampler
+
+    base = dict(flow_custom_timesteps=None, flow_schedule_shift=1.0, flow_schedule_auto_shift=False, flow_sigmoid_scale=1.0,
+                flux_fast_schedule=False, flow_use_beta_schedule=False, flow_use_uniform_schedule=False)
+    torch.manual_seed(3)
+    sig, t = FlowSigmaSampler(SimpleNamespace(**{**base, "flow_use_uniform_schedule": True}), None, "cpu").sample(5, None)
+    torch.manual_seed(3)
+    assert torch.equal(sig, torch.rand((5,))) and torch.equal(t, sig * 1000.0)
+    random.seed(5)
+    sig, _ = FlowSigmaSampler(SimpleNamespace(**{**base, "flux_fast_schedule": True}), None, "cpu").sample(6, None)
+    random.seed(5)
+    assert sig.tolist() == random.choices([1.0] * 7 + [0.75, 0.5, 0.25], k=6)
+    torch.manual_seed(9)
+    sig, _ = FlowSigmaSampler(SimpleNamespace(**{**base, "flow_use_beta_schedule": True, "flow_beta_schedule_alpha": 2.0,
+                                                 "flow_beta_schedule_beta": 2.0}), None, "cpu").sample(4, None)
+    torch.manual_seed(9)
+    assert torch.equal(sig, torch.distributions.Beta(2.0, 2.0).sample((4,)))
+    torch.manual_seed(1)
+    sig, _ = FlowSigmaSampler(SimpleNamespace(**{**base, "mixflow_enabled": True}), None, "cpu").sample(4, None)
+    torch.manual_seed(1)
+    assert torch.equal(sig, 1.0 - torch.sqrt(torch.rand((4,))))
