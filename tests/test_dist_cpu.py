@@ -21,8 +21,15 @@ def _worker(rank, world_size, init_method, q):
         layout = D.resolve_batch_layout(n)
         w = D.gather_sample_weighted_scalar(loss, n)
         g = D.gather_variable_batch_tensor(vals, layout)
+        # round-robin custom timesteps over the REAL collective layout (reference tests/test_flow_custom_timesteps.py:66-82)
+        from types import SimpleNamespace
+        from simpletuner_b200.training.schedule import FlowSigmaSampler
+        cfg = SimpleNamespace(flow_custom_timesteps="100,200,300,400,500,600,700,800", flow_timesteps_mode="round-robin")
+        smp = FlowSigmaSampler(cfg, None, "cpu")
+        t_first = smp.sample(n, None, {"global_step": 0})[1].tolist()
+        t_next = smp.sample(n, None, {"global_step": 0})[1].tolist()
         q.put(("ok", rank, float(w), g.tolist(), layout.global_batch_size, layout.local_batch_offset,
-               D.device_seed(42, rank), list(D.shard_units(8, rank, world_size))))
+               D.device_seed(42, rank), list(D.shard_units(8, rank, world_size)), t_first, t_next))
     except BaseException:
         q.put(("error", rank, traceback.format_exc()))
         raise
@@ -44,7 +51,9 @@ def test_gloo_rank_varying_batch_collectives():
         assert all(not p.is_alive() for p in procs)
     res = sorted((q.get(timeout=5) for _ in procs), key=lambda t: t[1])
     assert [r[0] for r in res] == ["ok", "ok"], res
-    for _, rank, w, g, total, off, seed, units in res:
+    for _, rank, w, g, total, off, seed, units, t_first, t_next in res:
+        assert t_first == ([100.0] if rank == 0 else [200.0, 300.0, 400.0])
+        assert t_next == ([500.0] if rank == 0 else [600.0, 700.0, 800.0])
         assert w == 3.5
         assert g == [10.0, 20.0, 30.0, 40.0]
         assert total == 4 and off == (0 if rank == 0 else 1)
