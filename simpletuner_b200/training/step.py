@@ -70,9 +70,10 @@ class TrainStep:
 
     def check_finite(self):
         """Host sync: raise like trainer.py:7103-7111 if any step since the last check saw a non-finite loss."""
-        if self._nonfinite is not None and bool(self._nonfinite.item()):
-            raise RuntimeError("Non-finite loss encountered during training.")
+        bad = self._nonfinite is not None and bool(self._nonfinite.item())
         self._nonfinite = None
+        if bad:
+            raise RuntimeError("Non-finite loss encountered during training.")
 
 
 class _null:
