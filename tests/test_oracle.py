@@ -57,3 +57,38 @@ def test_bf16_emulation_tracks_fp32():
     bb = {k: (v.bfloat16() if v.dtype == torch.float32 and k != "sigmas" else v) for k, v in b.items()}
     loss16, _ = O.flux_train_step_loss(Pb, CFG, bb)
     assert abs(loss16.item() - loss32.item()) / loss32.item() < 3e-2
+
+
+def test_oracle_attention_pieces_against_torch_modules():
+    """Independent cross-checks of the restated layer math with torch's own modules / functionals."""
+    import torch.nn.functional as F
+    from oracle import pixart_oracle as PO
+    from oracle import vae_oracle as VO
+
+    g = torch.Generator().manual_seed(0)
+    q, k, v = (torch.randn(2, 3, 17, 16, generator=g) for _ in range(3))
+    assert torch.allclose(O.sdpa(q, k, v), F.scaled_dot_product_attention(q, k, v), atol=1e-5)
+    x = torch.randn(2, 9, 24, generator=g)
+    assert torch.allclose(O.layer_norm_noaffine(x), torch.nn.LayerNorm(24, elementwise_affine=False, eps=1e-6)(x), atol=1e-6)
+    w = 1.0 + 0.1 * torch.randn(24, generator=g)
+    assert torch.allclose(O.rms_norm(x, w, 1e-6), F.rms_norm(x, (24,), w, 1e-6), atol=1e-6)
+    # PixArt cross attention with an additive key bias == SDPA with the same float mask
+    cfg = PO.PixArtConfig(num_attention_heads=3, attention_head_dim=8, num_layers=1, cross_attention_dim=24, caption_channels=12)
+    P = PO.init_pixart_params(cfg, std=0.2)
+    hs, ctx = torch.randn(2, 7, 24, generator=g), torch.randn(2, 5, 24, generator=g)
+    mask = torch.tensor([[1, 1, 1, 0, 0], [1, 1, 1, 1, 1.0]])
+    bias = ((1 - mask) * -10000.0).unsqueeze(1)
+    got = PO.attention(P, cfg, "transformer_blocks.0.attn2", hs, ctx, bias, None, 1.0)
+    p = "transformer_blocks.0.attn2"
+    heads = lambda t: t.view(2, -1, 3, 8).transpose(1, 2)
+    qh = heads(F.linear(hs, P[p + ".to_q.weight"], P[p + ".to_q.bias"]))
+    kh = heads(F.linear(ctx, P[p + ".to_k.weight"], P[p + ".to_k.bias"]))
+    vh = heads(F.linear(ctx, P[p + ".to_v.weight"], P[p + ".to_v.bias"]))
+    ref = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=bias[:, None])
+    ref = F.linear(ref.transpose(1, 2).reshape(2, 7, 24), P[p + ".to_out.0.weight"], P[p + ".to_out.0.bias"])
+    assert torch.allclose(got, ref, atol=1e-5)
+    # VAE mid-block attention (single head over H*W tokens) == nn.MultiheadAttention-free SDPA formulation
+    vc = VO.VaeConfig(block_out_channels=(32, 32), layers_per_block=1, latent_channels=4)
+    VP = VO.init_vae_params(vc, seed=1)
+    m = VO.vae_encode_moments(VP, vc, torch.randn(1, 3, 16, 16, generator=g))
+    assert m.shape == (1, 8, 8, 8) and torch.isfinite(m).all()
