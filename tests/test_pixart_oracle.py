@@ -88,3 +88,15 @@ def test_eps_step_pieces():
     assert torch.allclose(O.eps_loss(e, e), torch.tensor(0.0))
     w = torch.tensor([2.0, 0.0])
     assert torch.allclose(O.eps_loss(x, e, w), ((x[0] - e[0]) ** 2).mean())
+
+
+def test_sincos_table_matches_the_mae_implementation_shipped_with_transformers():
+    """diffusers' get_2d_sincos_pos_embed descends from MAE's; with base_size == grid size and interpolation_scale 1 the
+    two coincide.  `transformers` (installed here) ships MAE's version: an implementation we did not write."""
+    import numpy as np
+    import pytest
+    mae = pytest.importorskip("transformers.models.vit_mae.modeling_vit_mae")
+    ref = mae.get_2d_sincos_pos_embed(32, 6, add_cls_token=False)
+    ref = ref.numpy() if hasattr(ref, "numpy") else np.asarray(ref)
+    got = O.sincos_pos_embed_2d(32, 6, 6, base_size=6, interpolation_scale=1.0).numpy()
+    assert got.shape == ref.shape == (36, 32) and np.allclose(got, ref, atol=1e-6)
