@@ -1,0 +1,77 @@
+"""Exponential moving average of the trainable parameters — host-side mirror of reference
+simpletuner/helpers/training/ema.py (class EMAModel): `get_decay` (:321-349, fixed decay after `warmup_steps`, the
+`(1 + step) / (10 + step)` ramp, or the `1 - (1 + step / inv_gamma) ** -power` warm-up, clamped to [min_decay, decay]),
+`should_update_ema` (:29-38) and the foreach update `shadow -= (1 - decay) * (shadow - param)` (:352-420).
+SURVEY.md §8f rank 1 lists it next to the optimizer; it runs on 26 M LoRA parameters after the optimizer step (outside
+the benchmarked step unless enabled), as two torch foreach kernels — there is no activation-sized work here.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+
+
+def should_update_ema(ema_update_interval: Optional[int], step: int) -> bool:
+    return True if ema_update_interval is None else step % ema_update_interval == 0
+
+
+class EMAModel:
+    def __init__(self, parameters: Iterable[torch.nn.Parameter], decay: float = 0.9999, min_decay: float = 0.0,
+                 update_after_step: int = 0, warmup_steps: int = 0, use_ema_warmup: bool = False, inv_gamma: float = 1.0,
+                 power: float = 2 / 3, ema_update_interval: Optional[int] = None):
+        params = list(parameters)
+        self.shadow_params: List[torch.Tensor] = [p.detach().clone() for p in params]
+        self.decay, self.min_decay = decay, min_decay
+        self.update_after_step = update_after_step
+        self.warmup_steps = max(0, int(warmup_steps))
+        self.use_ema_warmup, self.inv_gamma, self.power = use_ema_warmup, inv_gamma, power
+        self.ema_update_interval = ema_update_interval
+        self.optimization_step = 0
+        self.cur_decay_value: Optional[float] = None
+
+    def get_decay(self, optimization_step: Optional[int] = None) -> float:
+        if optimization_step is None:
+            optimization_step = self.optimization_step
+        step = max(0, optimization_step - self.update_after_step - 1)
+        if self.warmup_steps > 0:   # copy weights through the warm-up, then the configured fixed decay
+            return 0.0 if optimization_step < self.warmup_steps else self.decay
+        if step <= 0:
+            return 0.0
+        if self.use_ema_warmup:
+            cur = 1 - (1 + step / self.inv_gamma) ** -self.power
+        else:
+            cur = (1 + step) / (10 + step)
+        return max(min(cur, self.decay), self.min_decay)
+
+    @torch.no_grad()
+    def step(self, parameters: Iterable[torch.nn.Parameter], global_step: Optional[int] = None):
+        if not should_update_ema(self.ema_update_interval, global_step):
+            return
+        params = list(parameters)
+        if len(params) != len(self.shadow_params):
+            raise RuntimeError(f"EMA tracks {len(self.shadow_params)} parameters but {len(params)} were given.")
+        if global_step is not None:      # periodic updates: the counter cannot be trusted (ema.py:381-385)
+            self.optimization_step = global_step
+        else:
+            self.optimization_step += 1
+        decay = self.get_decay(self.optimization_step)
+        self.cur_decay_value = decay
+        train = [(s, p) for s, p in zip(self.shadow_params, params) if p.requires_grad]
+        frozen = [(s, p) for s, p in zip(self.shadow_params, params) if not p.requires_grad]
+        if frozen:
+            torch._foreach_copy_([s for s, _ in frozen], [p for _, p in frozen], non_blocking=True)
+        if train:
+            shadows, ps = [s for s, _ in train], [p.detach() for _, p in train]
+            torch._foreach_sub_(shadows, torch._foreach_sub(shadows, ps), alpha=1 - decay)
+
+    @torch.no_grad()
+    def copy_to(self, parameters: Iterable[torch.nn.Parameter]) -> None:
+        params = list(parameters)
+        torch._foreach_copy_([p.data for p in params], [s.to(p.device) for s, p in zip(self.shadow_params, params)])
+
+    def state_dict(self):
+        return {"decay": self.decay, "min_decay": self.min_decay, "optimization_step": self.optimization_step,
+                "update_after_step": self.update_after_step, "warmup_steps": self.warmup_steps,
+                "use_ema_warmup": self.use_ema_warmup, "inv_gamma": self.inv_gamma, "power": self.power,
+                "shadow_params": self.shadow_params}
