@@ -153,7 +153,8 @@ class StbError(RuntimeError):
 
 
 def lib() -> C.CDLL:
-    """Load libstb200.so (building it first when sources are newer and nvcc is present)."""
+    """Load the prebuilt libstb200.so (never builds: `build()` / `__graft_entry__.build()` does that) and bind every
+    symbol include/stb200.h declares; raises StbError when the library is missing — there is no fallback."""
     global _lib
     if _lib is not None:
         return _lib

@@ -526,5 +526,6 @@ class FlowLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (dpred,) = ctx.saved_tensors
-        # g is the scalar upstream gradient (1.0 for loss.backward()); keep it on-device
-        return (dpred * g.to(dpred.dtype)), None, None, None, None, None
+        # g is the scalar upstream gradient (1.0 for loss.backward(), 1/accum under gradient accumulation); it stays on
+        # the device and multiplies in fp32 — rounding g itself to bf16 (1/3 -> 0.33398) would bias every gradient
+        return (dpred.float() * g.float()).to(dpred.dtype), None, None, None, None, None

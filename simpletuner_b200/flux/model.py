@@ -77,10 +77,60 @@ class Flux:
                                             target_modules=FLUX_LORA_TARGETS[c.flux_lora_target])
 
     # ------------------------------------------------------------------------------------------
+    @classmethod
+    def validate_config(cls, c) -> None:
+        """Load-time counterpart of the per-batch guards: options of the reference this path does not implement raise
+        NotImplementedError so that the shim (shim/foundation.py) keeps the reference module for such a run."""
+        g = lambda k, d=None: getattr(c, k, d)
+        if g("controlnet", False):
+            raise NotImplementedError("controlnet training is not supported by the libstb200 path")
+        if str(g("model_type", "lora")) not in ("lora",):
+            raise NotImplementedError(f"model_type={g('model_type')!r}: only LoRA training runs on the libstb200 path")
+        if str(g("lora_type", "standard") or "standard").lower() not in ("standard",):
+            raise NotImplementedError(f"lora_type={g('lora_type')!r} (LyCORIS) is not supported by the libstb200 path")
+        if g("use_dora", False):
+            raise NotImplementedError("DoRA is not supported by the libstb200 path")
+        if g("flux_attention_masked_training", False):
+            raise NotImplementedError("flux_attention_masked_training is not supported by the libstb200 Flux path (quirk Q2)")
+        if g("tread_config", None):
+            raise NotImplementedError("TREAD routing is not supported by the libstb200 path")
+        if g("flow_cubic_schedule", None) or g("flow_cubic_schedule_weights", None):
+            raise NotImplementedError("the cubic-spline flow schedule is not part of the libstb200 step")
+        for flag in ("twinflow_enabled", "crepa_enabled", "layersync_enabled", "scheduled_sampling_max_step_offset",
+                     "diff2flow_enabled"):
+            if g(flag, None):
+                raise NotImplementedError(f"{flag} is not supported by the libstb200 path")
+        if g("distillation_method", None) not in (None, "", "None"):
+            raise NotImplementedError("distillation is not supported by the libstb200 path")
+
+    def adopt_noise_schedule(self, sched) -> None:
+        """Use the reference family's scheduler object (its `.config` feeds the flow shift / timestep count)."""
+        self.noise_schedule = sched
+
+    def _check_supported(self, batch: Dict[str, Any]) -> None:
+        """Options of the reference wrapper this path does not implement must RAISE, never be ignored, so that a shim can
+        route such a config to the reference class: masked training (flux/model.py:813 passes
+        `encoder_attention_mask`), Kontext conditioning latents (flux/model.py:757-786)."""
+        if getattr(self.config, "flux_attention_masked_training", False):
+            raise NotImplementedError("flux_attention_masked_training is not supported by the libstb200 Flux path (quirk Q2)")
+        for k in ("conditioning_packed_latents", "conditioning_ids", "conditioning_latents"):
+            if batch.get(k) is not None:
+                raise NotImplementedError(f"Kontext / conditioning input `{k}` is not supported by the libstb200 Flux path")
+
+    def _check_loss_supported(self, prepared_batch: Dict[str, Any], apply_conditioning_mask: bool) -> None:
+        """common.py:6400-6424: with `apply_conditioning_mask` the reference multiplies the loss by the conditioning mask
+        when the dataset's `conditioning_type` is 'mask' or 'segmentation'.  Not implemented here -> raise."""
+        if not apply_conditioning_mask:
+            return
+        lm = prepared_batch.get("loss_mask_type") or prepared_batch.get("conditioning_type")   # legacy fallback, :6403-6408
+        if lm in ("mask", "segmentation"):
+            raise NotImplementedError("masked / segmentation-weighted loss is not supported by the libstb200 loss kernels")
+
     def prepare_batch(self, batch: Dict[str, Any], state: Dict[str, Any]) -> Dict[str, Any]:
         if not batch:
             return batch
         c = self.config
+        self._check_supported(batch)
         dev = self.accelerator.device
         kw = {"device": dev, "dtype": c.weight_dtype}
         if batch.get("prompt_embeds") is not None:
@@ -105,8 +155,19 @@ class Flux:
         sigmas, timesteps = self._sigma_sampler.sample(bsz, noise, state)
         batch["timesteps"] = timesteps
         batch["sigmas"] = sigmas.view(-1, 1, 1, 1)  # expand_sigmas, common.py:6825-6828
+        # MixFlow (common.py:4962-4991): the model sees `sigmas`, the interpolation uses the slowed-down
+        # sigma + U * gamma * (1 - sigma); the extra rand_like draw happens here, after the sigma draw, as in the reference
+        interp = sigmas
+        if getattr(c, "mixflow_enabled", False) is True:
+            gamma = float(getattr(c, "mixflow_gamma", 0.8))
+            if not 0.0 <= gamma <= 1.0:
+                raise ValueError("mixflow_gamma must be between 0.0 and 1.0.")
+            slow = torch.rand_like(sigmas) if gamma > 0.0 else torch.zeros_like(sigmas)
+            interp = sigmas if gamma == 0.0 else sigmas + slow * gamma * (1.0 - sigmas)
+            batch["mixflow_slowdown_factors"] = slow
+            batch["mixflow_interpolation_sigmas"] = interp
         # fused: noisy = (1 - s) x + s eps  AND  2x2 patchify  (common.py:4975-4992, flux/__init__.py:25-30)
-        noisy, packed = ops.flow_prep_pack(batch["latents"], batch["input_noise"], sigmas.float().contiguous(),
+        noisy, packed = ops.flow_prep_pack(batch["latents"], batch["input_noise"], interp.float().contiguous(),
                                            want_unpacked=True)
         batch["noisy_latents"] = noisy
         batch["_packed_noisy_latents"] = packed
@@ -127,9 +188,9 @@ class Flux:
         raise ValueError(f"Unsupported Flux guidance mode: {c.flux_guidance_mode!r}.")
 
     def model_predict(self, prepared_batch: Dict[str, Any]) -> Dict[str, Any]:
-        """flux/model.py:707-864.  Returns `model_prediction` in the PACKED token layout plus the
-        metadata needed to unpack; `unpacked_prediction()` materialises the reference's [B,C,H,W]
-        view on demand (the loss kernel consumes the packed layout directly)."""
+        """flux/model.py:707-864.  Returns the reference's dict (flux/model.py:855-864): `model_prediction` is the
+        un-packed [B, C, H, W] tensor (seam B9).  The packed token layout the loss kernel consumes rides along under the
+        private key `_packed_prediction`; `loss()` uses it when the caller has not replaced `model_prediction`."""
         pb = prepared_batch
         lat = pb["latents"]
         B, Cc, Hh, Ww = lat.shape
@@ -147,20 +208,50 @@ class Flux:
             pooled_projections=pb["added_cond_kwargs"]["text_embeds"], encoder_hidden_states=pb["encoder_hidden_states"],
             txt_ids=txt_ids, img_ids=img_ids, joint_attention_kwargs=None, return_dict=False,
         )[0]
-        return {"model_prediction": out, "model_prediction_layout": "packed", "latent_shape": (B, Cc, Hh, Ww),
+        return self._prediction_dict(out, (B, Cc, Hh, Ww))
+
+    PACKED_LAYOUT = "packed"
+
+    def _prediction_dict(self, out_packed: torch.Tensor, latent_shape) -> Dict[str, Any]:
+        unpacked = self._unpack(out_packed, latent_shape)
+        return {"model_prediction": unpacked, "_packed_prediction": out_packed, "_unpacked_ref": unpacked,
+                "model_prediction_layout": self.PACKED_LAYOUT, "latent_shape": tuple(latent_shape),
                 "crepa_hidden_states": None, "hidden_states_buffer": None}
 
     @staticmethod
-    def unpacked_prediction(model_output: Dict[str, Any]) -> torch.Tensor:
+    def _unpack(out_packed: torch.Tensor, latent_shape) -> torch.Tensor:
         from .functional import unpack_latents
-        B, Cc, Hh, Ww = model_output["latent_shape"]
-        return unpack_latents(model_output["model_prediction"], Hh * 8, Ww * 8, 16)
+        B, Cc, Hh, Ww = latent_shape
+        return unpack_latents(out_packed, Hh * 8, Ww * 8, 16)   # flux/model.py:856-861
+
+    @staticmethod
+    def _pack(pred: torch.Tensor) -> torch.Tensor:
+        from .functional import pack_latents
+        B, Cc, Hh, Ww = pred.shape
+        return pack_latents(pred, B, Cc, Hh, Ww)
+
+    @staticmethod
+    def unpacked_prediction(model_output: Dict[str, Any]) -> torch.Tensor:
+        return model_output["model_prediction"]
+
+    def _packed_for_loss(self, model_output: Dict[str, Any]) -> torch.Tensor:
+        """The packed prediction the loss kernels read.  A caller that REPLACED `model_prediction` (e.g. the x-prediction
+        fix-up of trainer.py:6099-6105) is honoured: the private packed tensor is only used while it still describes the
+        same object; a bare `{"model_prediction": packed_tensor}` (3-D) is accepted as already packed."""
+        pred = model_output["model_prediction"]
+        packed = model_output.get("_packed_prediction")
+        if packed is not None and model_output.get("_unpacked_ref") is pred:
+            return packed
+        if pred.dim() == 3:
+            return pred
+        return self._pack(pred).contiguous()
 
     # ------------------------------------------------------------------------------------------
     def loss(self, prepared_batch: Dict[str, Any], model_output: Dict[str, Any], apply_conditioning_mask: bool = True):
         """common.py:6217-6430, flow-matching / l2 branch: target = noise - latents (common.py:4610-4611),
         mse in fp32, mean over (C,H,W) then over the batch."""
-        return FlowLossFn.apply(model_output["model_prediction"], prepared_batch["latents"], prepared_batch["noise"],
+        self._check_loss_supported(prepared_batch, apply_conditioning_mask)
+        return FlowLossFn.apply(self._packed_for_loss(model_output), prepared_batch["latents"], prepared_batch["noise"],
                                 self.LOSS_LAYOUT, *self._loss_kind(prepared_batch))
 
     LOSS_LAYOUT = 0   # packed prediction feature order: 0 = (c, dy, dx) Flux, 1 = (dy, dx, c) SD3 / PixArt

@@ -256,7 +256,64 @@ def rope_tables(ids: torch.Tensor, axes_dim, theta: float = 10000.0) -> Tuple[to
     return torch.cat(cos_out, dim=-1).contiguous(), torch.cat(sin_out, dim=-1).contiguous()
 
 
-class FluxTransformer2DModel(nn.Module):
+class B200FusedAttnProcessor:
+    """Marker processor: the attention of this module runs inside the libstb200 block schedule (blocks.py)."""
+
+    def __call__(self, *a, **k):
+        raise RuntimeError("B200FusedAttnProcessor is a marker; the attention runs inside the fused block schedule")
+
+
+# processors whose arithmetic the fused block schedule reproduces (plain un-masked SDPA attention with the model's own
+# projections / QK-norm / RoPE): reference flux/transformer.py:116-224, flux/attention.py:309-579, diffusers
+# JointAttnProcessor2_0 / AttnProcessor2_0
+_EQUIVALENT_PROCESSORS = {
+    "B200FusedAttnProcessor", "FluxAttnProcessor2_0", "FluxAttnProcessor", "FluxFusedSDPAProcessor",
+    "FluxFusedFlashAttnProcessor3", "FluxSingleFusedFlashAttnProcessor3", "FusedFluxAttnProcessor2_0",
+    "JointAttnProcessor2_0", "FusedJointAttnProcessor2_0", "AttnProcessor2_0", "AttnProcessor", "FusedAttnProcessor2_0",
+}
+
+
+class AttnProcessorAPI:
+    """`attn_processors` / `set_attn_processor` of the reference denoisers (seam B2: flux/transformer.py:880-912, sd3
+    :483, pixart :404).  The B200 modules have no pluggable processor: setting one whose arithmetic the fused schedule
+    reproduces is recorded and accepted; anything else (IP-adapter, masked, custom) raises NotImplementedError so that the
+    caller keeps the reference module for that feature."""
+
+    def _attention_modules(self):
+        return {n: m for n, m in self.named_modules() if n.endswith(("attn", "attn1", "attn2")) and hasattr(m, "to_q")}
+
+    @property
+    def attn_processors(self):
+        store = self.__dict__.setdefault("_attn_processor_store", {})
+        return {f"{n}.processor": store.get(n, B200FusedAttnProcessor()) for n in self._attention_modules()}
+
+    def set_attn_processor(self, processor):
+        mods = self._attention_modules()
+        if isinstance(processor, dict):
+            if len(processor) != len(mods):
+                raise ValueError(f"A dict of processors was passed, but the number of processors {len(processor)} does not "
+                                 f"match the number of attention layers: {len(mods)}. Please make sure to pass {len(mods)} "
+                                 "processor classes.")
+            items = {k[: -len(".processor")] if k.endswith(".processor") else k: v for k, v in processor.items()}
+        else:
+            items = {n: processor for n in mods}
+        for n, proc in items.items():
+            if type(proc).__name__ not in _EQUIVALENT_PROCESSORS:
+                raise NotImplementedError(f"attention processor {type(proc).__name__} is not reproduced by the libstb200 "
+                                          "block schedule; use the reference module for it")
+        self.__dict__.setdefault("_attn_processor_store", {}).update(items)
+
+    def fuse_qkv_projections(self):
+        """diffusers `fuse_qkv_projections` (reference common.py:3547 calls the family hook after load): the fused
+        [3D, D] projection already IS the internal layout (blocks.AttnPlan.w_qkv); parameters keep their un-fused names so
+        that LoRA files stay PEFT / ComfyUI compatible.  Nothing to do."""
+        return None
+
+    def unfuse_qkv_projections(self):
+        return None
+
+
+class FluxTransformer2DModel(AttnProcessorAPI, nn.Module):
     _no_split_modules = ["FluxTransformerBlock", "FluxSingleTransformerBlock"]
     _supports_gradient_checkpointing = True
 
@@ -284,7 +341,7 @@ class FluxTransformer2DModel(nn.Module):
         self.norm_out = _AdaNorm(D, 2, dtype)
         self.proj_out = Linear(D, patch_size * patch_size * self.out_channels, dtype=dtype)
         self.gradient_checkpointing = False
-        self._rope_cache: Dict[Any, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._rope_cache: Dict[Any, Tuple[torch.Tensor, ...]] = {}
         self._tail_plan = None
         self._lora_scaling = 1.0
         self.peft_config: Dict[str, Any] = {}
@@ -382,12 +439,16 @@ class FluxTransformer2DModel(nn.Module):
 
     # ---- forward ------------------------------------------------------------------------------
     def _rope(self, txt_ids, img_ids, device):
-        key = (tuple(txt_ids.shape), tuple(img_ids.shape), float(img_ids.sum()), float(txt_ids.sum()), str(device))
+        # keyed on the id CONTENT: a sum (or the shape) does not identify a bucket — the (128, 64) and (64, 128) latent
+        # grids have the same shape and the same id sum but different (row, col) tables
+        ti, ii = txt_ids.detach().to("cpu", torch.float32).contiguous(), img_ids.detach().to("cpu", torch.float32).contiguous()
+        key = (tuple(ti.shape), tuple(ii.shape), hash(ti.numpy().tobytes()), hash(ii.numpy().tobytes()), str(device))
         hit = self._rope_cache.get(key)
+        if hit is not None and not (torch.equal(hit[2], ti) and torch.equal(hit[3], ii)):   # hash collision
+            hit = None
         if hit is None:
-            ids = torch.cat((txt_ids.detach().cpu().float(), img_ids.detach().cpu().float()), dim=0)
-            cos, sin = rope_tables(ids, self.config.axes_dims_rope)
-            hit = (cos.to(device), sin.to(device))
+            cos, sin = rope_tables(torch.cat((ti, ii), dim=0), self.config.axes_dims_rope)
+            hit = (cos.to(device), sin.to(device), ti, ii)
             if len(self._rope_cache) > 64:
                 self._rope_cache.clear()
             self._rope_cache[key] = hit
@@ -440,7 +501,7 @@ class FluxTransformer2DModel(nn.Module):
             txt_ids = txt_ids[0]
         if img_ids.ndim == 3:
             img_ids = img_ids[0]
-        cos, sin = self._rope(txt_ids, img_ids, dev)
+        cos, sin = self._rope(txt_ids, img_ids, dev)[:2]
         scaling = self._lora_scaling
         for i, blk in enumerate(self.transformer_blocks):
             h = self._run_block(i, blk, h, silu_temb, cos, sin, S_txt, scaling)

@@ -50,7 +50,7 @@ class _TargetLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (dpred,) = ctx.saved_tensors
-        return dpred * g.to(dpred.dtype), None, None, None, None, None
+        return (dpred.float() * g.float()).to(dpred.dtype), None, None, None, None, None   # fp32 scale, see FlowLossFn
 
 
 class PixartSigma(Flux):
@@ -160,17 +160,24 @@ class PixartSigma(Flux):
             encoder_attention_mask=mask, added_cond_kwargs=self._build_added_cond_kwargs(pb), return_dict=False,
             _packed_latents=pb.get("_packed_noisy_latents"), _packed_output="eps_half",
         )[0]
-        return {"model_prediction": out, "model_prediction_layout": "packed_dydxc", "latent_shape": (B, Cc, Hh, Ww),
-                "crepa_hidden_states": None, "hidden_states_buffer": None}
+        return self._prediction_dict(out, (B, Cc, Hh, Ww))
+
+    PACKED_LAYOUT = "packed_dydxc"
 
     @staticmethod
-    def unpacked_prediction(model_output: Dict[str, Any]) -> torch.Tensor:
-        B, Cc, Hh, Ww = model_output["latent_shape"]
-        o = model_output["model_prediction"].reshape(B, Hh // 2, Ww // 2, 2, 2, Cc)
+    def _unpack(out_packed: torch.Tensor, latent_shape) -> torch.Tensor:
+        B, Cc, Hh, Ww = latent_shape
+        o = out_packed.reshape(B, Hh // 2, Ww // 2, 2, 2, Cc)
         return torch.einsum("nhwpqc->nchpwq", o).reshape(B, Cc, Hh, Ww)
+
+    @staticmethod
+    def _pack(pred: torch.Tensor) -> torch.Tensor:
+        B, Cc, Hh, Ww = pred.shape
+        return pred.reshape(B, Cc, Hh // 2, 2, Ww // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, (Hh // 2) * (Ww // 2), 4 * Cc)
 
     def loss(self, prepared_batch, model_output, apply_conditioning_mask: bool = True):
         c = self.config
+        self._check_loss_supported(prepared_batch, apply_conditioning_mask)
         lt, hc = self._loss_kind(prepared_batch)
         # common.py:6376-6398: `snr_weight` multiplies the plain-l2 branch only; huber / smooth_l1 and the min-SNR
         # branch do not apply it
@@ -185,4 +192,4 @@ class PixartSigma(Flux):
                                   prepared_batch["timesteps"]).contiguous()
         else:
             target = prepared_batch["noise"]
-        return _TargetLossFn.apply(model_output["model_prediction"], target, weights, snr_w, lt, hc)
+        return _TargetLossFn.apply(self._packed_for_loss(model_output), target, weights, snr_w, lt, hc)

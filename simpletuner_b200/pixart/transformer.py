@@ -33,7 +33,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..flux.blocks import EPS, MlpPlan, TailFn, _linear_lora_dgrad, _linear_lora_fwd, _lora_grads, _t, pack_lora
-from ..flux.transformer import Linear, _FeedForward, _lora_list, _sinusoid, _TimestepEmbedding
+from ..flux.transformer import AttnProcessorAPI, Linear, _FeedForward, _lora_list, _sinusoid, _TimestepEmbedding
 
 PIXART_LORA_TARGETS = ["to_k", "to_q", "to_v", "to_out.0"]  # PixartSigma.DEFAULT_LORA_TARGET, reference pixart/model.py:59
 MASK_BIAS = -10000.0
@@ -299,7 +299,7 @@ def sincos_pos_embed_2d(dim: int, grid_h: int, grid_w: int, base_size: int, inte
     return torch.cat(parts, dim=1).float().to(device)
 
 
-class PixArtTransformer2DModel(nn.Module):
+class PixArtTransformer2DModel(AttnProcessorAPI, nn.Module):
     _no_split_modules = ["BasicTransformerBlock", "PatchEmbed"]
 
     def __init__(self, num_attention_heads: int = 16, attention_head_dim: int = 72, in_channels: int = 4,

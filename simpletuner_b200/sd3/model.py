@@ -48,13 +48,19 @@ class SD3(Flux):
             pooled_projections=pb["added_cond_kwargs"]["text_embeds"], return_dict=False,
             _packed_latents=pb.get("_packed_noisy_latents"), _packed_output=True,
         )[0]
-        return {"model_prediction": out, "model_prediction_layout": "packed_dydxc", "latent_shape": (B, Cc, Hh, Ww),
-                "crepa_hidden_states": None, "hidden_states_buffer": None}
+        return self._prediction_dict(out, (B, Cc, Hh, Ww))
+
+    PACKED_LAYOUT = "packed_dydxc"
 
     @staticmethod
-    def unpacked_prediction(model_output: Dict[str, Any]) -> torch.Tensor:
-        B, Cc, Hh, Ww = model_output["latent_shape"]
-        o = model_output["model_prediction"].reshape(B, Hh // 2, Ww // 2, 2, 2, Cc)
+    def _unpack(out_packed: torch.Tensor, latent_shape) -> torch.Tensor:
+        B, Cc, Hh, Ww = latent_shape
+        o = out_packed.reshape(B, Hh // 2, Ww // 2, 2, 2, Cc)
         return torch.einsum("nhwpqc->nchpwq", o).reshape(B, Cc, Hh, Ww)
+
+    @staticmethod
+    def _pack(pred: torch.Tensor) -> torch.Tensor:
+        B, Cc, Hh, Ww = pred.shape
+        return pred.reshape(B, Cc, Hh // 2, 2, Ww // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, (Hh // 2) * (Ww // 2), 4 * Cc)
 
     LOSS_LAYOUT = 1

@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..flux.blocks import AttnPlan, DoubleBlockFn, MlpPlan, TailFn, _t
-from ..flux.transformer import Linear, RMSNormWeight, _AdaNorm, _FeedForward, _TimestepEmbedding, _attn_plan, _lora_list, _sinusoid
+from ..flux.transformer import AttnProcessorAPI, Linear, RMSNormWeight, _AdaNorm, _FeedForward, _TimestepEmbedding, _attn_plan, _lora_list, _sinusoid
 
 SD3_LORA_TARGETS = ["to_k", "to_q", "to_v", "to_out.0"]  # SD3.DEFAULT_LORA_TARGET, reference sd3/model.py:122
 
@@ -139,7 +139,7 @@ class _TimeTextEmbed(nn.Module):
         self.text_embedder = _TimestepEmbedding(pooled_dim, dim, dtype)
 
 
-class SD3Transformer2DModel(nn.Module):
+class SD3Transformer2DModel(AttnProcessorAPI, nn.Module):
     _no_split_modules = ["JointTransformerBlock"]
 
     def __init__(self, sample_size: int = 128, patch_size: int = 2, in_channels: int = 16, num_layers: int = 18,

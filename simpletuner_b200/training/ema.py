@@ -46,8 +46,8 @@ class EMAModel:
 
     @torch.no_grad()
     def step(self, parameters: Iterable[torch.nn.Parameter], global_step: Optional[int] = None):
-        if not should_update_ema(self.ema_update_interval, global_step):
-            return
+        if global_step is not None and not should_update_ema(self.ema_update_interval, global_step):
+            return   # (global_step None = "always update": the reference would raise TypeError on `None % int`)
         params = list(parameters)
         if len(params) != len(self.shadow_params):
             raise RuntimeError(f"EMA tracks {len(self.shadow_params)} parameters but {len(params)} were given.")
@@ -75,3 +75,27 @@ class EMAModel:
                 "update_after_step": self.update_after_step, "warmup_steps": self.warmup_steps,
                 "use_ema_warmup": self.use_ema_warmup, "inv_gamma": self.inv_gamma, "power": self.power,
                 "shadow_params": self.shadow_params}
+
+    def load_state_dict(self, state_dict: dict) -> None:
+        """ema.py `load_state_dict`: restores the schedule fields, the step counter and the shadow weights (resume)."""
+        for k in ("decay", "min_decay", "optimization_step", "update_after_step", "warmup_steps", "use_ema_warmup", "inv_gamma",
+                  "power"):
+            if k in state_dict:
+                setattr(self, k, state_dict[k])
+        shadow = state_dict.get("shadow_params")
+        if shadow is not None:
+            shadow = list(shadow)
+            if len(shadow) != len(self.shadow_params):
+                raise ValueError(f"EMA state has {len(shadow)} shadow tensors, this model tracks {len(self.shadow_params)}.")
+            with torch.no_grad():
+                for dst, src in zip(self.shadow_params, shadow):
+                    if dst.shape != src.shape:
+                        raise ValueError(f"EMA shadow shape mismatch: {tuple(src.shape)} vs {tuple(dst.shape)}")
+                    dst.copy_(src.to(device=dst.device, dtype=dst.dtype))
+
+    def to(self, device=None, dtype=None, non_blocking: bool = False) -> "EMAModel":
+        """ema.py `to`: move (and optionally cast the floating-point) shadow weights."""
+        self.shadow_params = [
+            s.to(device=device, dtype=dtype, non_blocking=non_blocking) if s.is_floating_point()
+            else s.to(device=device, non_blocking=non_blocking) for s in self.shadow_params]
+        return self

@@ -54,8 +54,8 @@ class TrainStep:
         ddp = self.model.model if hasattr(self.model.model, "no_sync") else None
         ctx = ddp.no_sync() if (ddp is not None and not sync) else _null()
         with ctx:
-            out = self.model.model_predict(prepared)
-            loss, _ = self.model.loss_with_logs(prepared, out)
+            out = self.model_predict(prepared)
+            loss, _ = self.model.loss_with_logs(prepared, out, apply_conditioning_mask=True)
             (loss / self.accum if self.accum > 1 else loss).backward()
         ld = loss.detach()
         bad = ~torch.isfinite(ld)
@@ -67,6 +67,22 @@ class TrainStep:
             self.optimizer.zero_grad(set_to_none=True)
             self.state["global_step"] += 1
         return ld
+
+    def model_predict(self, prepared_batch):
+        """`Trainer.model_predict` (trainer.py:6051-6107) for the plain training path: family `model_predict`, then the
+        x-prediction fix-up (:6099-6105) — a scheduler with `prediction_type == "sample"` gets `prediction - noise`.  The
+        reference applies the subtraction to whatever `model_predict` returned; here it is applied to the
+        `model_prediction` entry of the dict (a new tensor, so the family's `loss()` re-packs it instead of using its
+        private packed copy)."""
+        out = self.model.model_predict(prepared_batch)
+        sched = getattr(self.model, "noise_schedule", None)
+        if sched is not None and getattr(getattr(sched, "config", None), "prediction_type", None) == "sample":
+            if isinstance(out, dict):
+                out = dict(out)
+                out["model_prediction"] = out["model_prediction"] - prepared_batch["noise"]
+            else:
+                out = out - prepared_batch["noise"]
+        return out
 
     def check_finite(self):
         """Host sync: raise like trainer.py:7103-7111 if any step since the last check saw a non-finite loss."""

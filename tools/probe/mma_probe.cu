@@ -83,20 +83,20 @@ __global__ void __launch_bounds__(128, 1) probe_mix(int mix, int iters, long lon
     for (int it = 0; it < iters; ++it) {
       const uint32_t w = it & 1;
       if (elect_one()) {
-        const bool wide = (mix == 4 || mix == 5 || mix == 6);
-        const uint32_t X = tm + (wide ? 0u : w * 64u), Y = tm + 128 + (wide ? 0u : w * 64u);
-        const int nscore = (mix == 5) ? 1 : 2;
+        const bool wide = (mix == 4 || mix == 5 || mix == 6 || mix == 7);
+        const uint32_t X = (mix == 8) ? tm : tm + (wide ? 0u : w * 64u), Y = (mix == 8) ? tm + 64 : tm + 128 + (wide ? 0u : w * 64u);
+        const int nscore = (mix == 5 || mix == 7) ? 1 : 2;
         for (int g = 0; g < nscore; ++g) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const uint32_t d = g ? Y : X;
-            if (mix == 2) mma_ts(d, tm + 384 + g * 64 + 8 * kk, sdesc_k(g ? b2_smem : b_smem, (kk / 4) * 8192 + (kk % 4) * 32), i64, kk > 0);
-            else if (mix == 6) mma_ts(d, tm + 384 + g * 64 + 8 * kk, sdesc_k(g ? b2_smem : b_smem, (kk / 4) * 16384 + (kk % 4) * 32), i128, kk > 0);
+            if (mix == 2 || mix == 8) mma_ts(d, tm + (mix == 8 ? 128 : 384) + g * 64 + 8 * kk, sdesc_k(g ? b2_smem : b_smem, (kk / 4) * 8192 + (kk % 4) * 32), i64, kk > 0);
+            else if (mix == 6 || mix == 7) mma_ts(d, tm + 384 + g * 64 + 8 * kk, sdesc_k(g ? b2_smem : b_smem, (kk / 4) * 16384 + (kk % 4) * 32), i128, kk > 0);
             else if (wide) mma_ss(d, sdesc_k(g ? a2_smem : a_smem, (kk / 4) * 16384 + (kk % 4) * 32), sdesc_k(g ? b2_smem : b_smem, (kk / 4) * 16384 + (kk % 4) * 32), i128, kk > 0);
             else mma_ss(d, sdesc_k(g ? a2_smem : a_smem, (kk / 4) * 16384 + (kk % 4) * 32), sdesc_k(g ? b2_smem : b_smem, (kk / 4) * 8192 + (kk % 4) * 32), i64, kk > 0);
           }
         }
-        const int nacc = (mix == 1 || mix == 4) ? 2 : 1;
+        const int nacc = (mix == 1 || mix == 4 || mix == 8) ? 2 : 1;
         const int ksteps = wide ? 8 : 4;
         for (int g = 0; g < nacc; ++g) {
 #pragma unroll 8
@@ -204,9 +204,9 @@ int main() {
   const int smem2 = 131072 + 1024 + 64;
   cudaFuncSetAttribute(probe_mix, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
   const char* names[] = {"", "dkdv 64-wide (SS scores)", "dq 64-wide (TS scores)", "dq 64-wide (SS scores)", "dkdv 128-wide (SS scores)",
-                         "fwd 128x128", "dq 128-wide (TS scores)"};
-  const double floors[] = {0, 1024, 768, 768, 2048, 1024, 1536};
-  for (int mix = 1; mix <= 6; ++mix) {
+                         "fwd 128x128", "dq 128-wide (TS scores)", "fwd 128x128 (TS scores)", "dkdv 64-wide (TS scores)"};
+  const double floors[] = {0, 1024, 768, 768, 2048, 1024, 1536, 1024, 1024};
+  for (int mix = 1; mix <= 8; ++mix) {
     for (int rep = 0; rep < 2; ++rep) {
       probe_mix<<<nsm, 128, smem2>>>(mix, 512, out);
       cudaError_t e = cudaDeviceSynchronize();
