@@ -6,11 +6,27 @@ import torch
 
 from oracle import flux_oracle as O
 
-# Tolerances (stated, per BASELINE north_star "noise-prediction loss within a stated bf16 tolerance"):
-#   compared against the fp32 oracle evaluated on the SAME bf16-rounded weights and inputs
-LOSS_RTOL = 2e-2      # |loss_cuda - loss_fp32| / loss_fp32
-PRED_COS = 0.999      # cosine(pred_cuda, pred_fp32) over all elements
-GRAD_COS = 0.98       # cosine per LoRA gradient tensor (bf16 backward through ~10 GEMMs per block)
+# Tolerances (stated, per BASELINE north_star "noise-prediction loss within a stated bf16 tolerance"; SURVEY.md 7):
+#   compared against the fp32 oracle evaluated on the SAME bf16-rounded weights and inputs.  Measured on B200 (r02, see
+#   DESIGN.md 4): toy width loss rel. err 6e-5 / pred cos 0.99999 / worst grad cos 0.9999; full width (D = 3072, S = 4608)
+#   in tests/test_fullwidth_parity_gpu.py.  The bounds leave ~10x head-room over what was measured, not 350x.
+LOSS_RTOL = 2e-3      # |loss_cuda - loss_fp32| / loss_fp32
+PRED_COS = 0.9995     # cosine(pred_cuda, pred_fp32) over all elements
+GRAD_COS = 0.999      # cosine per LoRA gradient tensor (bf16 backward through ~10 GEMMs per block)
+
+
+def record(tag: str, res: dict) -> dict:
+    """Append the measured deviations to gpurun_out/parity_report.jsonl (copied to profiles/ and quoted in DESIGN.md)."""
+    try:
+        import json
+        import pathlib
+        out = pathlib.Path(__file__).resolve().parent.parent / "gpurun_out"
+        if out.is_dir():
+            with open(out / "parity_report.jsonl", "a") as f:
+                f.write(json.dumps({"case": tag, **{k: v for k, v in res.items() if isinstance(v, (int, float, str, bool))}}) + "\n")
+    except Exception:
+        pass
+    return res
 
 
 def small_config(layers=2, single=2, heads=2, hd=128, joint=192, pooled=64):

@@ -336,6 +336,16 @@ CHECKS = {
     "skinny_ragged": lambda: check_skinny(B=3, S=333, R=16, N=200),
     "skinny_cuda_core_path": lambda: check_skinny(B=2, S=100, R=16, N=250),
 }
+# BASELINE-geometry kernel shapes: the deepest K of the Flux step (fc2 / single-block proj_out, K = 12288 and
+# the 2-segment 3072 + 12288 `cat([attn, mlp]) @ W_out`), and the attention backward at the full joint sequence
+CHECKS["gemm_k12288"] = lambda: check_gemm(4608, 3072, 12288, B=1, bias=True)
+CHECKS["gemm_seg2_3072_12288_gate_res"] = lambda: check_gemm(4608, 3072, 3072, B=1, segs=[12288], bias=True, epi=E.EPI_GATE_RES,
+                                                              nan_to_num=True)
+CHECKS["gemm_seg3_dgrad_12288_9216_48"] = lambda: check_gemm(4608, 3072, 12288, B=1, segs=[9216, 48])
+CHECKS["attn_bwd_s4608"] = lambda: check_attn_bwd(1, 2, 4608)
+CHECKS["attn_bwd_s4608_ragged_cross"] = lambda: check_attn_bwd(1, 2, 4096, 4608 - 77)
+CHECKS["attn_fwd_hd64_long"] = lambda: check_attn_fwd(2, 3, 1255, HD=64)
+CHECKS["attn_bwd_hd64_long"] = lambda: check_attn_bwd(2, 3, 1255, HD=64)
 CHECKS["skinny_r96"] = lambda: check_skinny(B=2, S=700, R=96, N=1536)
 CHECKS["skinny_r24"] = lambda: check_skinny(B=1, S=300, R=24, N=512)
 

@@ -91,6 +91,9 @@ def run_parity(cfg=None, B=2, Hh=16, Ww=24, S_txt=40, rank=16, seed=0, device="c
 
 
 def check(res):
+    import inspect
+    from tests.flux_parity import record
+    record("pixart:" + inspect.stack()[1].function, res)
     assert res["noisy_bit_exact"], res
     assert res["loss_rel_err"] <= LOSS_RTOL, res
     assert res["pred_cos"] >= PRED_COS, res
