@@ -197,74 +197,189 @@ def profile_kernels(step_fn, batch):
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
 class CpuBaseline:
-    """Depth-reduced Flux LoRA train step (full width 3072, full 4608-token sequence, B=1) through the fp32
-    CPU oracle; `step()` returns seconds for fwd + LoRA backward; `summary()` extrapolates linearly in depth."""
+    """Depth-reduced Flux LoRA train step through the fp32 CPU oracle: full width (D = 3072), full
+    4096 + 512-token sequence, B = 1.  One `step(kind)` = forward + LoRA backward of ONE block of that kind ("double" or
+    "single") inside the whole step pipeline (noisy latents, embedders, norm_out / proj_out, loss); the block kinds are
+    timed separately because a double block costs ~1.5x a single one, and a full-depth sample step is
+    19 * t_double + 38 * t_single (embedders / head / loss are < 0.1 % and are counted once per timed block, i.e. over-
+    counted)."""
 
-    def __init__(self, threads=None, blocks=(0, 1), seq=(S_IMG, S_TXT)):
+    def __init__(self, threads=None, seq=(S_IMG, S_TXT)):
         from oracle import flux_oracle as O
 
         self.O = O
         self.threads = threads or os.cpu_count() or 1
         torch.set_num_threads(self.threads)
-        self.blocks = blocks
-        self.cfg = O.FluxConfig(num_layers=blocks[0], num_single_layers=blocks[1], guidance_embeds=True)
-        self.P = O.init_flux_params(self.cfg, seed=0)
-        self.L = {k: v.requires_grad_(True) for k, v in O.init_lora_params(self.cfg, 16, seed=1).items()}
+        self.models = {}
+        for kind, blocks in (("double", (1, 0)), ("single", (0, 1))):
+            cfg = O.FluxConfig(num_layers=blocks[0], num_single_layers=blocks[1], guidance_embeds=True)
+            P = O.init_flux_params(cfg, seed=0)
+            L = {k: v.requires_grad_(True) for k, v in O.init_lora_params(cfg, 16, seed=1).items()}
+            self.models[kind] = (cfg, P, L)
         hw = int((seq[0] * 4) ** 0.5)
         g = torch.Generator().manual_seed(0)
         self.b = {"latents": torch.randn(1, 16, hw, hw, generator=g), "noise": torch.randn(1, 16, hw, hw, generator=g),
                   "sigmas": torch.tensor([0.6]), "prompt_embeds": torch.randn(1, seq[1], 4096, generator=g),
                   "pooled": torch.randn(1, 768, generator=g)}
         self.loss = None
+        self.times = {"double": [], "single": []}
 
-    def step(self) -> float:
+    def step(self, kind: str, record: bool = True) -> float:
+        cfg, P, L = self.models[kind]
         t0 = time.perf_counter()
-        loss, _ = self.O.flux_train_step_loss(self.P, self.cfg, self.b, lora=self.L)
+        loss, _ = self.O.flux_train_step_loss(P, cfg, self.b, lora=L)
         loss.backward()
         dt = time.perf_counter() - t0
-        for v in self.L.values():
+        for v in L.values():
             v.grad = None
         self.loss = float(loss.item())
+        if record:
+            self.times[kind].append(dt)
         return dt
 
-    def summary(self, sec: float):
-        full = sec / (self.blocks[0] + self.blocks[1]) * 57
-        return {"sec_per_sample_step": sec, "blocks": self.blocks, "threads": self.threads,
-                "extrapolated_full_depth_sec": full, "images_per_sec": 1.0 / full, "loss": self.loss}
+    def summary(self):
+        td = statistics.median(self.times["double"]) if self.times["double"] else None
+        ts = statistics.median(self.times["single"]) if self.times["single"] else None
+        if td is None:       # only singles were timed: a double block does the same attention + 1.5x the linear work
+            td = 1.5 * ts
+        if ts is None:
+            ts = td / 1.5
+        full = 19 * td + 38 * ts
+        return {"t_double_s": td, "t_single_s": ts, "n_double": len(self.times["double"]), "n_single": len(self.times["single"]),
+                "spread": {k: [round(min(v), 2), round(max(v), 2)] for k, v in self.times.items() if v},
+                "threads": self.threads, "extrapolated_full_depth_sec": full, "images_per_sec": 1.0 / full, "loss": self.loss}
 
 
-def cpu_baseline_sample(threads=None, repeats=1):
+PATTERN = ("double", "single", "single", "double", "single", "single")   # 2 double + 4 single per 6 steps (BASELINE.md 4)
+
+
+def cpu_baseline_sample(threads=None):
+    """Bounded sample for the b200 arm's `cpu_baseline` key: one double + one single block (~40 s of CPU work)."""
     cb = CpuBaseline(threads)
-    return cb.summary(min(cb.step() for _ in range(repeats)))
+    cb.step("double")
+    cb.step("single")
+    return cb.summary()
 
 
 # ------------------------------------------------------------------------------------------------ main arms
+WORKLOAD = ("Flux.1-dev LoRA rank16 (flux_lora_target=all, 266 targets, 26.1M trainable) bf16, 1024^2 cached latents [B,16,128,128] + "
+            "T5 [B,512,4096], train step = prepare_batch+fwd+loss+bwd+value-clip+optimizer")
+
+
 def run_reference(args):
+    """The reference path's CPU restatement on the host cores.  One "step" = one BLOCK-SAMPLE: forward + LoRA backward of
+    one Flux block (kinds cycle double, single, single, ... = 2 : 4) at full width and full sequence, B = 1, i.e. a
+    bounded 1/57-of-an-image piece of the workload; `ms_per_step` is the measured time of such a step and `value` is the
+    full-depth throughput 1 / (19 * median(t_double) + 38 * median(t_single))."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     cb = CpuBaseline(threads)
-    times = []
+    t_all = []
     for i in range(args.warmup + args.steps):
-        dt = cb.step()
+        dt = cb.step(PATTERN[i % len(PATTERN)], record=(i >= args.warmup))
         if i >= args.warmup:
-            times.append(dt)
-    sec = cb.summary(statistics.mean(times))["extrapolated_full_depth_sec"]
-    value = 1.0 / sec
-    sample = ("fp32 CPU oracle, B=1, ONE single-stream Flux block (of 19 double + 38 single; both kinds cost 1.31 TFLOP fwd) at full width (D=3072) and full sequence (4096+512 tokens), "
-              "fwd + LoRA backward; per-block time extrapolated linearly to 19+38 blocks")
+            t_all.append(dt)
+    sm = cb.summary()
+    value = sm["images_per_sec"]
+    sample = (f"fp32 CPU oracle port (reference needs diffusers/accelerate/peft: not installable), B=1, full width D=3072, full "
+              f"4096+512-token sequence; each step = fwd + LoRA bwd of ONE block, kinds cycling 2 double : 4 single; "
+              f"median t_double={sm['t_double_s']:.1f}s (n={sm['n_double']}), median t_single={sm['t_single_s']:.1f}s (n={sm['n_single']}), "
+              f"min/max {sm['spread']}; value = 1/(19 t_double + 38 t_single) (linear-in-depth extrapolation)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic (random-init Flux.1-dev architecture, seeded N(0,1) latents/embeds)",
-        "config": {"workload": "Flux.1-dev LoRA r16 1024^2 train step, CPU port of the reference path (depth-reduced sample, extrapolated)",
-                   "global_batch": 1, "parallelism": "cpu"},
+        "warmup": args.warmup, "ms_per_step": statistics.mean(t_all) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (random-init Flux.1-dev architecture; seeded N(0,1) cached latents + T5/CLIP embeds)",
+        "config": {"workload": WORKLOAD, "global_batch": 1, "per_gpu_batch": 1, "seq_len": S_IMG + S_TXT, "parallelism": "cpu",
+                   "step_is": "one block-sample = 1/57 of one image's train step (see cpu_baseline.sample)",
+                   "extrapolated_ms_per_image": sm["extrapolated_full_depth_sec"] * 1e3},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ eager torch baseline on the GPU
+def eager_gpu_step_fn(wrapper, device):
+    """What the reference's DEFAULT path costs on this box (informational): the dtype-agnostic oracle restatement of the
+    diffusers modules run as eager bf16 torch ops on the GPU, attention through `F.scaled_dot_product_attention`
+    (attention_mechanism="diffusers"), PEFT-style un-fused LoRA matmuls, every block under torch.utils.checkpoint
+    (gradient_checkpointing=true is the reference default), sharing the B200 model's own parameter tensors."""
+    import torch.nn.functional as F
+    from torch.utils.checkpoint import checkpoint
+
+    from oracle import flux_oracle as O
+
+    den = wrapper._denoiser()
+    P = {k: v.detach() for k, v in den.state_dict().items() if "lora_" not in k}
+    lora = {}
+    for name, lin in den.lora_linears().items():
+        lora[name + ".lora_A.weight"] = lin.lora_A["default"].weight
+        lora[name + ".lora_B.weight"] = lin.lora_B["default"].weight
+    cfg = O.FluxConfig(**{k: getattr(den.config, k) for k in ("in_channels", "num_layers", "num_single_layers", "attention_head_dim",
+                                                               "num_attention_heads", "joint_attention_dim", "pooled_projection_dim",
+                                                               "guidance_embeds", "axes_dims_rope")})
+    rope_cache = {}
+    o_rope, o_dbl, o_sgl = O.rope_tables, O.flux_double_block, O.flux_single_block
+
+    def rope_dev(ids, *a):
+        key = (tuple(ids.shape), float(ids.sum()))
+        if key not in rope_cache:
+            rope_cache[key] = tuple(t.to(device) for t in o_rope(ids.cpu(), *a))
+        return rope_cache[key]
+
+    def step(batch):
+        O.sdpa = lambda q, k, v: F.scaled_dot_product_attention(q, k, v)
+        O.rope_tables = rope_dev
+        O.flux_double_block = lambda P_, c, i, x, enc, temb, rope, lo, ls: checkpoint(
+            lambda x_, e_, t_: o_dbl(P_, c, i, x_, e_, t_, rope, lo, ls), x, enc, temb, use_reentrant=False)
+        O.flux_single_block = lambda P_, c, i, x, temb, rope, lo, ls: checkpoint(
+            lambda x_, t_: o_sgl(P_, c, i, x_, t_, rope, lo, ls), x, temb, use_reentrant=False)
+        try:
+            lat = batch["latent_batch"]
+            B, Cc, Hh, Ww = lat.shape
+            noise = torch.randn_like(lat)
+            sig = torch.sigmoid(torch.randn((B,), device=device))
+            sig = (3.0 * sig) / (1 + 2.0 * sig)
+            s4 = sig.view(-1, 1, 1, 1).to(lat.dtype)
+            noisy = (1 - s4) * lat + s4 * noise
+            packed = O.pack_latents(noisy, B, Cc, Hh, Ww)
+            img_ids = O.prepare_latent_image_ids(Hh, Ww).to(device)
+            txt_ids = torch.zeros(batch["prompt_embeds"].shape[1], 3, device=device)
+            g = torch.full((B,), 1.0, device=device)
+            out = O.flux_forward(P, cfg, packed, batch["prompt_embeds"], batch["add_text_embeds"], sig, img_ids, txt_ids, g, lora, 1.0)
+            pred = O.unpack_latents(out, Hh * 8, Ww * 8, 16)
+            loss = F.mse_loss(pred.float(), (noise - lat).float(), reduction="none").mean(dim=(1, 2, 3)).mean()
+            loss.backward()
+            return loss.detach()
+        finally:
+            O.sdpa, O.rope_tables, O.flux_double_block, O.flux_single_block = o_sdpa, o_rope, o_dbl, o_sgl
+
+    o_sdpa = O.sdpa
+    return step
+
+
+def time_eager_gpu(wrapper, device, batches, opt, steps=3, warmup=2):
+    fn = eager_gpu_step_fn(wrapper, device)
+
+    def one(i):
+        fn(batches[i % len(batches)])
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        one(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
 
 
 def run_b200(args):
@@ -289,7 +404,7 @@ def run_b200(args):
     wrapper = build_model(device, cfg_over, rank=16, seed=0)
     if args.gradient_checkpointing:   # non-default: the reference's --gradient_checkpointing memory / time trade-off
         wrapper._denoiser().enable_gradient_checkpointing()
-    if world > 1:
+    if world > 1 and args.dp == "ddp":
         wrap_ddp(wrapper, device_ids=[local_rank])
     params = wrapper._denoiser().trainable_parameters()
     if args.optimizer == "adamw_bf16":   # the reference's default optimizer, one libstb200 launch per step
@@ -297,7 +412,11 @@ def run_b200(args):
         opt = AdamWBF16(params, lr=1e-4, weight_decay=1e-2, eps=1e-6, seed=1234 + rank)
     else:
         opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-2, fused=True)
-    step = TrainStep(wrapper, opt, max_grad_norm=2.0, grad_clip_method="value")
+    grad_sync = None
+    if world > 1 and args.dp == "flat":
+        from simpletuner_b200.training.dist import FlatGradSync
+        grad_sync = FlatGradSync(params)
+    step = TrainStep(wrapper, opt, max_grad_norm=2.0, grad_clip_method="value", grad_sync=grad_sync)
     torch.manual_seed(42 + rank)  # seed_for_each_device=True (trainer.py:2554-2556)
     joint = cfg_over["joint_attention_dim"] if cfg_over else 4096
     pooled = cfg_over["pooled_projection_dim"] if cfg_over else 768
@@ -383,8 +502,8 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic (random-init Flux.1-dev architecture; seeded N(0,1) cached latents + T5/CLIP embeds)",
             "config": {
-                "workload": "Flux.1-dev LoRA rank16 (flux_lora_target=all, 266 targets, 26.1M trainable) bf16, 1024^2 cached latents [B,16,128,128] + T5 [B,512,4096], train step = prepare_batch+fwd+loss+bwd+value-clip+optimizer",
-                "global_batch": B * world, "per_gpu_batch": B, "seq_len": S_IMG + S_TXT, "parallelism": f"dp{world}",
+                "workload": WORKLOAD,
+                "global_batch": B * world, "per_gpu_batch": B, "seq_len": S_IMG + S_TXT, "parallelism": f"dp{world}", "grad_exchange": (None if world == 1 else args.dp),
                 "activation_recompute": ("every block re-run in backward (--gradient-checkpointing)" if args.gradient_checkpointing else
                                          "none (block-native minimal saves; reference default would recompute every block)"),
                 "host_syncs_in_step": 0, "l2_policy": "inputs larger than L2 (24 GB of weights + 16 MB fresh batch streamed every step)",
@@ -402,12 +521,24 @@ def run_b200(args):
                              "frac_of_peak": round(TF_STEP_SAMPLE * B / (ms_step * 1e-3) / peak_tf, 4)} if not args.tiny else None,
             "kernels": kern, "peak_mem_gb": round(mem_gb, 1),
         }
+        if world == 1 and not args.no_eager_baseline and not args.tiny:
+            try:   # informational: the reference's default eager path (SDPA + per-block checkpointing) on this GPU, same batch
+                torch.cuda.empty_cache()
+                ms_eager = time_eager_gpu(wrapper, device, dev_batches, opt)
+                line["gpu_eager_baseline"] = {
+                    "value": B / (ms_eager * 1e-3), "unit": UNIT, "ms_per_step": ms_eager,
+                    "what": "eager bf16 torch ops (oracle restatement of the diffusers modules) on this GPU, F.scaled_dot_product_attention, "
+                            "un-fused PEFT-style LoRA, torch.utils.checkpoint around every block (reference default "
+                            "gradient_checkpointing=true), same parameters / batch / optimizer; 3 timed steps after 2 warm-up"}
+            except Exception as e:  # noqa
+                line["gpu_eager_baseline"] = {"error": str(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cb = cpu_baseline_sample()
                 line["cpu_baseline"] = {"value": cb["images_per_sec"], "unit": UNIT, "cores": cb["threads"], "kind": "port",
-                                        "sample": "fp32 CPU oracle, B=1, one single-stream block at full width/sequence, fwd + LoRA bwd, "
-                                                  f"{cb['sec_per_sample_step']:.1f} s measured, extrapolated linearly to 57 blocks"}
+                                        "sample": "fp32 CPU oracle, B=1, full width / full 4608-token sequence, fwd + LoRA bwd of one double "
+                                                  f"block ({cb['t_double_s']:.1f} s) and one single block ({cb['t_single_s']:.1f} s), "
+                                                  "extrapolated as 19 t_double + 38 t_single; `--impl reference` times the 2:4 pattern with medians"}
             except Exception as e:  # noqa
                 line["cpu_baseline"] = {"error": str(e)[:200]}
         print(json.dumps(line))
@@ -424,8 +555,12 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--tiny", action="store_true", help="plumbing check on a toy config (not a benchmark value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the informational eager-torch GPU baseline (N=1 only)")
     ap.add_argument("--optimizer", default="adamw_bf16", choices=["adamw", "adamw_bf16"],
                     help="adamw_bf16 = the reference's default optimizer (one libstb200 launch); adamw = torch.optim.AdamW(fused)")
+    ap.add_argument("--dp", default="flat", choices=["flat", "ddp"],
+                    help="gradient exchange for N > 1: flat = one NCCL all-reduce of all LoRA gradients after backward "
+                         "(training.dist.FlatGradSync); ddp = torch DDP buckets overlapped with backward (the reference's mechanism)")
     ap.add_argument("--gradient-checkpointing", action="store_true",
                     help="re-run every block in backward like the reference's --gradient_checkpointing (not the headline config)")
     args = ap.parse_args()

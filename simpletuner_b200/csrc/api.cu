@@ -16,6 +16,7 @@
 
 #include "../../include/stb200.h"
 #include "attn_bwd.cuh"
+#include "attn_bwd128.cuh"
 #include "attn_fwd.cuh"
 #include "attn_fwd_pair.cuh"
 #include "optim.cuh"
@@ -277,18 +278,31 @@ static int launch_attn_bwd(const stb_attn_bwd_args* a, const stb::AttnBwdMaps& m
         static_cast<const __nv_bfloat16*>(a->d_o), a->do_b, a->do_s, a->do_h, a->delta, a->B, a->H, a->Sq);
     STB_LAUNCH_CHECK("attn_bwd_delta");
   }
+  // Kernel selection: the 128-wide phase-split kernels (attn_bwd128.cuh) are the default; the 64-wide double-buffered ones
+  // (attn_bwd.cuh) remain for the fused q / k pre-processing epilogue (qk_prep) and for A/B timing
+  // (STB_ATTN_BWD_DKDV=64 / STB_ATTN_BWD_DQ=64, read once per process).
+  static const bool old_dkdv = [] { const char* e = std::getenv("STB_ATTN_BWD_DKDV"); return e && e[0] == '6'; }();
+  static const bool old_dq = [] { const char* e = std::getenv("STB_ATTN_BWD_DQ"); return e && e[0] == '6'; }();
   constexpr int SMEM = stb::AttnBwdCfg<HD>::SMEM_BYTES;
+  constexpr int SMEM_DKDV = stb::AttnBwd128Cfg<HD>::SMEM_DKDV;
+  constexpr int SMEM_DQ = stb::AttnBwd128Cfg<HD>::SMEM_DQ;
   auto k1 = stb::attn_bwd_dkdv_kernel<HD>;
   auto k2 = stb::attn_bwd_dq_kernel<HD>;
+  auto n1 = stb::attn_bwd_dkdv128_kernel<HD>;
+  auto n2 = stb::attn_bwd_dq128_kernel<HD>;
   static bool configured = false;
   if (!configured) {
     if (int r = set_smem(k1, SMEM)) return r;
     if (int r = set_smem(k2, SMEM)) return r;
+    if (int r = set_smem(n1, SMEM_DKDV)) return r;
+    if (int r = set_smem(n2, SMEM_DQ)) return r;
     configured = true;
   }
-  k1<<<dim3((a->Sk + 127) / 128, a->H, a->B), 384, SMEM, st>>>(maps, p);
+  if (p.fuse_prep || old_dkdv) k1<<<dim3((a->Sk + 127) / 128, a->H, a->B), 384, SMEM, st>>>(maps, p);
+  else n1<<<dim3((a->Sk + 127) / 128, a->H, a->B), 384, SMEM_DKDV, st>>>(maps, p);
   STB_LAUNCH_CHECK("attn_bwd_dkdv");
-  k2<<<dim3((a->Sq + 127) / 128, a->H, a->B), 384, SMEM, st>>>(maps, p);
+  if (p.fuse_prep || old_dq) k2<<<dim3((a->Sq + 127) / 128, a->H, a->B), 384, SMEM, st>>>(maps, p);
+  else n2<<<dim3((a->Sq + 127) / 128, a->H, a->B), 384, SMEM_DQ, st>>>(maps, p);
   STB_LAUNCH_CHECK("attn_bwd_dq");
   return 0;
 }

@@ -93,3 +93,45 @@ def shard_units(num_units: int, rank: int, world_size: int) -> range:
     """Contiguous split of independent work units (micro-batches) across ranks for weak-scaling runs."""
     per = num_units // world_size
     return range(rank * per, (rank + 1) * per)
+
+
+class FlatGradSync:
+    """Data-parallel gradient exchange as ONE flat all-reduce after backward, on the compute stream.
+
+    The reference wraps the model in torch DDP (accelerator.prepare, trainer.py:4571, 1026-1041): bucketed all-reduces
+    launched from autograd hooks on NCCL's side stream, overlapping the backward.  For LoRA training the whole exchange
+    is 52 MB (26 M bf16 gradients): < 1 ms over NVLink 5 / NVSwitch, while the overlapped NCCL kernels take SMs away from
+    the persistent one-CTA-per-SM GEMM / attention grids of the backward for its whole duration (measured in round 1:
+    +36 ms per step from 4 ranks up, SCALE_r01.json).  So the exchange runs after backward instead: cat -> all_reduce
+    (mean) -> foreach copy back, three launches plus one collective.  `__call__` is invoked by TrainStep on
+    accumulation boundaries only (the reference's `no_sync` on the other micro-steps).  Parameters are broadcast from
+    rank 0 at construction, as DDP does."""
+
+    def __init__(self, params, group=None, broadcast: bool = True):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.sizes = [p.numel() for p in self.params]
+        if broadcast and self.world > 1 and self.params:
+            with torch.no_grad():
+                flat = torch.cat([p.detach().reshape(-1) for p in self.params])
+                dist.broadcast(flat, src=0, group=group)
+                torch._foreach_copy_([p.data for p in self.params], [c.view_as(p) for c, p in zip(flat.split(self.sizes), self.params)])
+
+    @torch.no_grad()
+    def __call__(self) -> None:
+        if self.world == 1 or not self.params:
+            return
+        grads = []
+        for p in self.params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            grads.append(p.grad)
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        backend = dist.get_backend(self.group)
+        if backend == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+        torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split(self.sizes), grads)])

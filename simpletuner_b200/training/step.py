@@ -10,8 +10,9 @@ What is deliberately different from the reference loop (and stated with every be
   * no device->host sync inside the step: the non-finite-loss check (`trainer.py:7103`) is folded
     into a device-side flag that the caller polls when it logs (`check_finite()`), and the
     sample-weighted loss all-gather + `.item()` per micro-step (`:7114-7115`) is deferred to logging;
-  * gradient all-reduce is torch DDP's bucketed NCCL all-reduce, overlapped with the block-by-block
-    backward (the wrapper is built by `wrap_ddp`), exactly one per optimizer step.
+  * the gradient exchange is exactly one per optimizer step: either `training.dist.FlatGradSync` (default of bench.py:
+    one flat NCCL all-reduce after backward on the compute stream) or torch DDP's bucketed all-reduce overlapped with the
+    block-by-block backward (`wrap_ddp`, the reference's mechanism).
 """
 from __future__ import annotations
 
@@ -22,7 +23,7 @@ import torch
 
 class TrainStep:
     def __init__(self, model, optimizer: torch.optim.Optimizer, *, max_grad_norm: float = 2.0,
-                 grad_clip_method: str = "value", gradient_accumulation_steps: int = 1):
+                 grad_clip_method: str = "value", gradient_accumulation_steps: int = 1, grad_sync=None):
         self.model = model            # simpletuner_b200.flux.model.Flux (or another family wrapper)
         self.optimizer = optimizer
         self.max_grad_norm = max_grad_norm
@@ -31,6 +32,7 @@ class TrainStep:
         self.state = {"global_step": 0, "micro_step": 0}
         self._params = [p for g in optimizer.param_groups for p in g["params"]]
         self._nonfinite = None
+        self.grad_sync = grad_sync    # e.g. training.dist.FlatGradSync: called once per optimizer step, before the clip
 
     def _clip(self):
         if self.max_grad_norm is None or self.max_grad_norm <= 0:
@@ -62,6 +64,8 @@ class TrainStep:
         self._nonfinite = bad if self._nonfinite is None else (self._nonfinite | bad)
         self.state["micro_step"] += 1
         if sync:
+            if self.grad_sync is not None:
+                self.grad_sync()
             self._clip()
             self.optimizer.step()
             self.optimizer.zero_grad(set_to_none=True)

@@ -122,3 +122,45 @@ def test_ddp_gloo_accumulation_all_reduces_once_and_averages():
     w0 = ref.model.weight.detach().clone()
     l.backward()
     assert torch.allclose(torch.tensor(res[0][2]), (w0 - 0.1 * ref.model.weight.grad).flatten(), atol=1e-6)
+
+
+def _flat_worker(rank, world_size, init_method, q):
+    try:
+        dist.init_process_group("gloo", init_method=init_method, rank=rank, world_size=world_size, timeout=timedelta(seconds=30))
+        from simpletuner_b200.training.dist import FlatGradSync
+        w = Toy()
+        with torch.no_grad():
+            w.model.weight.add_(float(rank))          # ranks start apart: the constructor broadcasts rank 0's weights
+        sync = FlatGradSync(w.model.parameters())
+        opt = torch.optim.SGD(w.model.parameters(), lr=0.1)
+        step = TrainStep(w, opt, max_grad_norm=0.0, gradient_accumulation_steps=2, grad_sync=sync)
+        step(_batch(10 + rank))         # accumulates locally, no collective
+        step(_batch(20 + rank))         # boundary: one flat all-reduce (mean) of the accumulated gradients
+        q.put(("ok", rank, w.model.weight.detach().flatten().tolist()))
+    except BaseException:
+        q.put(("error", rank, traceback.format_exc()))
+        raise
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_flat_grad_sync_gloo_matches_ddp_semantics():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with tempfile.TemporaryDirectory() as d:
+        init = f"file://{os.path.join(d, 'rdv')}"
+        procs = [ctx.Process(target=_flat_worker, args=(r, 2, init, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(90)
+        assert all(not p.is_alive() for p in procs)
+    res = sorted((q.get(timeout=5) for _ in procs), key=lambda t: t[1])
+    assert [r[0] for r in res] == ["ok", "ok"], res
+    assert res[0][2] == res[1][2]
+    ref = Toy()
+    l = sum(ref.loss_with_logs(b, ref.model_predict(b))[0] for b in (_batch(10), _batch(20), _batch(11), _batch(21))) / 4
+    w0 = ref.model.weight.detach().clone()
+    l.backward()
+    assert torch.allclose(torch.tensor(res[0][2]), (w0 - 0.1 * ref.model.weight.grad).flatten(), atol=1e-6)

@@ -8,13 +8,6 @@
 
 using namespace stb;
 
-__device__ __forceinline__ void tmem_ld_x64(uint32_t taddr, uint32_t (&r)[64]) {
-  uint32_t (&a)[32] = reinterpret_cast<uint32_t (&)[32]>(r[0]);
-  uint32_t (&b)[32] = reinterpret_cast<uint32_t (&)[32]>(r[32]);
-  tmem_ld_32x32b_x32(taddr, a);
-  tmem_ld_32x32b_x32(taddr + 32, b);
-}
-
 // mode 0: LDTM x32 repeated; 1: LDTM x128; 2: STTM x32; 3: ex2 only; 4..: softmax loops on a 128 x 128 tile per 4 warps
 __global__ void __launch_bounds__(256, 1) probe(int mode, int nwarps, int iters, long long* out, float* sink) {
   __shared__ uint32_t slot;
@@ -46,7 +39,7 @@ __global__ void __launch_bounds__(256, 1) probe(int mode, int nwarps, int iters,
         for (int c = 0; c < 128; c += 32) {
           tmem_ld_32x32b_x32(tm + lane_off + col0 + c, v);
           tc_wait_ld();
-          acc += __uint_as_float(v[it & 31]);
+          acc += __uint_as_float(v[0]) + __uint_as_float(v[31]);
         }
       }
     } else if (mode == 1) {
@@ -54,7 +47,7 @@ __global__ void __launch_bounds__(256, 1) probe(int mode, int nwarps, int iters,
         uint32_t v[128];
         tmem_ld_32x32b_x128(tm + lane_off + col0, v);
         tc_wait_ld();
-        acc += __uint_as_float(v[it & 127]);
+        acc += __uint_as_float(v[0]) + __uint_as_float(v[127]);
       }
     } else if (mode == 2) {
       uint32_t v[32];
@@ -95,14 +88,14 @@ __global__ void __launch_bounds__(256, 1) probe(int mode, int nwarps, int iters,
           m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
         }
         const float mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2 + mb * 0.f;
-        uint32_t pk[64];
+        uint32_t pkA[32], pkB[32];
         if (mode == 4) {
 #pragma unroll
           for (int i = 0; i < 128; i += 2) {
             const float x0 = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mt));
             const float x1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -mt));
             l0 += x0; l1 += x1;
-            pk[i / 2] = pack_bf16x2(x0, x1);
+            if (i < 64) pkA[i / 2] = pack_bf16x2(x0, x1); else pkB[i / 2 - 32] = pack_bf16x2(x0, x1);
           }
         } else {
           // mode 5: every 4th pair through a degree-3 polynomial on the FMA pipe (25 %); mode 6: every 2nd pair (50 %)
@@ -125,15 +118,11 @@ __global__ void __launch_bounds__(256, 1) probe(int mode, int nwarps, int iters,
               x0 = ex2f(a0); x1 = ex2f(a1);
             }
             l0 += x0; l1 += x1;
-            pk[i / 2] = pack_bf16x2(x0, x1);
+            if (i < 64) pkA[i / 2] = pack_bf16x2(x0, x1); else pkB[i / 2 - 32] = pack_bf16x2(x0, x1);
           }
         }
-        {
-          uint32_t (&pa)[32] = reinterpret_cast<uint32_t (&)[32]>(pk[0]);
-          uint32_t (&pb)[32] = reinterpret_cast<uint32_t (&)[32]>(pk[32]);
-          tmem_st_32x32b_x32(tm + lane_off + col0, pa);
-          tmem_st_32x32b_x32(tm + lane_off + col0 + 32, pb);
-        }
+        tmem_st_32x32b_x32(tm + lane_off + col0, pkA);
+        tmem_st_32x32b_x32(tm + lane_off + col0 + 32, pkB);
         tc_wait_st();
         // restore fp32-looking data so the next iteration computes on sane values
         {
