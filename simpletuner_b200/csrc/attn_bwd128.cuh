@@ -211,6 +211,7 @@ attn_bwd_dkdv128_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdP
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const uint32_t col0 = 64u * w;                 // this warpgroup's query columns of every tile
     const float sl2 = p.scale * 1.4426950408889634f;
+    const float2 sl2x2 = make_float2(sl2, sl2);
     const float l2e = 1.4426950408889634f;
     const long long stat_base = ((long long)b * p.H + h) * p.Sq;
     float* my_stat = stat_ptr + warp * 256;        // [2 parities][lse2 64 | delta 64], private to this warp
@@ -218,10 +219,11 @@ attn_bwd_dkdv128_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdP
     auto fetch = [&](int tile, float (&s)[4]) {
       const int q0 = tile * 128 + int(col0) + lane;
       const bool ok0 = q0 < p.Sq, ok1 = q0 + 32 < p.Sq;
-      s[0] = ok0 ? p.lse[stat_base + q0] * l2e : INFINITY;       // invalid query: P = exp2(-inf) = 0
-      s[1] = ok1 ? p.lse[stat_base + q0 + 32] * l2e : INFINITY;
-      s[2] = ok0 ? p.delta[stat_base + q0] : 0.f;
-      s[3] = ok1 ? p.delta[stat_base + q0 + 32] : 0.f;
+      // stored NEGATED: they are the addends of the packed FFMA2 / FADD2 below
+      s[0] = ok0 ? -p.lse[stat_base + q0] * l2e : -INFINITY;       // invalid query: P = exp2(-inf) = 0
+      s[1] = ok1 ? -p.lse[stat_base + q0 + 32] * l2e : -INFINITY;
+      s[2] = ok0 ? -p.delta[stat_base + q0] : 0.f;
+      s[3] = ok1 ? -p.delta[stat_base + q0 + 32] : 0.f;
     };
     auto stash = [&](int buf, const float (&s)[4]) {
       float* d = my_stat + buf * 128;
@@ -255,11 +257,10 @@ attn_bwd_dkdv128_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdP
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 4) {
           const int j = hf * 32 + jj;
-          const float4 l4 = *reinterpret_cast<const float4*>(lse_s + j);   // smem broadcast
-          const float x0 = ex2f(fmaf(__uint_as_float(pv[j + 0]), sl2, -l4.x));
-          const float x1 = ex2f(fmaf(__uint_as_float(pv[j + 1]), sl2, -l4.y));
-          const float x2 = ex2f(fmaf(__uint_as_float(pv[j + 2]), sl2, -l4.z));
-          const float x3 = ex2f(fmaf(__uint_as_float(pv[j + 3]), sl2, -l4.w));
+          const float4 l4 = *reinterpret_cast<const float4*>(lse_s + j);   // smem broadcast (-lse2)
+          const float2 a01 = __ffma2_rn(make_float2(__uint_as_float(pv[j + 0]), __uint_as_float(pv[j + 1])), sl2x2, make_float2(l4.x, l4.y));
+          const float2 a23 = __ffma2_rn(make_float2(__uint_as_float(pv[j + 2]), __uint_as_float(pv[j + 3])), sl2x2, make_float2(l4.z, l4.w));
+          const float x0 = ex2f(a01.x), x1 = ex2f(a01.y), x2 = ex2f(a23.x), x3 = ex2f(a23.y);
           pv[j + 0] = __float_as_uint(x0);
           pv[j + 1] = __float_as_uint(x1);
           pv[j + 2] = __float_as_uint(x2);
@@ -285,11 +286,13 @@ attn_bwd_dkdv128_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdP
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 4) {
           const int j = hf * 32 + jj;
-          const float4 d4 = *reinterpret_cast<const float4*>(del_s + j);
-          pk[jj / 2] = pack_bf16x2(__uint_as_float(pv[j + 0]) * (__uint_as_float(dv[jj + 0]) - d4.x),
-                                   __uint_as_float(pv[j + 1]) * (__uint_as_float(dv[jj + 1]) - d4.y));
-          pk[jj / 2 + 1] = pack_bf16x2(__uint_as_float(pv[j + 2]) * (__uint_as_float(dv[jj + 2]) - d4.z),
-                                       __uint_as_float(pv[j + 3]) * (__uint_as_float(dv[jj + 3]) - d4.w));
+          const float4 d4 = *reinterpret_cast<const float4*>(del_s + j);   // (-delta)
+          const float2 t01 = __fadd2_rn(make_float2(__uint_as_float(dv[jj + 0]), __uint_as_float(dv[jj + 1])), make_float2(d4.x, d4.y));
+          const float2 t23 = __fadd2_rn(make_float2(__uint_as_float(dv[jj + 2]), __uint_as_float(dv[jj + 3])), make_float2(d4.z, d4.w));
+          const float2 e01 = __fmul2_rn(make_float2(__uint_as_float(pv[j + 0]), __uint_as_float(pv[j + 1])), t01);
+          const float2 e23 = __fmul2_rn(make_float2(__uint_as_float(pv[j + 2]), __uint_as_float(pv[j + 3])), t23);
+          pk[jj / 2] = pack_bf16x2(e01.x, e01.y);
+          pk[jj / 2 + 1] = pack_bf16x2(e23.x, e23.y);
         }
         tmem_st_32x32b_x16(Y + lane_off + col0 + 16 * hf, pk);
       }
@@ -468,6 +471,7 @@ attn_bwd_dq128_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPar
     const long long stat_idx = ((long long)b * p.H + h) * p.Sq + qrow;
     const float lse2 = row_ok ? p.lse[stat_idx] * 1.4426950408889634f : INFINITY;
     const float delta = row_ok ? p.delta[stat_idx] : 0.f;
+    const float2 sl2x2 = make_float2(sl2, sl2), nlse2x2 = make_float2(-lse2, -lse2), ndeltax2 = make_float2(-delta, -delta);
     {  // warpgroup 0 stages this thread's Q row, warpgroup 1 its dO row (global -> registers -> TMEM)
       const __nv_bfloat16* src = (w == 0)
           ? p.q + (long long)b * p.q_b + (long long)qrow * p.q_s + (long long)h * p.q_h
@@ -505,7 +509,11 @@ attn_bwd_dq128_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPar
           if (i >= kv_valid) pv[i] = 0xff800000u;  // -inf -> P = 0
       }
 #pragma unroll
-      for (int i = 0; i < 64; ++i) pv[i] = __float_as_uint(ex2f(fmaf(__uint_as_float(pv[i]), sl2, -lse2)));
+      for (int i = 0; i < 64; i += 2) {   // packed FFMA2 halves the FMA-pipe instruction count of the phase
+        const float2 a = __ffma2_rn(make_float2(__uint_as_float(pv[i]), __uint_as_float(pv[i + 1])), sl2x2, nlse2x2);
+        pv[i] = __float_as_uint(ex2f(a.x));
+        pv[i + 1] = __float_as_uint(ex2f(a.y));
+      }
       // ---- phase B: dS = P o (dP - delta)   (softmax scale applied in the epilogue)
       mbar_wait(dp_full, j & 1, 77);
       tc_fence_after();
@@ -516,9 +524,11 @@ attn_bwd_dq128_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPar
         tc_wait_ld();
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          pk[i / 2] = pack_bf16x2(__uint_as_float(pv[hf * 32 + i]) * (__uint_as_float(dv[i]) - delta),
-                                  __uint_as_float(pv[hf * 32 + i + 1]) * (__uint_as_float(dv[i + 1]) - delta));
+        for (int i = 0; i < 32; i += 2) {
+          const float2 t = __fadd2_rn(make_float2(__uint_as_float(dv[i]), __uint_as_float(dv[i + 1])), ndeltax2);
+          const float2 e = __fmul2_rn(make_float2(__uint_as_float(pv[hf * 32 + i]), __uint_as_float(pv[hf * 32 + i + 1])), t);
+          pk[i / 2] = pack_bf16x2(e.x, e.y);
+        }
         tmem_st_32x32b_x16(Yb + lane_off + col0 + 16 * hf, pk);
       }
       tc_wait_st();

@@ -221,20 +221,20 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdMaps maps, const AttnFwdParams p)
       tc_fence_after();
       const int kv_valid = p.Sk - j * 128;  // >= 1; < 128 only on the last, ragged tile
       const bool ragged = kv_valid < 128;   // CTA-uniform: only the last, ragged key tile pays for masking
-      // ---- pass 1: row max (TMEM read #1; 4 independent max chains)
+      // ---- pass 1: row max, two 64-column TMEM reads (4 independent max chains)
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(s_t + c, v);
+      for (int c = 0; c < 128; c += 64) {
+        uint32_t v[64];
+        tmem_ld_32x32b_x64(s_t + c, v);
         tc_wait_ld();
         if (ragged) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
+          for (int i = 0; i < 64; ++i)
             if (c + i >= kv_valid) v[i] = 0xff800000u;  // -inf
         }
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < 64; i += 4) {
           m0 = fmaxf(m0, __uint_as_float(v[i]));
           m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
           m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
@@ -264,30 +264,34 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdMaps maps, const AttnFwdParams p)
           tc_wait_st();
         }
       }
-      // ---- pass 2: P = exp2(s*sl2 - m*sl2) -> bf16, in place over S (TMEM read #2)
-      const float mb = m_used * sl2;
-      float l0 = 0.f, l1 = 0.f;
+      // ---- pass 2: P = exp2(s*sl2 - m*sl2) -> bf16, in place over the first 64 columns of S (packed FFMA2 / FADD2 math).
+      // The packed store of columns [c/2, c/2 + 32) only overwrites fp32 columns that are already in registers.
+      const float2 sl2x2 = make_float2(sl2, sl2), nmb = make_float2(-m_used * sl2, -m_used * sl2);
+      float2 lacc = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(s_t + c, v);
+      for (int c = 0; c < 128; c += 64) {
+        uint32_t v[64];
+        tmem_ld_32x32b_x64(s_t + c, v);
         tc_wait_ld();
         if (ragged) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
+          for (int i = 0; i < 64; ++i)
             if (c + i >= kv_valid) v[i] = 0xff800000u;  // exp2(-inf) = 0
         }
-        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float x0 = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mb));
-          const float x1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -mb));
-          l0 += x0;
-          l1 += x1;
-          pk[i / 2] = pack_bf16x2(x0, x1);
+        for (int h2 = 0; h2 < 64; h2 += 32) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 a = __ffma2_rn(make_float2(__uint_as_float(v[h2 + i]), __uint_as_float(v[h2 + i + 1])), sl2x2, nmb);
+            const float2 x = make_float2(ex2f(a.x), ex2f(a.y));
+            lacc = __fadd2_rn(lacc, x);
+            pk[i / 2] = pack_bf16x2(x.x, x.y);
+          }
+          tmem_st_32x32b_x16(s_t + (c + h2) / 2, pk);
         }
-        tmem_st_32x32b_x16(s_t + c / 2, pk);
       }
+      const float l0 = lacc.x, l1 = lacc.y;
       const float lsum = l0 + l1;
       l += lsum;
       tc_wait_st();
