@@ -213,6 +213,18 @@ int stb_gate_mul(const void* x, long long x_b, long long x_s, const void* gate, 
                  long long y_b, long long y_s, int B, int S, int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * LoRA dropout (PEFT `lora_dropout`, reference common.py:1094-1117; default 0.1: field_registry/sections/lora.py:130-137).
+ * Masks are a counter-based function of (seed, stream0 + member, element index of the logical [B,S,K] tensor) and are
+ * regenerated in backward, never stored.
+ *   stb_dropout_expand: out[m, b, s, :] = bf16(x[b, s, :] * keep_m / (1 - p)), out contiguous [members, B, S, K]
+ *   stb_dropout_accum : dx[b, s, :] += sum_m keep_m / (1 - p) * d[m, b, s, :],  d contiguous [members, B, S, K]
+ * K multiple of 8, 0 <= p < 1. */
+int stb_dropout_expand(const void* x, long long x_b, long long x_s, void* out, int members, int B, int S, int K, float p,
+                       unsigned int seed, unsigned int stream0, void* stream);
+int stb_dropout_accum(const void* d, void* dx, long long dx_b, long long dx_s, int members, int B, int S, int K, float p,
+                      unsigned int seed, unsigned int stream0, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * LoRA weight gradients: out[r, n] += alpha * sum_m L[m, r] * Rm[m, n]   (fp32 out, R in 16..64)
  *   dA = s * (dY B)^T X   (L = dY B [M, r], Rm = X  [M, K])
  *   dB^T = s * (X A^T)^T dY (L = X A^T [M, r], Rm = dY [M, N])

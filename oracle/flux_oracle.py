@@ -150,15 +150,24 @@ def init_lora_params(cfg: FluxConfig, rank: int, seed: int = 1, dtype=torch.floa
 # --------------------------------------------------------------------------------------------------
 # layer restatements (diffusers semantics)
 # --------------------------------------------------------------------------------------------------
+# PEFT lora_dropout replay (tests only): {linear name: mask [B, S, K] already divided by (1 - p)}.  PEFT applies
+# `lora_B(lora_A(dropout(x)))` with one nn.Dropout per adapted Linear; the CUDA path draws its masks from its own
+# counter-based generator, so parity tests materialise those masks and replay them here.
+DROPOUT_MASKS: Optional[Dict[str, Tensor]] = None
+
+
 def linear(x: Tensor, P: Dict[str, Tensor], name: str, lora: Optional[Dict[str, Tensor]] = None,
            lora_scale: float = 1.0) -> Tensor:
     """nn.Linear, optionally wrapped by PEFT lora.Linear (reference common.py:1094-1117):
-    result = base(x) + lora_B(lora_A(x)) * scaling   (dropout pinned to 0 for parity runs)."""
+    result = base(x) + lora_B(lora_A(dropout(x))) * scaling   (dropout = identity unless DROPOUT_MASKS replays a mask)."""
     y = F.linear(x, P[name + ".weight"], P.get(name + ".bias"))
     if lora is not None and (name + ".lora_A.weight") in lora:
         a = lora[name + ".lora_A.weight"]
         b = lora[name + ".lora_B.weight"]
-        y = y + F.linear(F.linear(x, a), b) * lora_scale
+        xa = x
+        if DROPOUT_MASKS is not None and name in DROPOUT_MASKS:
+            xa = (x * DROPOUT_MASKS[name].to(x.dtype)).to(x.dtype)
+        y = y + F.linear(F.linear(xa, a), b) * lora_scale
     return y
 
 

@@ -4,6 +4,7 @@
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -710,6 +711,41 @@ int stb_gate_mul(const void* x, long long x_b, long long x_s, const void* gate, 
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
   stb::gate_mul_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_b, x_s, static_cast<const __nv_bfloat16*>(gate), g_b, static_cast<__nv_bfloat16*>(y), y_b, y_s, B, S, D);
   STB_LAUNCH_CHECK("gate_mul");
+  return 0;
+}
+
+static int dropout_args(const void* a, const void* b, int members, int B, int S, int K, float p) {
+  if (!a || !b || members < 1 || members > 8 || B < 1 || S < 1 || K < 8 || (K & 7)) return fail(STB_ERR_ARG, "dropout: bad shape (K multiple of 8, 1..8 members)");
+  if (!(p >= 0.f && p < 1.f)) return fail(STB_ERR_ARG, "dropout: p must be in [0, 1)");
+  if (!aligned16(a) || !aligned16(b)) return fail(STB_ERR_ARG, "dropout: pointers must be 16-byte aligned");
+  return 0;
+}
+
+int stb_dropout_expand(const void* x, long long x_b, long long x_s, void* out, int members, int B, int S, int K, float p,
+                       unsigned int seed, unsigned int stream0, void* stream) {
+  if (int r = check_device()) return r;
+  if (int r = dropout_args(x, out, members, B, S, K, p)) return r;
+  if ((x_b & 7) || (x_s & 7)) return fail(STB_ERR_ARG, "dropout_expand: strides must be multiples of 8 elements");
+  const long long total = (long long)B * S * (K >> 3);
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+  const uint32_t thresh = (uint32_t)std::llround(double(p) * 16777216.0);
+  stb::dropout_expand_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_b, x_s, static_cast<__nv_bfloat16*>(out), members, B, S, K, 1.f / (1.f - p), thresh, seed, stream0);
+  STB_LAUNCH_CHECK("dropout_expand");
+  return 0;
+}
+
+int stb_dropout_accum(const void* d, void* dx, long long dx_b, long long dx_s, int members, int B, int S, int K, float p,
+                      unsigned int seed, unsigned int stream0, void* stream) {
+  if (int r = check_device()) return r;
+  if (int r = dropout_args(d, dx, members, B, S, K, p)) return r;
+  if ((dx_b & 7) || (dx_s & 7)) return fail(STB_ERR_ARG, "dropout_accum: strides must be multiples of 8 elements");
+  const long long total = (long long)B * S * (K >> 3);
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+  const uint32_t thresh = (uint32_t)std::llround(double(p) * 16777216.0);
+  stb::dropout_accum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(d), static_cast<__nv_bfloat16*>(dx), dx_b, dx_s, members, B, S, K, 1.f / (1.f - p), thresh, seed, stream0);
+  STB_LAUNCH_CHECK("dropout_accum");
   return 0;
 }
 

@@ -649,6 +649,82 @@ gate_mul_kernel(const __nv_bfloat16* __restrict__ x, long long x_b, long long x_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// LoRA dropout (PEFT `lora_dropout`: result += lora_B(lora_A(dropout(x))) * scaling, reference common.py:1094-1117 with the
+// reference default lora_dropout = 0.1, field_registry/sections/lora.py:130-137).  Every adapted Linear owns its own
+// nn.Dropout, so the members of one fused projection group (to_q / to_k / to_v share the input x) need INDEPENDENT masks.
+// Masks are never stored: they are a pure function of (seed, stream, element index) — a counter-based generator, the
+// murmur3 32-bit finaliser over a Weyl-sequenced counter — and are regenerated by the backward kernels:
+//     keep(seed, stream, idx) = u24(mix32(idx * 0x9E3779B1 + stream * 0x85EBCA77 + seed)) >= p * 2^24
+// `idx` = (b * S + s) * K + k on the LOGICAL [B, S, K] tensor.  (torch's own Philox stream is not reproduced: the
+// distribution is the same, the draws are not; parity tests replay this mask into the oracle.)
+//   dropout_expand : out[m, b, s, :] = bf16( x[b, s, :] * keep_m / (1 - p) )          m = 0 .. members-1
+//   dropout_accum  : dx[b, s, :]    += sum_m keep_m / (1 - p) * d[m, b, s, :]          (backward through the same masks)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t stream, unsigned long long idx, uint32_t thresh24) {
+  const uint32_t lo = uint32_t(idx), hi = uint32_t(idx >> 32);
+  const uint32_t h = mix32(lo * 0x9E3779B1u + mix32(hi + stream * 0x85EBCA77u + seed));
+  return (h >> 8) >= thresh24;
+}
+
+__global__ void __launch_bounds__(256)
+dropout_expand_kernel(const __nv_bfloat16* __restrict__ x, long long x_b, long long x_s, __nv_bfloat16* __restrict__ out,
+                      int members, int B, int S, int K, float inv_keep, uint32_t thresh24, uint32_t seed, uint32_t stream0) {
+  const int vec_per_row = K >> 3;
+  const long long total = (long long)B * S * vec_per_row;
+  const long long plane = (long long)B * S * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % vec_per_row) * 8;
+    const long long r = i / vec_per_row;
+    const int s = int(r % S);
+    const int b = int(r / S);
+    float xv[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + b * x_b + s * x_s + c), xv);
+    const unsigned long long idx0 = (unsigned long long)r * K + c;
+    for (int m = 0; m < members; ++m) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = dropout_keep(seed, stream0 + m, idx0 + j, thresh24) ? xv[j] * inv_keep : 0.f;
+      *reinterpret_cast<uint4*>(out + m * plane + r * K + c) = pack8(o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dropout_accum_kernel(const __nv_bfloat16* __restrict__ d, __nv_bfloat16* __restrict__ dx, long long dx_b, long long dx_s,
+                     int members, int B, int S, int K, float inv_keep, uint32_t thresh24, uint32_t seed, uint32_t stream0) {
+  const int vec_per_row = K >> 3;
+  const long long total = (long long)B * S * vec_per_row;
+  const long long plane = (long long)B * S * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % vec_per_row) * 8;
+    const long long r = i / vec_per_row;
+    const int s = int(r % S);
+    const int b = int(r / S);
+    float acc[8];
+    __nv_bfloat16* dst = dx + b * dx_b + s * dx_s + c;
+    unpack8(*reinterpret_cast<const uint4*>(dst), acc);
+    const unsigned long long idx0 = (unsigned long long)r * K + c;
+    for (int m = 0; m < members; ++m) {
+      float dv[8];
+      unpack8(*reinterpret_cast<const uint4*>(d + m * plane + r * K + c), dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (dropout_keep(seed, stream0 + m, idx0 + j, thresh24)) acc[j] += dv[j] * inv_keep;
+    }
+    *reinterpret_cast<uint4*>(dst) = pack8(acc);
+  }
+}
+
 // fp32 -> bf16 cast with optional transpose-free accumulate into an existing bf16 grad
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {

@@ -119,15 +119,48 @@ def pack_lora(params: List[Optional[Tuple[torch.Tensor, torch.Tensor]]], n_out: 
     return LoraPack(a_stack, _t(a_stack), b_ext, _t(b_ext), r, scaling, members, n_out, rp, row_index, col_index)
 
 
-def _lora_down(x: torch.Tensor, pack: LoraPack) -> torch.Tensor:
-    """T = x A_stack^T  [B, S, R]."""
-    return ops.gemm([x], [pack.a_stack])
+@dataclass
+class LoraDrop:
+    """PEFT `lora_dropout` state of one forward pass: probability, the step's seed and the first mask stream of the block
+    (every adapted Linear of the model owns one stream, so q / k / v of one fused group draw independent masks)."""
+    p: float
+    seed: int
+    stream: int = 0
+
+    def at(self, offset: int) -> "LoraDrop":
+        return LoraDrop(self.p, self.seed, self.stream + offset)
 
 
-def _lora_grads(pack: LoraPack, x: torch.Tensor, t_down: torch.Tensor, dy: torch.Tensor, t_up: torch.Tensor):
-    """dA_stack [R, K] = T'^T x  (T' = dy B_ext, scaling already inside);  dB_ext^T [R, N] = T^T dy."""
+def _member_slices(pack: LoraPack):
+    rp = pack.rank_padded or pack.rank
+    return [(m, slice(m * rp, (m + 1) * rp)) for m, idx in enumerate(pack.members) if idx is not None]
+
+
+def _lora_down(x: torch.Tensor, pack: LoraPack, drop: Optional[LoraDrop] = None) -> torch.Tensor:
+    """T = x A_stack^T  [B, S, R];  with dropout member m sees its own masked copy: T_m = (x o keep_m / (1 - p)) A_m^T."""
+    if drop is None:
+        return ops.gemm([x], [pack.a_stack])
+    B, S, _ = x.shape
+    xm = ops.dropout_expand(x, len(pack.members), drop.p, drop.seed, drop.stream)
+    t = torch.zeros((B, S, pack.a_stack.shape[0]), device=x.device, dtype=torch.bfloat16)
+    for m, sl in _member_slices(pack):
+        ops.gemm([xm[m]], [pack.a_stack[sl]], out=t[:, :, sl])
+    return t
+
+
+def _lora_grads(pack: LoraPack, x: torch.Tensor, t_down: torch.Tensor, dy: torch.Tensor, t_up: torch.Tensor,
+                drop: Optional[LoraDrop] = None):
+    """dA_stack [R, K] = T'^T x  (T' = dy B_ext, scaling already inside);  dB_ext^T [R, N] = T^T dy.
+    With dropout dA_m contracts T'_m with the SAME masked copy of x the forward used (masks regenerated, not stored)."""
     R = pack.a_stack.shape[0]
-    d_a = ops.skinny_tn(t_up, x)        # [R, K] fp32
+    if drop is None:
+        d_a = ops.skinny_tn(t_up, x)        # [R, K] fp32
+    else:
+        d_a = torch.zeros((R, x.shape[-1]), device=x.device, dtype=torch.float32)
+        xm = ops.dropout_expand(x, len(pack.members), drop.p, drop.seed, drop.stream)
+        for m, sl in _member_slices(pack):
+            ops.skinny_tn(t_up[:, :, sl], xm[m], out=d_a[sl])
+        del xm
     d_bt = ops.skinny_tn(t_down, dy)    # [R, N] fp32
     out = []
     r, rp = pack.rank, (pack.rank_padded or pack.rank)
@@ -148,23 +181,38 @@ def _lora_grads(pack: LoraPack, x: torch.Tensor, t_down: torch.Tensor, dy: torch
     return out
 
 
+def _lora_dgrad_dropout(dx: torch.Tensor, t_up: torch.Tensor, pack: LoraPack, drop: LoraDrop) -> None:
+    """dx += sum_m keep_m / (1 - p) o (T'_m A_m): the LoRA branch of the input gradient through the dropout masks."""
+    B, S, K = dx.shape
+    M = len(pack.members)
+    d = torch.zeros((M, B, S, K), device=dx.device, dtype=torch.bfloat16) if any(i is None for i in pack.members) \
+        else torch.empty((M, B, S, K), device=dx.device, dtype=torch.bfloat16)
+    for m, sl in _member_slices(pack):
+        ops.gemm([t_up[:, :, sl]], [pack.a_stack_t[:, sl]], out=d[m])
+    ops.dropout_accum_(dx, d, drop.p, drop.seed, drop.stream)
+
+
 # ------------------------------------------------------------------------------------------------
 # shared pieces
 # ------------------------------------------------------------------------------------------------
-def _linear_lora_fwd(x, w, b, pack: Optional[LoraPack], **kw):
+def _linear_lora_fwd(x, w, b, pack: Optional[LoraPack], drop: Optional[LoraDrop] = None, **kw):
     """y = x W^T + b (+ T B_ext^T as an extra K-segment).  Returns (y, T or None)."""
     if pack is None:
         return ops.gemm([x], [w], b, **kw), None
-    t = _lora_down(x, pack)
+    t = _lora_down(x, pack, drop)
     return ops.gemm([x, t], [w, pack.b_ext], b, **kw), t
 
 
-def _linear_lora_dgrad(dy, w_t, pack: Optional[LoraPack], **kw):
+def _linear_lora_dgrad(dy, w_t, pack: Optional[LoraPack], drop: Optional[LoraDrop] = None, **kw):
     """dx = dy W (+ (dy B_ext) A_stack).  Returns (dx, T' or None)."""
     if pack is None:
         return ops.gemm([dy], [w_t], None, **kw), None
     t_up = ops.gemm([dy], [pack.b_ext_t])
-    return ops.gemm([dy, t_up], [w_t, pack.a_stack_t], None, **kw), t_up
+    if drop is None:
+        return ops.gemm([dy, t_up], [w_t, pack.a_stack_t], None, **kw), t_up
+    dx = ops.gemm([dy], [w_t], None, **kw)
+    _lora_dgrad_dropout(dx, t_up, pack, drop)
+    return dx, t_up
 
 
 # ------------------------------------------------------------------------------------------------
@@ -232,6 +280,8 @@ class DoubleBlockFn(torch.autograd.Function):
         dual = st.get("dual", False)
         nan_txt = st.get("nan_to_num_txt", True)
         dev = h.device
+        drop: Optional[LoraDrop] = st.get("lora_drop")
+        dr = (lambda off: drop.at(off)) if drop is not None else (lambda off: None)
         lora = list(lora) + [None] * (24 - len(lora))
         streams = (("txt", slice(0, S_txt), mod_txt, 8), ("img", slice(S_txt, S), mod_img, 0))
 
@@ -256,7 +306,7 @@ class DoubleBlockFn(torch.autograd.Function):
             packs[name + "_out"] = lp(base + 6, 1, D, D) if ap.w_out is not None else None
             sh, sc = mod_shift_scale(name, mod)
             nh = ops.ln_modulate_fwd(h[:, sl], sh, sc, EPS)
-            _, t = _linear_lora_fwd(nh, ap.w_qkv, ap.b_qkv, packs[name + "_qkv"], out=qkv[:, sl])
+            _, t = _linear_lora_fwd(nh, ap.w_qkv, ap.b_qkv, packs[name + "_qkv"], dr(base), out=qkv[:, sl])
             small[name + "_t_qkv"] = t
         ia: AttnPlan = plans["img_attn"]
         ta: AttnPlan = plans["txt_attn"]
@@ -274,7 +324,7 @@ class DoubleBlockFn(torch.autograd.Function):
                 h2[:, sl].copy_(h[:, sl])
                 small[name + "_t_out"] = None
                 continue
-            _, t = _linear_lora_fwd(o[:, sl], ap.w_out, ap.b_out, packs[name + "_out"], out=h1[:, sl],
+            _, t = _linear_lora_fwd(o[:, sl], ap.w_out, ap.b_out, packs[name + "_out"], dr(base + 6), out=h1[:, sl],
                                     epi=ops.EPI_GATE_RES, gate=mod[:, 2 * D:3 * D], res=h[:, sl])
             small[name + "_t_out"] = t
         qkv2 = o2 = lse2 = None
@@ -284,7 +334,7 @@ class DoubleBlockFn(torch.autograd.Function):
             packs["a2_qkv"] = lp(16, 3, D, D)
             packs["a2_out"] = lp(22, 1, D, D)
             nh2a = ops.ln_modulate_fwd(h[:, isl], mod_img[:, 6 * D:7 * D], mod_img[:, 7 * D:8 * D], EPS)
-            qkv2, t = _linear_lora_fwd(nh2a, a2.w_qkv, a2.b_qkv, packs["a2_qkv"])
+            qkv2, t = _linear_lora_fwd(nh2a, a2.w_qkv, a2.b_qkv, packs["a2_qkv"], dr(16))
             del nh2a
             small["a2_t_qkv"] = t
             q2, k2 = _qk_fwd(qkv2, D, H, hd, a2, None, 0, None, None)
@@ -292,7 +342,7 @@ class DoubleBlockFn(torch.autograd.Function):
             del q2, k2
             o2 = o2.view(B, S - S_txt, D)
             # h1_img += gate_msa2 * to_out2(o2)   (in place: every element is read then written by one thread)
-            _, t = _linear_lora_fwd(o2, a2.w_out, a2.b_out, packs["a2_out"], out=h1[:, isl], epi=ops.EPI_GATE_RES,
+            _, t = _linear_lora_fwd(o2, a2.w_out, a2.b_out, packs["a2_out"], dr(22), out=h1[:, isl], epi=ops.EPI_GATE_RES,
                                     gate=mod_img[:, 8 * D:9 * D], res=h1[:, isl])
             small["a2_t_out"] = t
         mlp_pre = {}
@@ -333,6 +383,8 @@ class DoubleBlockFn(torch.autograd.Function):
         plans = st["plans"]
         pre_only = st.get("context_pre_only", False)
         dual = st.get("dual", False)
+        drop: Optional[LoraDrop] = st.get("lora_drop")
+        dr = (lambda off: drop.at(off)) if drop is not None else (lambda off: None)
         dh2 = dh2.contiguous()
         streams = (("txt", slice(0, S_txt), mod_txt, 8, pre_txt, t_qkv_txt, t_out_txt),
                    ("img", slice(S_txt, S), mod_img, 0, pre_img, t_qkv_img, t_out_img))
@@ -357,9 +409,9 @@ class DoubleBlockFn(torch.autograd.Function):
             # ---- attention output projection: h1 = h + gate_msa * to_out(o)
             g1 = ops.gate_mul(dh1[:, sl], mod[:, 2 * D:3 * D])
             pk = packs[name + "_out"]
-            _, t_up = _linear_lora_dgrad(g1, ap.w_out_t, pk, out=d_o[:, sl])
+            _, t_up = _linear_lora_dgrad(g1, ap.w_out_t, pk, dr(base + 6), out=d_o[:, sl])
             if pk is not None:
-                (da, db), = _lora_grads(pk, o[:, sl], t_out, g1, t_up)
+                (da, db), = _lora_grads(pk, o[:, sl], t_out, g1, t_up, dr(base + 6))
                 grads[base + 6], grads[base + 7] = da, db
             del g1
         # ---- image-only second attention (SD3.5 dual attention)
@@ -369,18 +421,18 @@ class DoubleBlockFn(torch.autograd.Function):
             a2: AttnPlan = plans["img_attn2"]
             g = ops.gate_mul(dh1[:, isl], mod_img[:, 8 * D:9 * D])
             pk = packs["a2_out"]
-            d_o2, t_up = _linear_lora_dgrad(g, a2.w_out_t, pk)
+            d_o2, t_up = _linear_lora_dgrad(g, a2.w_out_t, pk, dr(22))
             if pk is not None:
-                (da, db), = _lora_grads(pk, o2, t_out_a2, g, t_up)
+                (da, db), = _lora_grads(pk, o2, t_out_a2, g, t_up, dr(22))
                 grads[22], grads[23] = da, db
             del g
             d_qkv2 = _attn_core_bwd(qkv2, o2, d_o2, lse2, D, H, hd, a2, None, 0, None, None)
             del d_o2
             pk = packs["a2_qkv"]
-            d_nh2a, t_up = _linear_lora_dgrad(d_qkv2, a2.w_qkv_t, pk)
+            d_nh2a, t_up = _linear_lora_dgrad(d_qkv2, a2.w_qkv_t, pk, dr(16))
             if pk is not None:
                 nh2a = ops.ln_modulate_fwd(h[:, isl], mod_img[:, 6 * D:7 * D], mod_img[:, 7 * D:8 * D], EPS)
-                for m, (da, db) in enumerate(_lora_grads(pk, nh2a, t_qkv_a2, d_qkv2, t_up)):
+                for m, (da, db) in enumerate(_lora_grads(pk, nh2a, t_qkv_a2, d_qkv2, t_up, dr(16))):
                     grads[16 + 2 * m], grads[16 + 2 * m + 1] = da, db
                 del nh2a
             del d_qkv2
@@ -394,10 +446,10 @@ class DoubleBlockFn(torch.autograd.Function):
                 sh_, sc_ = mod[:, D:2 * D], mod[:, 0:D]
             else:
                 sh_, sc_ = mod[:, 0:D], mod[:, D:2 * D]
-            d_nh, t_up = _linear_lora_dgrad(d_qkv[:, sl], ap.w_qkv_t, pk)
+            d_nh, t_up = _linear_lora_dgrad(d_qkv[:, sl], ap.w_qkv_t, pk, dr(base))
             if pk is not None:
                 nh = ops.ln_modulate_fwd(h[:, sl], sh_, sc_, EPS)
-                for m, (da, db) in enumerate(_lora_grads(pk, nh, t_qkv, d_qkv[:, sl], t_up)):
+                for m, (da, db) in enumerate(_lora_grads(pk, nh, t_qkv, d_qkv[:, sl], t_up, dr(base))):
                     grads[base + 2 * m], grads[base + 2 * m + 1] = da, db
                 del nh
             ops.ln_modulate_bwd(d_nh, h[:, sl], sc_, add=dh1[:, sl], eps=EPS, out=dh[:, sl])
@@ -430,8 +482,9 @@ class SingleBlockFn(torch.autograd.Function):
             a, b = lora[2 * m], lora[2 * m + 1]
             ps.append(None if a is None else (a, b))
         pk = pack_lora(ps, D, D, st["lora_scaling"], dev)
+        drop: Optional[LoraDrop] = st.get("lora_drop")
         nh = ops.ln_modulate_fwd(h, mod[:, 0:D], mod[:, D:2 * D], EPS)
-        qkv, t_qkv = _linear_lora_fwd(nh, ap.w_qkv, ap.b_qkv, pk)
+        qkv, t_qkv = _linear_lora_fwd(nh, ap.w_qkv, ap.b_qkv, pk, drop)
         q, k = ops.qk_rmsnorm_rope_fwd(qkv, D, H, hd, ap.norm_q, ap.norm_k, None, None, 0, cos, sin, EPS)
         v = qkv[:, :, 2 * D:].unflatten(-1, (H, hd))
         o, lse = ops.attn_fwd(q, k, v)
@@ -471,10 +524,15 @@ class SingleBlockFn(torch.autograd.Function):
         if pk is None:
             d_nh = ops.gemm([d_pre, d_qkv], [mp.w1_t, ap.w_qkv_t], None)
         else:
+            drop: Optional[LoraDrop] = st.get("lora_drop")
             t_up = ops.gemm([d_qkv], [pk.b_ext_t])
-            d_nh = ops.gemm([d_pre, d_qkv, t_up], [mp.w1_t, ap.w_qkv_t, pk.a_stack_t], None)
+            if drop is None:
+                d_nh = ops.gemm([d_pre, d_qkv, t_up], [mp.w1_t, ap.w_qkv_t, pk.a_stack_t], None)
+            else:
+                d_nh = ops.gemm([d_pre, d_qkv], [mp.w1_t, ap.w_qkv_t], None)
+                _lora_dgrad_dropout(d_nh, t_up, pk, drop)
             nh = ops.ln_modulate_fwd(h, mod[:, 0:D], mod[:, D:2 * D], EPS)
-            for m, (da, db) in enumerate(_lora_grads(pk, nh, t_qkv, d_qkv, t_up)):
+            for m, (da, db) in enumerate(_lora_grads(pk, nh, t_qkv, d_qkv, t_up, drop)):
                 grads[2 * m], grads[2 * m + 1] = da, db
             del nh
         del d_pre, d_qkv

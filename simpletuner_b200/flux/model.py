@@ -69,12 +69,11 @@ class Flux:
     def add_lora_adapter(self):
         """common.py:1049-1117 for the Flux targets (flux/model.py:1235-1383)."""
         c = self.config
-        if getattr(c, "lora_dropout", 0.0):
-            raise NotImplementedError("lora_dropout > 0 is not supported by the fused LoRA path (pin --lora_dropout=0)")
         alpha = c.lora_alpha if c.lora_alpha is not None else c.lora_rank
         from .transformer import FLUX_LORA_TARGETS
         return self._denoiser().add_adapter(rank=c.lora_rank, lora_alpha=alpha,
-                                            target_modules=FLUX_LORA_TARGETS[c.flux_lora_target])
+                                            target_modules=FLUX_LORA_TARGETS[c.flux_lora_target],
+                                            lora_dropout=getattr(c, "lora_dropout", 0.0))
 
     # ------------------------------------------------------------------------------------------
     @classmethod

@@ -31,7 +31,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .blocks import AttnPlan, DoubleBlockFn, MlpPlan, SingleBlockFn, TailFn, _t
+from .blocks import AttnPlan, DoubleBlockFn, LoraDrop, MlpPlan, SingleBlockFn, TailFn, _t
 
 FLUX_LORA_TARGETS = {
     # reference flux/model.py:1235-1383 (names that exist un-fused)
@@ -178,7 +178,8 @@ class FluxTransformerBlock(nn.Module):
         D = self.dim
         mod_img = self.norm1.linear(silu_temb)
         mod_txt = self.norm1_context.linear(silu_temb)
-        st = {"S_txt": S_txt, "H": self.heads, "hd": self.head_dim, "plans": self.plans(), "lora_scaling": lora_scaling}
+        st = {"S_txt": S_txt, "H": self.heads, "hd": self.head_dim, "plans": self.plans(), "lora_scaling": lora_scaling,
+              "lora_drop": getattr(self, "_lora_drop", None)}
         a = self.attn
         lora = _lora_list([a.to_q, a.to_k, a.to_v, a.to_out[0], a.add_q_proj, a.add_k_proj, a.add_v_proj, a.to_add_out])
         return DoubleBlockFn.apply(h, mod_img, mod_txt, cos, sin, st, *lora)
@@ -208,7 +209,8 @@ class FluxSingleTransformerBlock(nn.Module):
 
     def forward(self, h, silu_temb, cos, sin, lora_scaling):
         mod = self.norm.linear(silu_temb)
-        st = {"H": self.heads, "hd": self.head_dim, "plans": self.plans(), "lora_scaling": lora_scaling}
+        st = {"H": self.heads, "hd": self.head_dim, "plans": self.plans(), "lora_scaling": lora_scaling,
+              "lora_drop": getattr(self, "_lora_drop", None)}
         a = self.attn
         return SingleBlockFn.apply(h, mod, cos, sin, st, *_lora_list([a.to_q, a.to_k, a.to_v]))
 
@@ -313,7 +315,31 @@ class AttnProcessorAPI:
         return None
 
 
-class FluxTransformer2DModel(AttnProcessorAPI, nn.Module):
+class LoraDropoutAPI:
+    """PEFT `lora_dropout` for the fused LoRA path (reference common.py:1094-1117; default 0.1,
+    field_registry/sections/lora.py:130-137).  Active only in training mode (`module.training`, like nn.Dropout).  One seed
+    is drawn per forward from torch's CPU default generator (no device sync; seeded runs are reproducible); every block gets
+    16 mask streams (one per adapted Linear), regenerated — not stored — by the backward kernels (csrc/elementwise.cuh)."""
+
+    _lora_dropout_p: float = 0.0
+    STREAMS_PER_BLOCK = 16
+
+    def _begin_lora_dropout(self, blocks) -> None:
+        p = float(getattr(self, "_lora_dropout_p", 0.0) or 0.0)
+        active = p > 0.0 and self.training and torch.is_grad_enabled()
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if active else 0
+        for i, blk in enumerate(blocks):
+            blk._lora_drop = LoraDrop(p, seed, i * self.STREAMS_PER_BLOCK) if active else None
+
+    @staticmethod
+    def _check_dropout_p(p) -> float:
+        p = float(p or 0.0)
+        if not 0.0 <= p < 1.0:
+            raise ValueError(f"lora_dropout must be in [0, 1), got {p}")
+        return p
+
+
+class FluxTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
     _no_split_modules = ["FluxTransformerBlock", "FluxSingleTransformerBlock"]
     _supports_gradient_checkpointing = True
 
@@ -399,10 +425,7 @@ class FluxTransformer2DModel(AttnProcessorAPI, nn.Module):
             lora_dropout = getattr(lora_config, "lora_dropout", lora_dropout)
         if rank is None:
             raise ValueError("LoRA rank is required")
-        if lora_dropout and lora_dropout > 0:
-            raise NotImplementedError(
-                "lora_dropout > 0 is not implemented in the fused LoRA epilogue yet (reference default 0.1, "
-                "sections/lora.py:130-137); parity runs pin --lora_dropout=0")
+        lora_dropout = self._check_dropout_p(lora_dropout)
         if not 1 <= rank <= 40:
             raise NotImplementedError("fused LoRA path supports rank 1..40 (three fused projections share a 128-wide rank block)")
         lora_alpha = float(lora_alpha) if lora_alpha is not None else float(rank)  # common.py:1090-1093
@@ -422,8 +445,9 @@ class FluxTransformer2DModel(AttnProcessorAPI, nn.Module):
         if n == 0:
             raise ValueError(f"no module matched LoRA targets {targets}")
         self._lora_scaling = lora_alpha / rank
+        self._lora_dropout_p = lora_dropout
         self.peft_config[adapter_name] = SimpleNamespace(r=rank, lora_alpha=lora_alpha, target_modules=targets,
-                                                         lora_dropout=0.0)
+                                                         lora_dropout=lora_dropout)
         return n
 
     def disable_lora(self):
@@ -503,6 +527,7 @@ class FluxTransformer2DModel(AttnProcessorAPI, nn.Module):
             img_ids = img_ids[0]
         cos, sin = self._rope(txt_ids, img_ids, dev)[:2]
         scaling = self._lora_scaling
+        self._begin_lora_dropout(list(self.transformer_blocks) + list(self.single_transformer_blocks))
         for i, blk in enumerate(self.transformer_blocks):
             h = self._run_block(i, blk, h, silu_temb, cos, sin, S_txt, scaling)
         for i, blk in enumerate(self.single_transformer_blocks):

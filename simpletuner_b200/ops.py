@@ -322,6 +322,26 @@ def gate_mul(x, gate, out=None):
     return out
 
 
+def dropout_expand(x, members: int, p: float, seed: int, stream0: int):
+    """x [B, S, K] (view) -> [members, B, S, K]: x * keep_m / (1 - p) with an independent counter-based mask per member."""
+    _chk(x, "x")
+    B, S, K = x.shape
+    out = torch.empty((members, B, S, K), device=x.device, dtype=torch.bfloat16)
+    check(_lib.lib().stb_dropout_expand(x.data_ptr(), x.stride(0), x.stride(1), out.data_ptr(), members, B, S, K, float(p),
+                                        int(seed) & 0xFFFFFFFF, int(stream0) & 0xFFFFFFFF, _stream()))
+    return out
+
+
+def dropout_accum_(dx, d, p: float, seed: int, stream0: int):
+    """dx [B, S, K] (view, in place) += sum_m keep_m / (1 - p) * d[m]; d [members, B, S, K] contiguous."""
+    _chk(dx, "dx"); _chk(d, "d")
+    assert d.is_contiguous() and d.dim() == 4 and tuple(d.shape[1:]) == tuple(dx.shape)
+    members, B, S, K = d.shape
+    check(_lib.lib().stb_dropout_accum(d.data_ptr(), dx.data_ptr(), dx.stride(0), dx.stride(1), members, B, S, K, float(p),
+                                       int(seed) & 0xFFFFFFFF, int(stream0) & 0xFFFFFFFF, _stream()))
+    return dx
+
+
 def skinny_tn(L, Rm, alpha: float = 1.0, out: Optional[torch.Tensor] = None):
     """out[r, n] += alpha * sum_m L[m, r] * Rm[m, n].  L [B,S,R] or [M,R]; Rm [B,S,N] or [M,N]; out fp32."""
     L3, R3 = _as3d(L), _as3d(Rm)

@@ -78,10 +78,9 @@ class PixartSigma(Flux):
 
     def add_lora_adapter(self):
         c = self.config
-        if getattr(c, "lora_dropout", 0.0):
-            raise NotImplementedError("lora_dropout > 0 is not supported by the fused LoRA path (pin --lora_dropout=0)")
         alpha = c.lora_alpha if c.lora_alpha is not None else c.lora_rank
-        return self._denoiser().add_adapter(rank=c.lora_rank, lora_alpha=alpha, target_modules=PIXART_LORA_TARGETS)
+        return self._denoiser().add_adapter(rank=c.lora_rank, lora_alpha=alpha, target_modules=PIXART_LORA_TARGETS,
+                                            lora_dropout=getattr(c, "lora_dropout", 0.0))
 
     def _coefs(self, timesteps: torch.Tensor, dev):
         tab = self._sched_dev.get(dev)

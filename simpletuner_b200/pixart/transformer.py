@@ -33,7 +33,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..flux.blocks import EPS, MlpPlan, TailFn, _linear_lora_dgrad, _linear_lora_fwd, _lora_grads, _t, pack_lora
-from ..flux.transformer import AttnProcessorAPI, Linear, _FeedForward, _lora_list, _sinusoid, _TimestepEmbedding
+from ..flux.transformer import AttnProcessorAPI, LoraDropoutAPI, Linear, _FeedForward, _lora_list, _sinusoid, _TimestepEmbedding
 
 PIXART_LORA_TARGETS = ["to_k", "to_q", "to_v", "to_out.0"]  # PixartSigma.DEFAULT_LORA_TARGET, reference pixart/model.py:59
 MASK_BIAS = -10000.0
@@ -81,6 +81,8 @@ class PixArtBlockFn(torch.autograd.Function):
         scaling, scale = st["lora_scaling"], hd ** -0.5
         ridx = st["pad_index"]
         dev = h.device
+        drop = st.get("lora_drop")
+        dr = (lambda off: drop.at(off)) if drop is not None else (lambda off: None)
 
         def lp(base, n, n_out, k_in, rows):
             ps = []
@@ -93,23 +95,23 @@ class PixArtBlockFn(torch.autograd.Function):
               "kv2": lp(10, 2, Hp, enc.shape[2], True), "out2": lp(14, 1, D, Hp, False)}
         # ---- self attention
         nh = ops.ln_modulate_fwd(h, mod[:, 0:D], mod[:, D:2 * D], EPS)
-        qkv, t_qkv = _linear_lora_fwd(nh, pl["w_qkv1"], pl["b_qkv1"], pk["qkv1"])
+        qkv, t_qkv = _linear_lora_fwd(nh, pl["w_qkv1"], pl["b_qkv1"], pk["qkv1"], dr(0))
         del nh
         q5 = qkv.view(B, S, 3, H, hdp)
         o, lse = ops.attn_fwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], scale=scale)
         o = o.view(B, S, Hp)
-        h1, t_out1 = _linear_lora_fwd(o, pl["w_out1"], pl["b_out1"], pk["out1"], epi=ops.EPI_GATE_RES,
+        h1, t_out1 = _linear_lora_fwd(o, pl["w_out1"], pl["b_out1"], pk["out1"], dr(3), epi=ops.EPI_GATE_RES,
                                       gate=mod[:, 2 * D:3 * D], res=h)
         # ---- cross attention on the un-normed stream (ada_norm_single: no norm2 before attn2)
-        q2, t_q2 = _linear_lora_fwd(h1, pl["w_q2"], pl["b_q2"], pk["q2"])
-        kv2, t_kv2 = _linear_lora_fwd(enc, pl["w_kv2"], pl["b_kv2"], pk["kv2"])
+        q2, t_q2 = _linear_lora_fwd(h1, pl["w_q2"], pl["b_q2"], pk["q2"], dr(4))
+        kv2, t_kv2 = _linear_lora_fwd(enc, pl["w_kv2"], pl["b_kv2"], pk["kv2"], dr(5))
         St = enc.shape[1]
         kv5 = kv2.view(B, St, 2, H, hdp)
         if kbias is not None:
             kv5[:, :, 0, :, hd] = kbias[:, :, None]          # mask column (see module docstring)
         o2, lse2 = ops.attn_fwd(q2.view(B, S, H, hdp), kv5[:, :, 0], kv5[:, :, 1], scale=scale)
         o2 = o2.view(B, S, Hp)
-        h2, t_out2 = _linear_lora_fwd(o2, pl["w_out2"], pl["b_out2"], pk["out2"], epi=ops.EPI_ADD_RES, res=h1)
+        h2, t_out2 = _linear_lora_fwd(o2, pl["w_out2"], pl["b_out2"], pk["out2"], dr(7), epi=ops.EPI_ADD_RES, res=h1)
         # ---- feed forward
         mp: MlpPlan = pl["mlp"]
         nh2 = ops.ln_modulate_fwd(h2, mod[:, 3 * D:4 * D], mod[:, 4 * D:5 * D], EPS)
@@ -138,6 +140,8 @@ class PixArtBlockFn(torch.autograd.Function):
         mp: MlpPlan = pl["mlp"]
         scale = hd ** -0.5
         grads: List[Optional[torch.Tensor]] = [None] * 16
+        drop = st.get("lora_drop")
+        dr = (lambda off: drop.at(off)) if drop is not None else (lambda off: None)
         dh3 = dh3.contiguous()
         # ---- feed forward: h3 = h2 + gate_mlp * fc2(gelu(fc1(LNmod(h2))))
         g = ops.gate_mul(dh3, mod[:, 5 * D:6 * D])
@@ -148,9 +152,9 @@ class PixArtBlockFn(torch.autograd.Function):
         dh2 = ops.ln_modulate_bwd(d_nh2, h2, mod[:, 4 * D:5 * D], add=dh3, eps=EPS)
         del d_nh2
         # ---- cross attention: h2 = h1 + to_out2(attn(q2(h1), kv2(ctx)))
-        d_o2, t_up = _linear_lora_dgrad(dh2, pl["w_out2_t"], pk["out2"])
+        d_o2, t_up = _linear_lora_dgrad(dh2, pl["w_out2_t"], pk["out2"], dr(7))
         if pk["out2"] is not None:
-            (grads[14], grads[15]), = _lora_grads(pk["out2"], o2, t_out2, dh2, t_up)
+            (grads[14], grads[15]), = _lora_grads(pk["out2"], o2, t_out2, dh2, t_up, dr(7))
         kv5 = kv2.view(B, St, 2, H, hdp)
         d_q2 = torch.empty_like(q2)
         d_kv2 = torch.empty_like(kv2)
@@ -158,20 +162,20 @@ class PixArtBlockFn(torch.autograd.Function):
         ops.attn_bwd(q2.view(B, S, H, hdp), kv5[:, :, 0], kv5[:, :, 1], o2.view(B, S, H, hdp), d_o2.view(B, S, H, hdp), lse2,
                      scale=scale, dq=d_q2.view(B, S, H, hdp), dk=dkv5[:, :, 0], dv=dkv5[:, :, 1])
         del d_o2
-        dh1, t_up = _linear_lora_dgrad(d_q2, pl["w_q2_t"], pk["q2"], epi=ops.EPI_ADD_RES, res=dh2)
+        dh1, t_up = _linear_lora_dgrad(d_q2, pl["w_q2_t"], pk["q2"], dr(4), epi=ops.EPI_ADD_RES, res=dh2)
         if pk["q2"] is not None:
-            (grads[8], grads[9]), = _lora_grads(pk["q2"], h1, t_q2, d_q2, t_up)
+            (grads[8], grads[9]), = _lora_grads(pk["q2"], h1, t_q2, d_q2, t_up, dr(4))
         del d_q2
         if pk["kv2"] is not None:   # no d ctx: the caption projection is frozen and carries no adapter
             t_up = ops.gemm([d_kv2], [pk["kv2"].b_ext_t])
-            for m, (da, db) in enumerate(_lora_grads(pk["kv2"], enc, t_kv2, d_kv2, t_up)):
+            for m, (da, db) in enumerate(_lora_grads(pk["kv2"], enc, t_kv2, d_kv2, t_up, dr(5))):
                 grads[10 + 2 * m], grads[11 + 2 * m] = da, db
         del d_kv2
         # ---- self attention: h1 = h + gate_msa * to_out1(attn(qkv(LNmod(h))))
         g1 = ops.gate_mul(dh1, mod[:, 2 * D:3 * D])
-        d_o, t_up = _linear_lora_dgrad(g1, pl["w_out1_t"], pk["out1"])
+        d_o, t_up = _linear_lora_dgrad(g1, pl["w_out1_t"], pk["out1"], dr(3))
         if pk["out1"] is not None:
-            (grads[6], grads[7]), = _lora_grads(pk["out1"], o, t_out1, g1, t_up)
+            (grads[6], grads[7]), = _lora_grads(pk["out1"], o, t_out1, g1, t_up, dr(3))
         del g1
         q5 = qkv.view(B, S, 3, H, hdp)
         d_qkv = torch.empty_like(qkv)
@@ -179,10 +183,10 @@ class PixArtBlockFn(torch.autograd.Function):
         ops.attn_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], o.view(B, S, H, hdp), d_o.view(B, S, H, hdp), lse, scale=scale,
                      dq=dq5[:, :, 0], dk=dq5[:, :, 1], dv=dq5[:, :, 2])
         del d_o
-        d_nh, t_up = _linear_lora_dgrad(d_qkv, pl["w_qkv1_t"], pk["qkv1"])
+        d_nh, t_up = _linear_lora_dgrad(d_qkv, pl["w_qkv1_t"], pk["qkv1"], dr(0))
         if pk["qkv1"] is not None:
             nh = ops.ln_modulate_fwd(h, mod[:, 0:D], mod[:, D:2 * D], EPS)
-            for m, (da, db) in enumerate(_lora_grads(pk["qkv1"], nh, t_qkv, d_qkv, t_up)):
+            for m, (da, db) in enumerate(_lora_grads(pk["qkv1"], nh, t_qkv, d_qkv, t_up, dr(0))):
                 grads[2 * m], grads[2 * m + 1] = da, db
             del nh
         del d_qkv
@@ -235,7 +239,7 @@ class PixArtTransformerBlock(nn.Module):
         # reference :98-102 / diffusers: (scale_shift_table[None] + timestep.reshape(B, 6, -1)) in the weight dtype
         mod = (self.scale_shift_table[None] + t6.reshape(B, 6, D)).reshape(B, 6 * D)
         st = {"H": self.heads, "hd": self.head_dim, "hdp": self.hdp, "plans": self.plans(), "lora_scaling": lora_scaling,
-              "pad_index": pad_index}
+              "pad_index": pad_index, "lora_drop": getattr(self, "_lora_drop", None)}
         a1, a2 = self.attn1, self.attn2
         lora = _lora_list([a1.to_q, a1.to_k, a1.to_v, a1.to_out[0], a2.to_q, a2.to_k, a2.to_v, a2.to_out[0]])
         return PixArtBlockFn.apply(h, ctx, kbias, mod, st, *lora)
@@ -299,7 +303,7 @@ def sincos_pos_embed_2d(dim: int, grid_h: int, grid_w: int, base_size: int, inte
     return torch.cat(parts, dim=1).float().to(device)
 
 
-class PixArtTransformer2DModel(AttnProcessorAPI, nn.Module):
+class PixArtTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
     _no_split_modules = ["BasicTransformerBlock", "PatchEmbed"]
 
     def __init__(self, num_attention_heads: int = 16, attention_head_dim: int = 72, in_channels: int = 4,
@@ -388,8 +392,7 @@ class PixArtTransformer2DModel(AttnProcessorAPI, nn.Module):
             lora_alpha = getattr(lora_config, "lora_alpha", lora_alpha)
             target_modules = getattr(lora_config, "target_modules", target_modules)
             lora_dropout = getattr(lora_config, "lora_dropout", lora_dropout)
-        if lora_dropout and lora_dropout > 0:
-            raise NotImplementedError("lora_dropout > 0 is not implemented in the fused LoRA path (pin --lora_dropout=0)")
+        lora_dropout = self._check_dropout_p(lora_dropout)
         if not 1 <= rank <= 40:
             raise NotImplementedError("fused LoRA path supports rank 1..40 (three fused projections share a 128-wide rank block)")
         lora_alpha = float(lora_alpha) if lora_alpha is not None else float(rank)
@@ -408,7 +411,8 @@ class PixArtTransformer2DModel(AttnProcessorAPI, nn.Module):
         if n == 0:
             raise ValueError(f"no module matched LoRA targets {targets}")
         self._lora_scaling = lora_alpha / rank
-        self.peft_config[adapter_name] = SimpleNamespace(r=rank, lora_alpha=lora_alpha, target_modules=targets, lora_dropout=0.0)
+        self._lora_dropout_p = lora_dropout
+        self.peft_config[adapter_name] = SimpleNamespace(r=rank, lora_alpha=lora_alpha, target_modules=targets, lora_dropout=lora_dropout)
         return n
 
     def disable_lora(self):
@@ -493,6 +497,7 @@ class PixArtTransformer2DModel(AttnProcessorAPI, nn.Module):
                 kbias = (bias.float() / hd ** -0.5).to(dt).contiguous()
         if self._pad_index is None and hdp != hd:
             self._pad_index = (torch.arange(H, device=dev)[:, None] * hdp + torch.arange(hd, device=dev)[None, :]).reshape(-1)
+        self._begin_lora_dropout(list(self.transformer_blocks))
         for blk in self.transformer_blocks:
             h = self._run_block(blk, h, ctx, kbias, t6, self._lora_scaling, self._pad_index)
         # 3. output: LN -> (scale_shift_table + embedded) modulate -> proj_out  (reference :749-760)

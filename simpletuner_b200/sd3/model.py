@@ -32,10 +32,9 @@ class SD3(Flux):
 
     def add_lora_adapter(self):
         c = self.config
-        if getattr(c, "lora_dropout", 0.0):
-            raise NotImplementedError("lora_dropout > 0 is not supported by the fused LoRA path (pin --lora_dropout=0)")
         alpha = c.lora_alpha if c.lora_alpha is not None else c.lora_rank
-        return self._denoiser().add_adapter(rank=c.lora_rank, lora_alpha=alpha, target_modules=SD3_LORA_TARGETS)
+        return self._denoiser().add_adapter(rank=c.lora_rank, lora_alpha=alpha, target_modules=SD3_LORA_TARGETS,
+                                            lora_dropout=getattr(c, "lora_dropout", 0.0))
 
     def model_predict(self, prepared_batch: Dict[str, Any]) -> Dict[str, Any]:
         pb = prepared_batch

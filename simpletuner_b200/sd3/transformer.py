@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..flux.blocks import AttnPlan, DoubleBlockFn, MlpPlan, TailFn, _t
-from ..flux.transformer import AttnProcessorAPI, Linear, RMSNormWeight, _AdaNorm, _FeedForward, _TimestepEmbedding, _attn_plan, _lora_list, _sinusoid
+from ..flux.transformer import AttnProcessorAPI, LoraDropoutAPI, Linear, RMSNormWeight, _AdaNorm, _FeedForward, _TimestepEmbedding, _attn_plan, _lora_list, _sinusoid
 
 SD3_LORA_TARGETS = ["to_k", "to_q", "to_v", "to_out.0"]  # SD3.DEFAULT_LORA_TARGET, reference sd3/model.py:122
 
@@ -106,7 +106,7 @@ class JointTransformerBlock(nn.Module):
         mod_txt = self.norm1_context.linear(silu_temb)
         st = {"S_txt": S_txt, "H": self.heads, "hd": self.head_dim, "plans": self.plans(), "lora_scaling": lora_scaling,
               "nan_to_num_txt": False, "context_pre_only": self.context_pre_only, "dual": self.use_dual_attention,
-              "_n_lora": 24}
+              "_n_lora": 24, "lora_drop": getattr(self, "_lora_drop", None)}
         a = self.attn
         lins = [a.to_q, a.to_k, a.to_v, a.to_out[0], a.add_q_proj, a.add_k_proj, a.add_v_proj]
         lora = _lora_list(lins)
@@ -139,7 +139,7 @@ class _TimeTextEmbed(nn.Module):
         self.text_embedder = _TimestepEmbedding(pooled_dim, dim, dtype)
 
 
-class SD3Transformer2DModel(AttnProcessorAPI, nn.Module):
+class SD3Transformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
     _no_split_modules = ["JointTransformerBlock"]
 
     def __init__(self, sample_size: int = 128, patch_size: int = 2, in_channels: int = 16, num_layers: int = 18,
@@ -217,8 +217,7 @@ class SD3Transformer2DModel(AttnProcessorAPI, nn.Module):
             lora_alpha = getattr(lora_config, "lora_alpha", lora_alpha)
             target_modules = getattr(lora_config, "target_modules", target_modules)
             lora_dropout = getattr(lora_config, "lora_dropout", lora_dropout)
-        if lora_dropout and lora_dropout > 0:
-            raise NotImplementedError("lora_dropout > 0 is not implemented in the fused LoRA path (pin --lora_dropout=0)")
+        lora_dropout = self._check_dropout_p(lora_dropout)
         if not 1 <= rank <= 40:
             raise NotImplementedError("fused LoRA path supports rank 1..40 (three fused projections share a 128-wide rank block)")
         lora_alpha = float(lora_alpha) if lora_alpha is not None else float(rank)
@@ -238,7 +237,8 @@ class SD3Transformer2DModel(AttnProcessorAPI, nn.Module):
         if n == 0:
             raise ValueError(f"no module matched LoRA targets {targets}")
         self._lora_scaling = lora_alpha / rank
-        self.peft_config[adapter_name] = SimpleNamespace(r=rank, lora_alpha=lora_alpha, target_modules=targets, lora_dropout=0.0)
+        self._lora_dropout_p = lora_dropout
+        self.peft_config[adapter_name] = SimpleNamespace(r=rank, lora_alpha=lora_alpha, target_modules=targets, lora_dropout=lora_dropout)
         return n
 
     def disable_lora(self):
@@ -301,6 +301,7 @@ class SD3Transformer2DModel(AttnProcessorAPI, nn.Module):
         tte = self.time_text_embed
         temb = tte.timestep_embedder(_sinusoid(timestep.to(dev).float()).to(dt)) + tte.text_embedder(pooled_projections.to(dt).contiguous())
         silu_temb = F.silu(temb).contiguous()
+        self._begin_lora_dropout(list(self.transformer_blocks))
         for blk in self.transformer_blocks:
             h = self._run_block(blk, h, silu_temb, S_txt, self._lora_scaling)
         if self._tail_plan is None:
