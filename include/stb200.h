@@ -225,6 +225,19 @@ int stb_dropout_accum(const void* d, void* dx, long long dx_b, long long dx_s, i
                       unsigned int seed, unsigned int stream0, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Full-rank weight gradient (full fine-tune, BASELINE config 3; autograd of nn.Linear.weight under
+ * `accelerator.backward`, reference trainer.py:7126, sd3/transformer.py:145-241):
+ *   dW[n, k] = alpha * sum_{b,s} dY[b, s, n] * X[b, s, k]  (+ dW[n, k] if accumulate)     bf16 [N, K], row stride dw_row_stride
+ * dY [B, S, N] / X [B, S, K] bf16 views (last dim contiguous; strides in elements, multiples of 8); N, K multiples of 8.
+ *
+ * stb_colsum2: per-(batch, column) token reductions for the adaLN / gate / bias gradients:
+ *   sum[b, d] = sum_s dy[b, s, d];   dot[b, d] = sum_s dy[b, s, d] * z[b, s, d]     fp32 [B, D], either may be NULL. */
+int stb_wgrad_full(const void* dy, long long dy_b, long long dy_s, const void* x, long long x_b, long long x_s, void* dw,
+                   long long dw_row_stride, int B, int S, int N, int K, float alpha, int accumulate, void* stream);
+int stb_colsum2(const void* dy, long long dy_b, long long dy_s, const void* z, long long z_b, long long z_s, float* sum,
+                float* dot, int B, int S, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * LoRA weight gradients: out[r, n] += alpha * sum_m L[m, r] * Rm[m, n]   (fp32 out, R in 16..64)
  *   dA = s * (dY B)^T X   (L = dY B [M, r], Rm = X  [M, K])
  *   dB^T = s * (X A^T)^T dY (L = X A^T [M, r], Rm = dY [M, N])

@@ -138,6 +138,8 @@ SYMBOLS = {
     "stb_gate_mul": (_I, [_P, _LL, _LL, _P, _LL, _P, _LL, _LL, _I, _I, _I, _P]),
     "stb_dropout_expand": (_I, [_P, _LL, _LL, _P, _I, _I, _I, _I, _F, C.c_uint, C.c_uint, _P]),
     "stb_dropout_accum": (_I, [_P, _P, _LL, _LL, _I, _I, _I, _I, _F, C.c_uint, C.c_uint, _P]),
+    "stb_wgrad_full": (_I, [_P, _LL, _LL, _P, _LL, _LL, _P, _LL, _I, _I, _I, _I, _F, _I, _P]),
+    "stb_colsum2": (_I, [_P, _LL, _LL, _P, _LL, _LL, _P, _P, _I, _I, _I, _P]),
     "stb_skinny_tn": (_I, [_P, _LL, _LL, _P, _LL, _LL, _P, _I, _I, _I, _I, _F, _P]),
     "stb_conv3x3_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "stb_conv_in_3ch": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),

@@ -23,6 +23,7 @@
 #include "optim.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "wgrad_full.cuh"
 #include "vae.cuh"
 #include "wgrad.cuh"
 
@@ -746,6 +747,70 @@ int stb_dropout_accum(const void* d, void* dx, long long dx_b, long long dx_s, i
   stb::dropout_accum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(d), static_cast<__nv_bfloat16*>(dx), dx_b, dx_s, members, B, S, K, 1.f / (1.f - p), thresh, seed, stream0);
   STB_LAUNCH_CHECK("dropout_accum");
+  return 0;
+}
+
+int stb_wgrad_full(const void* dy, long long dy_b, long long dy_s, const void* x, long long x_b, long long x_s, void* dw,
+                   long long dw_row_stride, int B, int S, int N, int K, float alpha, int accumulate, void* stream) {
+  if (int r = check_device()) return r;
+  if (!dy || !x || !dw || B < 1 || S < 1 || N < 8 || K < 8 || (N & 7) || (K & 7)) return fail(STB_ERR_ARG, "wgrad_full: N, K must be positive multiples of 8");
+  if (!aligned16(dw) || (dw_row_stride & 7)) return fail(STB_ERR_ARG, "wgrad_full: dW must be 16-byte aligned with a row stride multiple of 8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  stb::WgradFullMaps maps;
+  unsigned bx[3] = {64, 64, 1};
+  {
+    unsigned long long d[3] = {(unsigned long long)N, (unsigned long long)S, (unsigned long long)B};
+    unsigned long long sb[2] = {(unsigned long long)dy_s * 2ull, (unsigned long long)(B == 1 ? dy_s * (long long)S : dy_b) * 2ull};
+    if (int r = make_map(&maps.dy, dy, 3, d, sb, bx)) return r;
+  }
+  {
+    unsigned long long d[3] = {(unsigned long long)K, (unsigned long long)S, (unsigned long long)B};
+    unsigned long long sb[2] = {(unsigned long long)x_s * 2ull, (unsigned long long)(B == 1 ? x_s * (long long)S : x_b) * 2ull};
+    if (int r = make_map(&maps.x, x, 3, d, sb, bx)) return r;
+  }
+  stb::WgradFullParams p;
+  p.S = S; p.B = B; p.N = N; p.K = K;
+  p.alpha = alpha;
+  p.accumulate = accumulate;
+  p.out = static_cast<__nv_bfloat16*>(dw);
+  p.out_row_stride = dw_row_stride;
+  const int tiles_n = (N + 127) / 128;
+  const int sms = num_sms();
+  // 256-wide tiles unless they leave more than half of the SMs idle
+  const bool wide = tiles_n * ((K + 255) / 256) >= sms / 2 || K <= 128;
+  if (wide) {
+    auto kern = stb::wgrad_full_kernel<256>;
+    constexpr int SMEM = stb::WgradFullCfg<256>::SMEM_BYTES;
+    static bool configured = false;
+    if (!configured) { if (int r = set_smem(kern, SMEM)) return r; configured = true; }
+    const int tiles = tiles_n * ((K + 255) / 256);
+    kern<<<std::min(tiles, sms), 256, SMEM, st>>>(maps, p);
+  } else {
+    auto kern = stb::wgrad_full_kernel<128>;
+    constexpr int SMEM = stb::WgradFullCfg<128>::SMEM_BYTES;
+    static bool configured = false;
+    if (!configured) { if (int r = set_smem(kern, SMEM)) return r; configured = true; }
+    const int tiles = tiles_n * ((K + 127) / 128);
+    kern<<<std::min(tiles, sms), 256, SMEM, st>>>(maps, p);
+  }
+  STB_LAUNCH_CHECK("wgrad_full");
+  return 0;
+}
+
+int stb_colsum2(const void* dy, long long dy_b, long long dy_s, const void* z, long long z_b, long long z_s, float* sum,
+                float* dot, int B, int S, int D, void* stream) {
+  if (int r = check_device()) return r;
+  if (!dy || (!sum && !dot) || B < 1 || S < 1 || D < 8 || (D & 7)) return fail(STB_ERR_ARG, "colsum2: bad arguments (D multiple of 8)");
+  if (dot && !z) return fail(STB_ERR_ARG, "colsum2: dot needs z");
+  if (!aligned16(dy) || (dy_b & 7) || (dy_s & 7) || (z && (!aligned16(z) || (z_b & 7) || (z_s & 7))))
+    return fail(STB_ERR_ARG, "colsum2: operands must be 16-byte aligned with strides multiple of 8");
+  const int vecs = D >> 3;
+  const int gx = (vecs + 255) / 256;
+  int rows = std::max(8, (int)(((long long)S * B * gx + 148LL * 8 - 1) / (148LL * 8)));
+  dim3 grid(gx, (S + rows - 1) / rows, B);
+  stb::colsum2_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), dy_b, dy_s, static_cast<const __nv_bfloat16*>(z), z_b, z_s, sum, dot, B, S, D, rows);
+  STB_LAUNCH_CHECK("colsum2");
   return 0;
 }
 

@@ -24,7 +24,7 @@ namespace stb {
 enum GemmEpi : int {
   EPI_STORE = 0,        // D = acc + bias
   EPI_GELU = 1,         // D = gelu_tanh(acc + bias); aux (optional) = acc + bias (pre-activation)
-  EPI_GATE_RES = 2,     // D = res + gate[b, n] * (acc + bias); optional nan_to_num
+  EPI_GATE_RES = 2,     // D = res + gate[b, n] * (acc + bias); optional nan_to_num; aux (optional) = acc + bias
   EPI_MUL_DGELU = 3,    // D = acc * gelu_tanh'(aux)          (dgrad through the activation)
   EPI_ADD_RES = 4,      // D = acc + bias + res                (gradient accumulation)
 };
@@ -45,7 +45,7 @@ struct GemmParams {
   long long gate_batch_stride;
   const __nv_bfloat16* res;
   long long res_batch_stride, res_row_stride;
-  __nv_bfloat16* aux;  // EPI_GELU: written; EPI_MUL_DGELU: read
+  __nv_bfloat16* aux;  // EPI_GELU / EPI_GATE_RES: written (optional); EPI_MUL_DGELU: read
   long long aux_batch_stride, aux_row_stride;
   // CONV mode (3x3 NHWC implicit GEMM): a "batch" is one output image row, a "row" an output pixel x.
   // maps.a[0] is then a 4-D map (c, x, y, img) with box (64, 128, 1, 1) and x element-stride = conv_stride;
@@ -399,6 +399,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
               }
               // reference order: bias -> (bf16 linear output) -> gate * y -> residual + (...)
               // (flux/transformer.py:464-465, 584-586, 652-653); each step is a bf16 tensor there.
+              if (xrow) {   // full fine-tune: keep the (bf16) linear output — the gate gradient is sum_s dOut * y
+                if (full) {
+                  uint4* xp = reinterpret_cast<uint4*>(xrow + n);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    uint4 u;
+                    u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                    u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                    u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                    u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                    xp[q] = u;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (n + j < p.N) xrow[n + j] = __float2bfloat16(f[j]);
+                }
+              }
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float y = __bfloat162float(__float2bfloat16(f[j]));

@@ -80,7 +80,10 @@ class Linear(nn.Module):
             return None, None
         return self.lora_A[adapter_name].weight, self.lora_B[adapter_name].weight
 
-    def forward(self, x):  # small-M helper path (embedders / conditioning MLPs)
+    def forward(self, x):  # small-M helper path (embedders / conditioning MLPs on [B, D] vectors)
+        if self.weight.requires_grad and torch.is_grad_enabled():
+            # full fine-tune: the conditioning path trains through plain torch autograd (< 0.1 % of the step's work)
+            return F.linear(x, self.weight, self.bias)
         return ops.gemm([x.contiguous()], [self.weight], self.bias)
 
 

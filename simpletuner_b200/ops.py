@@ -342,6 +342,41 @@ def dropout_accum_(dx, d, p: float, seed: int, stream0: int):
     return dx
 
 
+def wgrad_full(dy, x, out: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False):
+    """dW [N, K] bf16 = alpha * sum over tokens dy[..., n] * x[..., k] (+ out if accumulate).  dy [B,S,N] / x [B,S,K] views."""
+    d3, x3 = _as3d(dy), _as3d(x)
+    _chk(d3, "dy"); _chk(x3, "x")
+    B, S, N = d3.shape
+    K = x3.shape[2]
+    assert x3.shape[0] == B and x3.shape[1] == S
+    if out is None:
+        assert not accumulate
+        out = torch.empty((N, K), device=dy.device, dtype=torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and out.shape == (N, K) and out.stride(1) == 1
+    check(_lib.lib().stb_wgrad_full(d3.data_ptr(), d3.stride(0), d3.stride(1), x3.data_ptr(), x3.stride(0), x3.stride(1),
+                                    out.data_ptr(), out.stride(0), B, S, N, K, float(alpha), int(accumulate), _stream()))
+    return out
+
+
+def colsum2(dy, z=None, want_sum: bool = True):
+    """(sum [B, D] or None, dot [B, D] or None) in fp32: sum_s dy, sum_s dy * z."""
+    d3 = _as3d(dy)
+    _chk(d3, "dy")
+    B, S, D = d3.shape
+    sm = torch.zeros((B, D), device=dy.device, dtype=torch.float32) if want_sum else None
+    dt = None
+    zb = zs = 0
+    if z is not None:
+        z3 = _as3d(z)
+        _chk(z3, "z")
+        assert z3.shape == d3.shape
+        dt = torch.zeros((B, D), device=dy.device, dtype=torch.float32)
+        zb, zs = z3.stride(0), z3.stride(1)
+    check(_lib.lib().stb_colsum2(d3.data_ptr(), d3.stride(0), d3.stride(1), _ptr(z3) if z is not None else None, zb, zs,
+                                 _ptr(sm), _ptr(dt), B, S, D, _stream()))
+    return sm, dt
+
+
 def skinny_tn(L, Rm, alpha: float = 1.0, out: Optional[torch.Tensor] = None):
     """out[r, n] += alpha * sum_m L[m, r] * Rm[m, n].  L [B,S,R] or [M,R]; Rm [B,S,N] or [M,N]; out fp32."""
     L3, R3 = _as3d(L), _as3d(Rm)

@@ -12,7 +12,8 @@ image-only `attn2` (dual_attention_layers) and the `context_pre_only` last block
 The 2x2 stride-2 PatchEmbed conv is a K=64 GEMM on the patchified latents (same (c, dy, dx) feature order as
 Flux `pack_latents`) with the cropped positional table added in the epilogue.
 Unsupported: TREAD routing, controlnet residuals, token-wise timesteps, flow-map / TwinFlow inputs, full
-fine-tune (weight gradients of the base model) — they raise so a shim can keep the reference module.
+— they raise so a shim can keep the reference module.  Full fine-tune (model_type=full, BASELINE configs[2]) runs
+through sd3/fullft.py after `enable_full_finetune()`.
 """
 from __future__ import annotations
 
@@ -101,9 +102,26 @@ class JointTransformerBlock(nn.Module):
             self._plans = pl
         return self._plans
 
+    FULL_PARAM_ORDER = None
+
+    def full_param_names(self):
+        """Block-local names of every trainable tensor the full fine-tune schedule produces a gradient for (adaLN linears
+        are differentiated by torch autograd outside the block Function)."""
+        if self.FULL_PARAM_ORDER is None:
+            skip = ("norm1.", "norm1_context.")
+            self.FULL_PARAM_ORDER = [n for n, _ in self.named_parameters() if not n.startswith(skip) and ".lora_" not in n]
+        return self.FULL_PARAM_ORDER
+
     def forward(self, h, silu_temb, S_txt, lora_scaling):
         mod_img = self.norm1.linear(silu_temb)
         mod_txt = self.norm1_context.linear(silu_temb)
+        if getattr(self, "_full_ft", False):
+            from .fullft import JointBlockFullFn
+            names = self.full_param_names()
+            params = dict(self.named_parameters())
+            st = {"S_txt": S_txt, "H": self.heads, "hd": self.head_dim, "plans": self.plans(),
+                  "context_pre_only": self.context_pre_only, "dual": self.use_dual_attention, "param_names": names}
+            return JointBlockFullFn.apply(h, mod_img, mod_txt, st, *[params[n] for n in names])
         st = {"S_txt": S_txt, "H": self.heads, "hd": self.head_dim, "plans": self.plans(), "lora_scaling": lora_scaling,
               "nan_to_num_txt": False, "context_pre_only": self.context_pre_only, "dual": self.use_dual_attention,
               "_n_lora": 24, "lora_drop": getattr(self, "_lora_drop", None)}
@@ -195,6 +213,24 @@ class SD3Transformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
             blk._plans = None
         self._tail_plan = None
         self._pos_cache.clear()
+
+    def enable_full_finetune(self, enabled: bool = True):
+        """model_type=full (BASELINE configs[2]): every parameter trains.  The joint blocks switch to the full fine-tune
+        schedule (sd3/fullft.py); fused / transposed weight layouts are rebuilt after every optimizer step
+        (`after_optimizer_step`, called by TrainStep) because the base weights now change."""
+        if enabled and self.lora_linears():
+            raise NotImplementedError("full fine-tune and LoRA adapters are mutually exclusive on the libstb200 path")
+        self._full_ft = bool(enabled)
+        for p in self.parameters():
+            p.requires_grad_(bool(enabled))
+        for blk in self.transformer_blocks:
+            blk._full_ft = bool(enabled)
+        self.invalidate_plans()
+        return self
+
+    def after_optimizer_step(self):
+        if getattr(self, "_full_ft", False):
+            self.invalidate_plans()
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
@@ -291,13 +327,19 @@ class SD3Transformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
             x = hidden_states.to(dt).view(B, C, hp, 2, wp, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, S_img, C * 4)
         else:
             x = _packed_latents
-        h = torch.empty((B, S_txt + S_img, D), device=dev, dtype=dt)
-        # PatchEmbed: conv2x2/s2 == GEMM over (c, dy, dx) features; + cropped pos table in the epilogue
-        w_pe = self.pos_embed.proj.weight.detach().reshape(D, C * 4)
+        full = getattr(self, "_full_ft", False) and torch.is_grad_enabled()
         pos = self._cropped_pos(hp, wp, dt).expand(B, S_img, D)
-        ops.gemm([x.contiguous()], [w_pe], self.pos_embed.proj.bias.detach(), out=h[:, S_txt:], epi=ops.EPI_ADD_RES, res=pos)
-        ops.gemm([encoder_hidden_states.to(dt).contiguous()], [self.context_embedder.weight], self.context_embedder.bias,
-                 out=h[:, :S_txt])
+        if full:
+            from .fullft import EmbedFullFn, TailFullFn
+            h = EmbedFullFn.apply(x.contiguous(), encoder_hidden_states.to(dt).contiguous(), pos, self.pos_embed.proj.weight,
+                                  self.pos_embed.proj.bias, self.context_embedder.weight, self.context_embedder.bias)
+        else:
+            h = torch.empty((B, S_txt + S_img, D), device=dev, dtype=dt)
+            # PatchEmbed: conv2x2/s2 == GEMM over (c, dy, dx) features; + cropped pos table in the epilogue
+            w_pe = self.pos_embed.proj.weight.detach().reshape(D, C * 4)
+            ops.gemm([x.contiguous()], [w_pe], self.pos_embed.proj.bias.detach(), out=h[:, S_txt:], epi=ops.EPI_ADD_RES, res=pos)
+            ops.gemm([encoder_hidden_states.to(dt).contiguous()], [self.context_embedder.weight], self.context_embedder.bias,
+                     out=h[:, :S_txt])
         tte = self.time_text_embed
         temb = tte.timestep_embedder(_sinusoid(timestep.to(dev).float()).to(dt)) + tte.text_embedder(pooled_projections.to(dt).contiguous())
         silu_temb = F.silu(temb).contiguous()
@@ -308,7 +350,10 @@ class SD3Transformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
             self._tail_plan = {"w_proj": self.proj_out.weight.detach(), "b_proj": self.proj_out.bias.detach(),
                                "w_proj_t": _t(self.proj_out.weight.detach())}
         mod = self.norm_out.linear(silu_temb)
-        out = TailFn.apply(h, mod, {"S_txt": S_txt, **self._tail_plan})  # [B, S_img, p*p*C_out] in (dy, dx, c) order
+        if full:
+            out = TailFullFn.apply(h, mod, self.proj_out.weight, self.proj_out.bias, S_txt)
+        else:
+            out = TailFn.apply(h, mod, {"S_txt": S_txt, **self._tail_plan})  # [B, S_img, p*p*C_out] in (dy, dx, c) order
         if not _packed_output:
             Co = self.out_channels
             out = torch.einsum("nhwpqc->nchpwq", out.reshape(B, hp, wp, 2, 2, Co)).reshape(B, Co, hp * 2, wp * 2)

@@ -69,6 +69,11 @@ class TrainStep:
             self._clip()
             self.optimizer.step()
             self.optimizer.zero_grad(set_to_none=True)
+            den = getattr(self.model, "model", None)
+            den = getattr(den, "module", den)
+            hook = getattr(den, "after_optimizer_step", None)
+            if callable(hook):          # full fine-tune: derived weight layouts must be rebuilt from the updated weights
+                hook()
             self.state["global_step"] += 1
         return ld
 

@@ -549,3 +549,44 @@ CHECKS.update({
     "conv_in_3ch_c64": lambda: check_conv_in(B=1, H=33, W=130, C=64),
     "conv_in_3ch_c8_cuda_core": lambda: check_conv_in(B=1, H=12, W=20, C=8),  # C % 16 != 0 -> CUDA-core fallback kernel
 })
+
+
+# --------------------------------------------------------------------------------------------- full-rank weight gradient
+def check_wgrad_full(B=2, S=300, N=256, K=320, strided=False, accumulate=False, alpha=1.0):
+    if strided:   # row ranges / column ranges of larger buffers, like the joint hidden buffer and the fused qkv gradient
+        dyf = _rand(B, S + 5, N + 64, seed=41)
+        xf = _rand(B, S + 9, K + 32, seed=42)
+        dy, x = dyf[:, 3:S + 3, 32:32 + N], xf[:, 4:S + 4, 8:8 + K]
+    else:
+        dy, x = _rand(B, S, N, seed=41), _rand(B, S, K, seed=42)
+    ref = alpha * torch.einsum("bsn,bsk->nk", dy.float(), x.float())
+    out = None
+    if accumulate:
+        out = _rand(N, K, seed=43)
+        ref = ref + out.float()
+    got = ops.wgrad_full(dy, x, out=out, alpha=alpha, accumulate=accumulate)
+    torch.cuda.synchronize()
+    return _report(f"wgrad_full_B{B}_S{S}_N{N}_K{K}", got, ref, atol=float(ref.abs().max()) * 6e-3, rtol=1.6e-2)
+
+
+def check_colsum2(B=3, S=333, D=1536):
+    dyf, zf = _rand(B, S + 3, D + 16, seed=51), _rand(B, S, D, seed=52)
+    dy = dyf[:, 1:S + 1, 8:8 + D]
+    sm, dt = ops.colsum2(dy, zf)
+    torch.cuda.synchronize()
+    r1 = _report("colsum", sm, dy.float().sum(1), atol=0.05, rtol=1e-3)
+    r2 = _report("coldot", dt, (dy.float() * zf.float()).sum(1), atol=0.05, rtol=1e-3)
+    only = ops.colsum2(dy, None)[0]
+    return {"name": f"colsum2_B{B}_S{S}_D{D}", "ok": r1["ok"] and r2["ok"] and bool(torch.allclose(only, sm, atol=1e-3)),
+            "max_err": max(r1["max_err"], r2["max_err"])}
+
+
+CHECKS.update({
+    "wgrad_full_basic": lambda: check_wgrad_full(),
+    "wgrad_full_strided_accum": lambda: check_wgrad_full(B=3, S=231, N=384, K=200, strided=True, accumulate=True, alpha=0.5),
+    "wgrad_full_sd3_qkv": lambda: check_wgrad_full(B=2, S=1255, N=4608, K=1536),
+    "wgrad_full_narrow": lambda: check_wgrad_full(B=1, S=1000, N=128, K=64),
+    "wgrad_full_flux_mlp": lambda: check_wgrad_full(B=1, S=4608, N=3072, K=12288),
+    "colsum2": lambda: check_colsum2(),
+    "colsum2_small": lambda: check_colsum2(B=1, S=7, D=64),
+})
