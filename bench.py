@@ -130,6 +130,66 @@ def synth_batch(B, device, pinned=False, seed=0, hw=128, s_txt=S_TXT, joint=4096
     return {k: v.to(device) for k, v in b.items()}
 
 
+# SD3.5-medium geometry (BASELINE configs[2]: "SD3-medium MMDiT full fine-tune bf16, 512^2 aspect buckets, batch=8, 8xB200 DDP")
+SD35_MEDIUM = dict(sample_size=128, patch_size=2, in_channels=16, num_layers=24, attention_head_dim=64, num_attention_heads=24,
+                   joint_attention_dim=4096, caption_projection_dim=1536, pooled_projection_dim=2048, out_channels=16,
+                   pos_embed_max_size=384, dual_attention_layers=tuple(range(13)), qk_norm="rms_norm")
+SD3_BUCKETS = [(64, 64), (56, 72), (72, 56), (48, 80), (80, 48)]    # latent (h, w) of the 64-px aligned 512^2-area buckets
+SD3_S_TXT = 231       # 77 CLIP + 154 T5 tokens (sd3/model.py)
+
+
+def sd3_tf_per_sample(hw=(64, 64), s_txt=SD3_S_TXT, full_ft=True):
+    """Algorithmic TFLOP of one SD3.5-medium training sample (GEMM 2MNK, attention 4 S^2 D fwd / 8 S^2 D bwd)."""
+    D, L, n_dual = 1536, 24, 13
+    s_img = (hw[0] // 2) * (hw[1] // 2)
+    S = s_img + s_txt
+    lin = 0.0
+    for i in range(L):
+        pre_only = i == L - 1
+        lin += 2 * s_img * (3 * D * D + D * D + 8 * D * D)                              # img: qkv, out, mlp
+        lin += 2 * s_txt * (3 * D * D + (0 if pre_only else D * D + 8 * D * D))         # txt
+        if i < n_dual:
+            lin += 2 * s_img * (4 * D * D)                                              # attn2 qkv + out
+    attn = sum(4 * S * S * D + (4 * s_img * s_img * D if i < n_dual else 0) for i in range(L))
+    fwd = (lin + attn) * 1e-12
+    return fwd * 3 if full_ft else fwd + lin * 1e-12 + 2 * attn * 1e-12
+
+
+def build_sd3_fullft(device, seed=0, tiny=False):
+    from simpletuner_b200.flux.model import default_config
+    from simpletuner_b200.sd3.model import SD3
+    from simpletuner_b200.sd3.transformer import SD3Transformer2DModel
+
+    kw = dict(SD35_MEDIUM)
+    if tiny:
+        kw.update(num_layers=3, attention_head_dim=64, num_attention_heads=4, joint_attention_dim=256, caption_projection_dim=256,
+                  pooled_projection_dim=64, pos_embed_max_size=96, dual_attention_layers=(0,))
+    with torch.device(device):
+        m = SD3Transformer2DModel(**kw)
+    g = torch.Generator(device=device).manual_seed(seed)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if "norm_q" in name or "norm_k" in name or "norm_added" in name:
+                p.fill_(1.0)
+            elif name.endswith(".bias"):
+                p.normal_(0.0, 0.01, generator=g)
+            else:
+                p.normal_(0.0, 0.02, generator=g)
+        m.pos_embed.pos_embed.normal_(0.0, 0.02, generator=g)
+    m.enable_full_finetune()
+    return SD3(default_config(model_type="full"), transformer=m, device=device)
+
+
+def synth_batch_sd3(B, device, hw, pinned=False, seed=0, s_txt=SD3_S_TXT, joint=4096, pooled=2048):
+    g = torch.Generator().manual_seed(seed)
+    b = {"latent_batch": torch.randn(B, 16, hw[0], hw[1], generator=g).bfloat16(),
+         "prompt_embeds": torch.randn(B, s_txt, joint, generator=g).bfloat16(),
+         "add_text_embeds": torch.randn(B, pooled, generator=g).bfloat16()}
+    if pinned:
+        return {k: v.pin_memory() for k, v in b.items()}
+    return {k: v.to(device) for k, v in b.items()}
+
+
 def batch_bytes(b):
     return int(sum(v.numel() * v.element_size() for v in b.values()))
 
@@ -395,18 +455,24 @@ def run_b200(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    B = args.batch
+    sd3 = args.config == "sd3_fullft"
+    B = args.batch if args.batch else (8 if sd3 else 4)
     cfg_over = None
     hw, s_txt = 128, S_TXT
     if args.tiny:  # plumbing check only (never a bench value)
         cfg_over = dict(num_layers=1, num_single_layers=2, num_attention_heads=4, joint_attention_dim=256, pooled_projection_dim=64)
         hw, s_txt = 32, 64
-    wrapper = build_model(device, cfg_over, rank=16, seed=0)
+    if sd3:
+        wrapper = build_sd3_fullft(device, seed=0, tiny=args.tiny)
+        if args.dp == "flat" and world > 1:
+            args.dp = "ddp"      # 5 GB of gradients: bucketed all-reduce overlapped with backward (the reference's DDP), not one flat exchange
+    else:
+        wrapper = build_model(device, cfg_over, rank=16, seed=0)
     if args.gradient_checkpointing:   # non-default: the reference's --gradient_checkpointing memory / time trade-off
         wrapper._denoiser().enable_gradient_checkpointing()
     if world > 1 and args.dp == "ddp":
         wrap_ddp(wrapper, device_ids=[local_rank])
-    params = wrapper._denoiser().trainable_parameters()
+    params = [p for p in wrapper._denoiser().parameters() if p.requires_grad]
     if args.optimizer == "adamw_bf16":   # the reference's default optimizer, one libstb200 launch per step
         from simpletuner_b200.training.optim import AdamWBF16
         opt = AdamWBF16(params, lr=1e-4, weight_decay=1e-2, eps=1e-6, seed=1234 + rank)
@@ -420,8 +486,18 @@ def run_b200(args):
     torch.manual_seed(42 + rank)  # seed_for_each_device=True (trainer.py:2554-2556)
     joint = cfg_over["joint_attention_dim"] if cfg_over else 4096
     pooled = cfg_over["pooled_projection_dim"] if cfg_over else 768
-    dev_batches = [synth_batch(B, device, seed=100 + rank * 10 + i, hw=hw, s_txt=s_txt, joint=joint, pooled=pooled) for i in range(2)]
-    host_batches = [synth_batch(B, device, pinned=True, seed=200 + rank * 10 + i, hw=hw, s_txt=s_txt, joint=joint, pooled=pooled) for i in range(2)]
+    if sd3:
+        # aspect buckets: every rank walks the five 512^2-area buckets round-robin (ranks start at different buckets, as the
+        # reference's per-rank samplers do), one uniform shape inside a micro-batch
+        kw3 = dict(s_txt=64, joint=256, pooled=64) if args.tiny else {}
+        bks = [(16, 16), (12, 20)] if args.tiny else SD3_BUCKETS
+        nb = len(bks)
+        dev_batches = [synth_batch_sd3(B, device, bks[(i + rank) % nb], seed=100 + rank * 10 + i, **kw3) for i in range(nb)]
+        host_batches = [synth_batch_sd3(B, device, bks[(i + rank) % nb], pinned=True, seed=200 + rank * 10 + i, **kw3) for i in range(nb)]
+    else:
+        dev_batches = [synth_batch(B, device, seed=100 + rank * 10 + i, hw=hw, s_txt=s_txt, joint=joint, pooled=pooled) for i in range(2)]
+        host_batches = [synth_batch(B, device, pinned=True, seed=200 + rank * 10 + i, hw=hw, s_txt=s_txt, joint=joint, pooled=pooled) for i in range(2)]
+    nbat = len(dev_batches)
 
     def barrier():
         if world > 1:
@@ -443,7 +519,7 @@ def run_b200(args):
 
     # ---- device-resident arm
     def dev_step(i):
-        step({k: v for k, v in dev_batches[i % 2].items()})
+        step({k: v for k, v in dev_batches[i % nbat].items()})
 
     for i in range(args.warmup):
         dev_step(i)
@@ -460,7 +536,7 @@ def run_b200(args):
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def e2e_step(i):
-        hb = host_batches[i % 2]
+        hb = host_batches[i % nbat]
         ld = step({k: v.to(device, non_blocking=True) for k, v in hb.items()})
         loss_host.copy_(ld, non_blocking=False)  # device->host read of the step's result (synchronises)
 
@@ -470,7 +546,7 @@ def run_b200(args):
 
     # ---- per-kernel pass (extra step, outside both timed regions)
     # (every rank runs it: the step contains the DDP gradient all-reduce)
-    kern = profile_kernels(lambda b: step(b), dict(dev_batches[0]))
+    kern = profile_kernels(lambda b: step(b), dict(dev_batches[0])) if not sd3 else None
     barrier()
     mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
 
@@ -497,13 +573,22 @@ def run_b200(args):
                     "peak_burst": float(peaks.get("bf16_tflops", 0.0)),
                     "frac_of_burst": round(gb["tflops"] / float(peaks.get("bf16_tflops", peak_tf)), 4), "traffic": traffic,
                     "avg_launch_ms": gb["avg_ms"], "tflop_per_launch": gb["tflop_per_launch"], "launches_per_step": gb["launches"]}
+        tf_sample = TF_STEP_SAMPLE
+        metric, workload = METRIC, WORKLOAD
+        if sd3:
+            tf_sample = sum(sd3_tf_per_sample(hw_) for hw_ in SD3_BUCKETS) / len(SD3_BUCKETS)
+            metric = "images/sec SD3.5-medium full fine-tune bf16 512^2 buckets"
+            workload = ("SD3.5-medium (24 joint blocks, D=1536, 13 dual-attention layers, QK-RMSNorm) FULL fine-tune bf16, 512^2-area aspect "
+                        "buckets (64x64, 56x72, 72x56, 48x80, 80x48 latents) + 231 text tokens, train step = prepare_batch+fwd+loss+bwd "
+                        "(every weight gradient)+value-clip+adamw_bf16 on all 2.5 B parameters")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic (random-init Flux.1-dev architecture; seeded N(0,1) cached latents + T5/CLIP embeds)",
             "config": {
-                "workload": WORKLOAD,
-                "global_batch": B * world, "per_gpu_batch": B, "seq_len": S_IMG + S_TXT, "parallelism": f"dp{world}", "grad_exchange": (None if world == 1 else args.dp),
+                "workload": workload, "config_name": args.config,
+                "global_batch": B * world, "per_gpu_batch": B, "seq_len": (S_IMG + S_TXT) if not sd3 else 1024 + SD3_S_TXT,
+                "parallelism": f"dp{world}", "grad_exchange": (None if world == 1 else args.dp),
                 "activation_recompute": ("every block re-run in backward (--gradient-checkpointing)" if args.gradient_checkpointing else
                                          "none (block-native minimal saves; reference default would recompute every block)"),
                 "host_syncs_in_step": 0, "l2_policy": "inputs larger than L2 (24 GB of weights + 16 MB fresh batch streamed every step)",
@@ -516,12 +601,18 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
-            "model_tflops": {"algorithmic_tf_per_image": round(TF_STEP_SAMPLE, 1),
-                             "achieved_tflops_per_gpu": round(TF_STEP_SAMPLE * B / (ms_step * 1e-3), 1),
-                             "frac_of_peak": round(TF_STEP_SAMPLE * B / (ms_step * 1e-3) / peak_tf, 4)} if not args.tiny else None,
+            "model_tflops": {"algorithmic_tf_per_image": round(tf_sample, 2),
+                             "achieved_tflops_per_gpu": round(tf_sample * B / (ms_step * 1e-3), 1),
+                             "frac_of_peak": round(tf_sample * B / (ms_step * 1e-3) / peak_tf, 4)} if not args.tiny else None,
             "kernels": kern, "peak_mem_gb": round(mem_gb, 1),
         }
-        if world == 1 and not args.no_eager_baseline and not args.tiny:
+        if sd3 and roof is None:
+            ach = tf_sample * B / (ms_step * 1e-3)
+            roof = {"bound": "tensor", "kernel": "whole step (GEMM + full-rank wgrad + attention), algorithmic 3x forward", "achieved": round(ach, 1),
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4), "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})",
+                    "traffic": None}
+            line["roofline"] = roof
+        if world == 1 and not args.no_eager_baseline and not args.tiny and not sd3:
             try:   # informational: the reference's default eager path (SDPA + per-block checkpointing) on this GPU, same batch
                 torch.cuda.empty_cache()
                 ms_eager = time_eager_gpu(wrapper, device, dev_batches, opt)
@@ -532,7 +623,7 @@ def run_b200(args):
                             "gradient_checkpointing=true), same parameters / batch / optimizer; 3 timed steps after 2 warm-up"}
             except Exception as e:  # noqa
                 line["gpu_eager_baseline"] = {"error": str(e)[:300]}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not sd3:
             try:
                 cb = cpu_baseline_sample()
                 line["cpu_baseline"] = {"value": cb["images_per_sec"], "unit": UNIT, "cores": cb["threads"], "kind": "port",
@@ -552,7 +643,9 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 4 for flux_lora, 8 for sd3_fullft)")
+    ap.add_argument("--config", default="flux_lora", choices=["flux_lora", "sd3_fullft"],
+                    help="flux_lora = BASELINE configs[1] (the headline metric); sd3_fullft = configs[2] (SD3.5-medium full fine-tune, DDP)")
     ap.add_argument("--tiny", action="store_true", help="plumbing check on a toy config (not a benchmark value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the informational eager-torch GPU baseline (N=1 only)")
