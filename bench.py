@@ -464,8 +464,8 @@ def run_b200(args):
         hw, s_txt = 32, 64
     if sd3:
         wrapper = build_sd3_fullft(device, seed=0, tiny=args.tiny)
-        if args.dp == "flat" and world > 1:
-            args.dp = "ddp"      # 5 GB of gradients: bucketed all-reduce overlapped with backward (the reference's DDP), not one flat exchange
+        if args.dp == "auto":
+            args.dp = "flat"     # CUDA-graph replay of fwd + bwd, then one flat 5 GB all-reduce; `--dp ddp` = torch DDP buckets (eager)
     else:
         wrapper = build_model(device, cfg_over, rank=16, seed=0)
     if args.gradient_checkpointing:   # non-default: the reference's --gradient_checkpointing memory / time trade-off
@@ -483,6 +483,10 @@ def run_b200(args):
         from simpletuner_b200.training.dist import FlatGradSync
         grad_sync = FlatGradSync(params)
     step = TrainStep(wrapper, opt, max_grad_norm=2.0, grad_clip_method="value", grad_sync=grad_sync)
+    use_graph = args.graph == "on" or (args.graph == "auto" and sd3 and args.dp != "ddp")
+    if use_graph:
+        from simpletuner_b200.training.step import GraphedTrainStep
+        step = GraphedTrainStep(step)
     torch.manual_seed(42 + rank)  # seed_for_each_device=True (trainer.py:2554-2556)
     joint = cfg_over["joint_attention_dim"] if cfg_over else 4096
     pooled = cfg_over["pooled_projection_dim"] if cfg_over else 768
@@ -546,7 +550,8 @@ def run_b200(args):
 
     # ---- per-kernel pass (extra step, outside both timed regions)
     # (every rank runs it: the step contains the DDP gradient all-reduce)
-    kern = profile_kernels(lambda b: step(b), dict(dev_batches[0])) if not sd3 else None
+    eager_step = step.step if use_graph else step
+    kern = profile_kernels(lambda b: eager_step(b), dict(dev_batches[0])) if not sd3 else None
     barrier()
     mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
 
@@ -588,7 +593,7 @@ def run_b200(args):
             "config": {
                 "workload": workload, "config_name": args.config,
                 "global_batch": B * world, "per_gpu_batch": B, "seq_len": (S_IMG + S_TXT) if not sd3 else 1024 + SD3_S_TXT,
-                "parallelism": f"dp{world}", "grad_exchange": (None if world == 1 else args.dp),
+                "parallelism": f"dp{world}", "grad_exchange": (None if world == 1 else args.dp), "cuda_graph": bool(use_graph),
                 "activation_recompute": ("every block re-run in backward (--gradient-checkpointing)" if args.gradient_checkpointing else
                                          "none (block-native minimal saves; reference default would recompute every block)"),
                 "host_syncs_in_step": 0, "l2_policy": "inputs larger than L2 (24 GB of weights + 16 MB fresh batch streamed every step)",
@@ -651,12 +656,16 @@ def main():
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the informational eager-torch GPU baseline (N=1 only)")
     ap.add_argument("--optimizer", default="adamw_bf16", choices=["adamw", "adamw_bf16"],
                     help="adamw_bf16 = the reference's default optimizer (one libstb200 launch); adamw = torch.optim.AdamW(fused)")
-    ap.add_argument("--dp", default="flat", choices=["flat", "ddp"],
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="capture prepare_batch+fwd+loss+bwd in a CUDA graph per batch shape (auto: on for sd3_fullft, whose step is launch-bound)")
+    ap.add_argument("--dp", default="auto", choices=["auto", "flat", "ddp"],
                     help="gradient exchange for N > 1: flat = one NCCL all-reduce of all LoRA gradients after backward "
                          "(training.dist.FlatGradSync); ddp = torch DDP buckets overlapped with backward (the reference's mechanism)")
     ap.add_argument("--gradient-checkpointing", action="store_true",
                     help="re-run every block in backward like the reference's --gradient_checkpointing (not the headline config)")
     args = ap.parse_args()
+    if args.dp == "auto" and args.config != "sd3_fullft":
+        args.dp = "flat"
     if args.warmup < 3 and args.impl == "b200" and not args.tiny:
         args.warmup = 3
     if args.impl == "reference":

@@ -232,6 +232,12 @@ class SD3Transformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
         if getattr(self, "_full_ft", False):
             self.invalidate_plans()
 
+    def before_graph_capture(self):
+        """training.step.GraphedTrainStep: in full fine-tune the fused / transposed layouts are rebuilt INSIDE the captured
+        step (they depend on weights the optimizer changes between replays)."""
+        if getattr(self, "_full_ft", False):
+            self.invalidate_plans()
+
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         self.invalidate_plans()

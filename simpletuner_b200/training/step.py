@@ -101,6 +101,92 @@ class TrainStep:
             raise RuntimeError("Non-finite loss encountered during training.")
 
 
+class GraphedTrainStep:
+    """TrainStep whose micro-step body (prepare_batch -> model_predict -> loss -> backward) is captured ONCE per batch shape
+    into a CUDA graph and replayed; gradient exchange, clip and optimizer stay eager.
+
+    Why: with short kernels (SD3.5-medium full fine-tune: ~3000 launches of 20-50 us per step) the step is bound by the
+    Python / launch path, not by the GPU.  A replay issues the same kernels from one `cudaGraphLaunch`.  The reference has
+    no equivalent (its loop is eager); numerics are unchanged — the graph contains exactly the eager launches, and torch's
+    CUDA generator is capture-aware, so noise / sigmas still advance every replay.
+    Constraints: gradient_accumulation_steps == 1, no torch DDP wrapper (use `FlatGradSync`), one uniform shape per call
+    (aspect buckets -> one graph per bucket shape), gradients stay allocated between steps (their addresses are baked into
+    the graph), the model must not change structure after the first call."""
+
+    def __init__(self, step: "TrainStep", warmup: int = 2):
+        if step.accum != 1:
+            raise NotImplementedError("GraphedTrainStep supports gradient_accumulation_steps == 1")
+        if hasattr(step.model.model, "no_sync"):
+            raise NotImplementedError("GraphedTrainStep: wrap with FlatGradSync instead of torch DDP")
+        self.step = step
+        self.warmup = warmup
+        self._graphs: Dict[Any, Any] = {}
+        self._pool = None          # one memory pool shared by the per-bucket graphs (they never replay concurrently)
+
+    @property
+    def state(self):
+        return self.step.state
+
+    def check_finite(self):
+        return self.step.check_finite()
+
+    def _body(self, batch):
+        st = self.step
+        prepared = st.model.prepare_batch(batch, st.state)
+        out = st.model_predict(prepared)
+        loss, _ = st.model.loss_with_logs(prepared, out, apply_conditioning_mask=True)
+        loss.backward()
+        return loss.detach()
+
+    def _finish(self, ld):
+        st = self.step
+        bad = ~torch.isfinite(ld)
+        st._nonfinite = bad if st._nonfinite is None else (st._nonfinite | bad)
+        st.state["micro_step"] += 1
+        if st.grad_sync is not None:
+            st.grad_sync()
+        st._clip()
+        st.optimizer.step()
+        # NO zero_grad(set_to_none): the captured backward writes the same .grad tensors again on the next replay
+        st.state["global_step"] += 1
+        return ld
+
+    def __call__(self, batch: Dict[str, Any]) -> torch.Tensor:
+        key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.items()) if torch.is_tensor(v))
+        entry = self._graphs.get(key)
+        if entry is None:
+            static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+            for p in self.step._params:
+                p.grad = None
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):          # lazy initialisation (weight layouts, tensor maps, smem attributes)
+                    self._body(dict(static))
+                    for p in self.step._params:
+                        p.grad = None
+            torch.cuda.current_stream().wait_stream(side)
+            den = getattr(self.step.model, "model", None)
+            hook = getattr(den, "before_graph_capture", None)
+            if callable(hook):      # full fine-tune: the rebuild of the derived weight layouts must be PART of the graph
+                hook()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=self._pool):
+                loss = self._body(dict(static))
+            if self._pool is None:
+                self._pool = graph.pool()
+            entry = (graph, static, loss, [p.grad for p in self.step._params])
+            self._graphs[key] = entry
+        graph, static, loss, grads = entry
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                static[k].copy_(v, non_blocking=True)
+        for p, g in zip(self.step._params, grads):       # several bucket graphs own different gradient buffers
+            p.grad = g
+        graph.replay()
+        return self._finish(loss.clone())
+
+
 class _null:
     def __enter__(self):
         return None
