@@ -150,7 +150,8 @@ int stb_qk_rmsnorm_rope_bwd(const void* dq, const void* dk, long long d_b, long 
                             long long src_b, long long src_s, int k_off, const void* wq, const void* wk,
                             const void* wq_added, const void* wk_added, int s_split, const float* cos_t,
                             const float* sin_t, void* dsrc, long long ds_b, long long ds_s, int B, int S,
-                            int H, int HD, float eps, void* stream);
+                            int H, int HD, float eps, float* dw /* optional fp32 [4][HD], accumulated: d(wq, wk, wq_added, wk_added) */,
+                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Flow-matching batch prep and loss (Flux 2x2 patchify folded into the index math).

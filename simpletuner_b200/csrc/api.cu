@@ -605,7 +605,7 @@ int stb_qk_rmsnorm_rope_bwd(const void* dq, const void* dk, long long d_b, long 
                             long long src_b, long long src_s, int k_off, const void* wq, const void* wk,
                             const void* wq_added, const void* wk_added, int s_split, const float* cos_t,
                             const float* sin_t, void* dsrc, long long ds_b, long long ds_s, int B, int S,
-                            int H, int HD, float eps, void* stream) {
+                            int H, int HD, float eps, float* dw, void* stream) {
   if (int r = check_device()) return r;
   if (HD != 128 && HD != 64) return fail(STB_ERR_UNSUPPORTED, "head_dim %d not supported", HD);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -613,9 +613,9 @@ int stb_qk_rmsnorm_rope_bwd(const void* dq, const void* dk, long long d_b, long 
   const unsigned grid = (unsigned)((warps + 7) / 8);
   auto cast = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
   if (HD == 128)
-    stb::qk_rmsnorm_rope_bwd_kernel<128><<<grid, 256, 0, st>>>(cast(dq), cast(dk), d_b, d_s, cast(src), src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(dsrc), ds_b, ds_s, B, S, H, eps);
+    stb::qk_rmsnorm_rope_bwd_kernel<128><<<grid, 256, 0, st>>>(cast(dq), cast(dk), d_b, d_s, cast(src), src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(dsrc), ds_b, ds_s, B, S, H, eps, dw);
   else
-    stb::qk_rmsnorm_rope_bwd_kernel<64><<<grid, 256, 0, st>>>(cast(dq), cast(dk), d_b, d_s, cast(src), src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(dsrc), ds_b, ds_s, B, S, H, eps);
+    stb::qk_rmsnorm_rope_bwd_kernel<64><<<grid, 256, 0, st>>>(cast(dq), cast(dk), d_b, d_s, cast(src), src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(dsrc), ds_b, ds_s, B, S, H, eps, dw);
   STB_LAUNCH_CHECK("qk_rmsnorm_rope_bwd");
   return 0;
 }

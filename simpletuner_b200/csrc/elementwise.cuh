@@ -308,12 +308,21 @@ qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bflo
                            const __nv_bfloat16* __restrict__ wq1, const __nv_bfloat16* __restrict__ wk1,
                            int s_split, const float* __restrict__ cosT, const float* __restrict__ sinT,
                            __nv_bfloat16* __restrict__ dsrc, long long ds_b, long long ds_s, int B, int S,
-                           int H, float eps) {
+                           int H, float eps, float* __restrict__ dw) {
+  // dw (optional, full fine-tune): fp32 [4][HD] gradients of the RMSNorm weights (wq0, wk0, wq1, wk1), accumulated with
+  // shared-memory atomics per block and one global atomic per entry per block:  dw[i] += (R^T d_out)[i] * xhat[i]
   constexpr int EPL = HD / 32;
   constexpr int U = 4;
+  __shared__ float dw_s[4 * HD];
+  if (dw) {
+    for (int i = threadIdx.x; i < 4 * HD; i += blockDim.x) dw_s[i] = 0.f;
+    __syncthreads();
+  }
   const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (tok >= (long long)B * S) return;
+  const bool active = tok < (long long)B * S;
+  if (!active && !dw) return;
   const int lane = threadIdx.x & 31;
+  if (active) {
   const int s = int(tok % S);
   const int b = int(tok / S);
   const bool txt = s < s_split;
@@ -331,6 +340,9 @@ qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bflo
   __nv_bfloat16* out_tok = dsrc + b * ds_b + s * ds_s + lane * EPL;
   const long long g_tok = b * d_b + s * d_s + lane * EPL;
   const int rows = 2 * H;
+  float dwacc[2][EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) dwacc[0][i] = 0.f, dwacc[1][i] = 0.f;
   for (int r0 = 0; r0 < rows; r0 += U) {
     float x[U][EPL], go[U][EPL];
 #pragma unroll
@@ -358,6 +370,8 @@ qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bflo
         const float dy1 = go[u][i + 1] * cs[i + 1] - go[u][i] * sn[i];
         g[u][i] = dy0 * (which ? wkv[i] : wqv[i]);
         g[u][i + 1] = dy1 * (which ? wkv[i + 1] : wqv[i + 1]);
+        go[u][i] = dy0;        // keep the pre-weight gradient for dw
+        go[u][i + 1] = dy1;
       }
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
@@ -384,7 +398,25 @@ qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bflo
 #pragma unroll
       for (int i = 0; i < EPL; ++i) o[i] = rstd * (g[u][i] - (x[u][i] * rstd) * m);
       st_row<EPL>(out_tok + (which ? k_off : 0) + hh * HD, o);
+      if (dw) {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) dwacc[which][i] += go[u][i] * (x[u][i] * rstd);
+      }
     }
+  }
+  if (dw) {
+    const int base = (txt ? 2 : 0) * HD;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      atomicAdd(&dw_s[base + lane * EPL + i], dwacc[0][i]);
+      atomicAdd(&dw_s[base + HD + lane * EPL + i], dwacc[1][i]);
+    }
+  }
+  }  // active
+  if (dw) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * HD; i += blockDim.x)
+      if (dw_s[i] != 0.f) atomicAdd(dw + i, dw_s[i]);
   }
 }
 

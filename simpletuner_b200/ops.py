@@ -225,8 +225,9 @@ def qk_rmsnorm_rope_fwd(src, k_off, H, HD, wq, wk, wq_added=None, wk_added=None,
 
 
 def qk_rmsnorm_rope_bwd(dq, dk, src, k_off, H, HD, wq, wk, wq_added=None, wk_added=None, s_split=0,
-                        cos=None, sin=None, eps: float = 1e-6, dsrc=None):
-    """Writes the q / k column ranges of dsrc ([B, S, C], same layout as src)."""
+                        cos=None, sin=None, eps: float = 1e-6, dsrc=None, dw=None):
+    """Writes the q / k column ranges of dsrc ([B, S, C], same layout as src).  dw (optional): zero-initialised fp32
+    [4, HD] that receives the RMSNorm weight gradients (wq, wk, wq_added, wk_added) — full fine-tune."""
     B, S, _ = src.shape
     assert dq.stride() == dk.stride() and dq.stride(2) == HD
     if dsrc is None:
@@ -234,7 +235,7 @@ def qk_rmsnorm_rope_bwd(dq, dk, src, k_off, H, HD, wq, wk, wq_added=None, wk_add
     check(_lib.lib().stb_qk_rmsnorm_rope_bwd(
         dq.data_ptr(), dk.data_ptr(), dq.stride(0), dq.stride(1), src.data_ptr(), src.stride(0), src.stride(1),
         k_off, _ptr(wq), _ptr(wk), _ptr(wq_added), _ptr(wk_added), s_split, _ptr(cos), _ptr(sin),
-        dsrc.data_ptr(), dsrc.stride(0), dsrc.stride(1), B, S, H, HD, eps, _stream()))
+        dsrc.data_ptr(), dsrc.stride(0), dsrc.stride(1), B, S, H, HD, eps, _ptr(dw), _stream()))
     return dsrc
 
 

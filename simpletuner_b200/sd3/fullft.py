@@ -10,9 +10,8 @@ diffusers' JointTransformerBlock in the reference (trainer.py:7126; sd3/transfor
   * biases and the adaLN chunks (shift / scale / gate of norm1, norm1_context, the dual-attention norm): per-(batch, column)
     token reductions `ops.colsum2` (sum_s dy, sum_s dy * z with z = LayerNorm(x) or the gated linear output that the
     GATE_RES epilogue now also writes);
-  * the per-head RMSNorm weights of q / k (SD3.5 qk_norm="rms_norm"): 4 x [head_dim] vectors per attention — reduced
-    with torch ops on the [B, S, H, hd] gradient (parameter-sized outputs, activation-sized read; the one place left on
-    torch here);
+  * the per-head RMSNorm weights of q / k (SD3.5 qk_norm="rms_norm"): 4 x [head_dim] vectors per attention, accumulated
+    inside the RMSNorm backward kernel (`ops.qk_rmsnorm_rope_bwd(dw=...)`, shared-memory atomics per block);
   * mod_img / mod_txt receive gradients, so norm1.linear / norm1_context.linear and the timestep / pooled-text embedders
     train through plain torch autograd on [B, D] tensors (the conditioning path is < 0.1 % of the step).
 
@@ -267,16 +266,14 @@ def _attn_bwd_full(qkv, o, d_o, lse, D, H, hd, img_plan: AttnPlan, txt_plan: Opt
     dk = torch.empty_like(k)
     ops.attn_bwd(q, k, v, o.view(B, S, H, hd), d_o.view(B, S, H, hd), lse, dq=dq, dk=dk, dv=dv)
     del q, k
-    xq = qkv[:, :, 0:D].unflatten(-1, (H, hd))
-    xk = qkv[:, :, D:2 * D].unflatten(-1, (H, hd))
-    nq = {"q_img": _rms_weight_grads(dq[:, S_txt:], xq[:, S_txt:]).to(torch.bfloat16),
-          "k_img": _rms_weight_grads(dk[:, S_txt:], xk[:, S_txt:]).to(torch.bfloat16)}
-    if txt_plan is not None and S_txt > 0:
-        nq["q_txt"] = _rms_weight_grads(dq[:, :S_txt], xq[:, :S_txt]).to(torch.bfloat16)
-        nq["k_txt"] = _rms_weight_grads(dk[:, :S_txt], xk[:, :S_txt]).to(torch.bfloat16)
     tq = txt_plan.norm_q if txt_plan is not None else None
     tk = txt_plan.norm_k if txt_plan is not None else None
-    ops.qk_rmsnorm_rope_bwd(dq, dk, qkv, D, H, hd, img_plan.norm_q, img_plan.norm_k, tq, tk, S_txt, None, None, EPS, dsrc=d_qkv)
+    dw = torch.zeros((4, hd), device=qkv.device, dtype=torch.float32)     # d(norm_q, norm_k, norm_added_q, norm_added_k)
+    ops.qk_rmsnorm_rope_bwd(dq, dk, qkv, D, H, hd, img_plan.norm_q, img_plan.norm_k, tq, tk, S_txt, None, None, EPS, dsrc=d_qkv, dw=dw)
+    dwb = dw.to(torch.bfloat16)
+    nq = {"q_img": dwb[0], "k_img": dwb[1]}
+    if txt_plan is not None and S_txt > 0:
+        nq["q_txt"], nq["k_txt"] = dwb[2], dwb[3]
     return d_qkv, nq
 
 
