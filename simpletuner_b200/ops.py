@@ -392,12 +392,23 @@ def skinny_tn(L, Rm, alpha: float = 1.0, out: Optional[torch.Tensor] = None):
     return out
 
 
+_graph_launches = 0   # libstb200 kernels executed by CUDA-graph replays (the C counter only sees direct launches)
+
+
 def launch_count() -> int:
-    return int(_lib.lib().stb_launch_count())
+    return int(_lib.lib().stb_launch_count()) + _graph_launches
 
 
 def reset_launch_count() -> None:
+    global _graph_launches
+    _graph_launches = 0
     _lib.lib().stb_reset_launch_count()
+
+
+def note_graph_replay(n_kernels: int) -> None:
+    """training.step.GraphedTrainStep: a replay runs the `n_kernels` libstb200 launches recorded at capture time."""
+    global _graph_launches
+    _graph_launches += int(n_kernels)
 
 
 # ---------------------------------------------------------------------------------------------- VAE encode

@@ -170,20 +170,24 @@ class GraphedTrainStep:
             hook = getattr(den, "before_graph_capture", None)
             if callable(hook):      # full fine-tune: the rebuild of the derived weight layouts must be PART of the graph
                 hook()
+            from .. import ops
+            n0 = ops.launch_count()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, pool=self._pool):
                 loss = self._body(dict(static))
             if self._pool is None:
                 self._pool = graph.pool()
-            entry = (graph, static, loss, [p.grad for p in self.step._params])
+            entry = (graph, static, loss, [p.grad for p in self.step._params], ops.launch_count() - n0)
             self._graphs[key] = entry
-        graph, static, loss, grads = entry
+        graph, static, loss, grads, n_kernels = entry
         for k, v in batch.items():
             if torch.is_tensor(v):
                 static[k].copy_(v, non_blocking=True)
         for p, g in zip(self.step._params, grads):       # several bucket graphs own different gradient buffers
             p.grad = g
         graph.replay()
+        from .. import ops
+        ops.note_graph_replay(n_kernels)
         return self._finish(loss.clone())
 
 
