@@ -643,7 +643,7 @@ int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* 
                       const float* huber_c, void* stream) {
   if (int r = check_device()) return r;
   if (int r = check_loss_type(loss_type, huber_c)) return r;
-  if (layout != 0 && layout != 1) return fail(STB_ERR_ARG, "flow_mse_loss layout must be 0 (Flux) or 1 (SD3)");
+  if (layout < 0 || layout > 2) return fail(STB_ERR_ARG, "flow_mse_loss layout must be 0 (Flux), 1 (SD3) or 2 (NCHW)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   STB_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
   const long long n = (long long)B * C * Hh * Ww;
@@ -671,8 +671,8 @@ int stb_target_mse_loss(const void* pred_packed, const void* target, const float
                         const float* huber_c, void* stream) {
   if (int r = check_device()) return r;
   if (int r = check_loss_type(loss_type, huber_c)) return r;
-  if (layout != 0 && layout != 1) return fail(STB_ERR_ARG, "target_mse_loss layout must be 0 (c,dy,dx) or 1 (dy,dx,c)");
-  if ((Hh & 1) || (Ww & 1)) return fail(STB_ERR_ARG, "latent H and W must be even for 2x2 patchify");
+  if (layout < 0 || layout > 2) return fail(STB_ERR_ARG, "target_mse_loss layout must be 0 (c,dy,dx), 1 (dy,dx,c) or 2 (NCHW)");
+  if (layout != 2 && ((Hh & 1) || (Ww & 1))) return fail(STB_ERR_ARG, "latent H and W must be even for 2x2 patchify");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   STB_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
   const long long n = (long long)B * C * Hh * Ww;

@@ -503,7 +503,7 @@ flow_mse_loss_kernel(const __nv_bfloat16* __restrict__ pred_packed, const __nv_b
     const long long tok = (long long)ph * (Ww >> 1) + pw;
     // token features: Flux pack_latents order (c, dy, dx)  |  SD3 unpatchify order (dy, dx, c) ("nhwpqc->nchpwq")
     const int feat = layout == 0 ? ((c * 2 + dy) * 2 + dx) : ((dy * 2 + dx) * C + c);
-    const long long pi = ((long long)b * ((Hh >> 1) * (Ww >> 1)) + tok) * (4 * C) + feat;
+    const long long pi = layout == 2 ? i : ((long long)b * ((Hh >> 1) * (Ww >> 1)) + tok) * (4 * C) + feat;   // 2 = NCHW (UNet output)
     // target = noise - latents computed in the latent dtype (bf16 tensor), then .float()
     const float tgt = bf16r(__bfloat162float(noise[i]) - __bfloat162float(lat[i]));
     const float d = __bfloat162float(pred_packed[pi]) - tgt;
@@ -578,7 +578,7 @@ target_mse_loss_kernel(const __nv_bfloat16* __restrict__ pred_packed, const __nv
     const int ph = hh >> 1, dy = hh & 1, pw = w >> 1, dx = w & 1;
     const long long tok = (long long)ph * (Ww >> 1) + pw;
     const int feat = layout == 0 ? ((c * 2 + dy) * 2 + dx) : ((dy * 2 + dx) * C + c);
-    const long long pi = ((long long)b * ((Hh >> 1) * (Ww >> 1)) + tok) * (4 * C) + feat;
+    const long long pi = layout == 2 ? i : ((long long)b * ((Hh >> 1) * (Ww >> 1)) + tok) * (4 * C) + feat;   // 2 = NCHW (UNet output)
     const float wgt = weights ? weights[b] : 1.f;
     const float d = __bfloat162float(pred_packed[pi]) - __bfloat162float(target[i]);
     float lv, lg;

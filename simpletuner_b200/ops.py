@@ -300,7 +300,7 @@ def target_mse_loss(pred_packed, target, weights=None, want_grad: bool = True, g
     assert pred_packed.is_contiguous() and target.is_contiguous()
     _chk(pred_packed, "pred"); _chk(target, "target")
     B, Cc, Hh, Ww = target.shape
-    assert pred_packed.shape[-1] == 4 * Cc
+    assert pred_packed.shape == target.shape if layout == 2 else pred_packed.shape[-1] == 4 * Cc
     if weights is not None:
         assert weights.dtype == torch.float32 and weights.numel() == B and weights.is_cuda
         weights = weights.contiguous()

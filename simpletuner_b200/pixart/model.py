@@ -41,16 +41,16 @@ def default_config(**over) -> SimpleNamespace:
 
 class _TargetLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred_packed, target, weights, snr_weight, loss_type="l2", huber_c=None):
+    def forward(ctx, pred_packed, target, weights, snr_weight, loss_type="l2", huber_c=None, layout=1):
         loss, dpred = ops.target_mse_loss(pred_packed.contiguous(), target, weights, want_grad=True, grad_scale=snr_weight,
-                                          layout=1, loss_type=loss_type, huber_c=huber_c)
+                                          layout=layout, loss_type=loss_type, huber_c=huber_c)
         ctx.save_for_backward(dpred)
         return loss[0] * snr_weight if snr_weight != 1.0 else loss[0]
 
     @staticmethod
     def backward(ctx, g):
         (dpred,) = ctx.saved_tensors
-        return (dpred.float() * g.float()).to(dpred.dtype), None, None, None, None, None   # fp32 scale, see FlowLossFn
+        return (dpred.float() * g.float()).to(dpred.dtype), None, None, None, None, None, None   # fp32 scale, see FlowLossFn
 
 
 class PixartSigma(Flux):

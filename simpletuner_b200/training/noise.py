@@ -144,3 +144,40 @@ def compute_time_ids(intermediary_size: Sequence[int], target_size: Sequence[int
     else:
         ids = list((original_height, original_width) + tuple(crop_coordinates) + (target_height, target_width))
     return torch.tensor([ids], dtype=weight_dtype)
+
+
+def gather_conditional_pixart_size_features(examples, latents: torch.Tensor, weight_dtype, device=None) -> dict:
+    """collate.py:487-498: PixArt micro-conditioning for a (uniform-shape) batch — pixel resolution and aspect ratio."""
+    bsz = len(examples)
+    batch_height = latents.shape[2] * 8          # 1/8th scale VAE
+    batch_width = latents.shape[3] * 8
+    resolution = torch.tensor([batch_height, batch_width]).repeat(bsz, 1)
+    aspect_ratio = torch.tensor([float(batch_height / batch_width)]).repeat(bsz, 1)
+    return {"resolution": resolution.to(dtype=weight_dtype, device=device),
+            "aspect_ratio": aspect_ratio.to(dtype=weight_dtype, device=device)}
+
+
+def gather_conditional_sdxl_size_features(examples, latents, weight_dtype, refiner_aesthetic_score: Optional[float] = None) -> torch.Tensor:
+    """collate.py:501-523: per-example SDXL `add_time_ids` [B, 1, 6]; the intermediary size stands in for the original size
+    (images are resized to it before cropping); dropped-conditioning examples get zeros."""
+    if len(examples) != len(latents):
+        raise ValueError(f"Number of examples ({len(examples)}) and latents ({len(latents)}) must match.")
+    out = []
+    for idx, example in enumerate(examples):
+        time_ids = compute_time_ids(intermediary_size=tuple(example.get("intermediary_size", example.get("original_size"))),
+                                    target_size=latents[idx].shape, crop_coordinates=example["crop_coordinates"],
+                                    weight_dtype=weight_dtype, refiner_aesthetic_score=refiner_aesthetic_score)
+        if example["drop_conditioning"]:
+            time_ids = torch.zeros_like(time_ids)
+        out.append(time_ids)
+    return torch.stack(out, dim=0)
+
+
+def max_grad_value(params):
+    """Trainer._max_grad_value (trainer.py:6376-6398): `get_total_norm(gradients, inf)` over the trainable gradients, what
+    the reference stores in `self.grad_norm` whenever it does not norm-clip (:7144-7147).  Returns a device scalar (no host
+    sync), or float("-inf") when no parameter has a gradient, as the reference does."""
+    grads = [p.grad for p in params if getattr(p, "grad", None) is not None]
+    if not grads:
+        return float("-inf")
+    return torch.nn.utils.get_total_norm(grads, norm_type=float("inf"))

@@ -33,9 +33,15 @@ class TrainStep:
         self._params = [p for g in optimizer.param_groups for p in g["params"]]
         self._nonfinite = None
         self.grad_sync = grad_sync    # e.g. training.dist.FlatGradSync: called once per optimizer step, before the clip
+        self.track_grad_norm = False  # True: keep the reference's logged `grad_norm` (inf-norm unless norm-clipping) as a device scalar
+        self.grad_norm = None
 
     def _clip(self):
-        if self.max_grad_norm is None or self.max_grad_norm <= 0:
+        clipping = self.max_grad_norm is not None and self.max_grad_norm > 0
+        if self.track_grad_norm and (self.grad_clip_method != "norm" or not clipping):
+            from .noise import max_grad_value       # trainer.py:7144-7147: self.grad_norm = self._max_grad_value()
+            self.grad_norm = max_grad_value(self._params)
+        if not clipping:
             return
         grads = [p.grad for p in self._params if p.grad is not None]
         if not grads:
@@ -44,7 +50,9 @@ class TrainStep:
             torch._foreach_clamp_min_(grads, -self.max_grad_norm)
             torch._foreach_clamp_max_(grads, self.max_grad_norm)
         elif self.grad_clip_method == "norm":
-            torch.nn.utils.clip_grad_norm_(self._params, self.max_grad_norm)
+            gn = torch.nn.utils.clip_grad_norm_(self._params, self.max_grad_norm)
+            if self.track_grad_norm:
+                self.grad_norm = gn
         else:
             raise ValueError(f"unknown grad_clip_method {self.grad_clip_method}")
 
