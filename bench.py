@@ -190,6 +190,156 @@ def synth_batch_sd3(B, device, hw, pinned=False, seed=0, s_txt=SD3_S_TXT, joint=
     return {k: v.to(device) for k, v in b.items()}
 
 
+# PixArt-Sigma XL (BASELINE configs[4]: "PixArt-Sigma DiT LoRA rank=32, mixed aspect buckets 512-1536, grad-accum=4, 8xB200")
+PIXART_SIGMA = dict(num_attention_heads=16, attention_head_dim=72, in_channels=4, out_channels=8, num_layers=28, cross_attention_dim=1152,
+                    sample_size=128, caption_channels=4096)
+PIXART_BUCKETS = [(64, 64), (96, 128), (128, 128), (112, 144), (160, 160), (192, 192), (128, 96), (144, 112)]   # latent (h, w): 512^2 .. 1536^2 px
+PIXART_S_TXT = 300
+
+
+def pixart_tf_per_sample(hw, s_txt=PIXART_S_TXT):
+    """LoRA step (fwd + dgrad + attention backward) of one PixArt-Sigma sample, SURVEY.md 8d counting."""
+    D, L = 1152, 28
+    S = (hw[0] // 2) * (hw[1] // 2)
+    lin = L * (2 * S * (4 * D * D + 2 * D * D + 8 * D * D) + 2 * s_txt * 2 * D * D)
+    attn = L * (4 * S * S * D + 4 * S * s_txt * D)
+    return (2 * lin + 3 * attn) * 1e-12
+
+
+def build_pixart_lora(device, rank=32, seed=0, tiny=False):
+    from simpletuner_b200.pixart.model import PixartSigma, default_config
+    from simpletuner_b200.pixart.transformer import PixArtTransformer2DModel
+
+    kw = dict(PIXART_SIGMA)
+    if tiny:
+        kw.update(num_attention_heads=4, num_layers=2, cross_attention_dim=288, caption_channels=96)
+    with torch.device(device):
+        m = PixArtTransformer2DModel(**kw)
+    g = torch.Generator(device=device).manual_seed(seed)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if name.endswith(".bias"):
+                p.normal_(0.0, 0.01, generator=g)
+            else:
+                p.normal_(0.0, 0.02, generator=g)
+    w = PixartSigma(default_config(lora_rank=rank), transformer=m, device=device)
+    w.add_lora_adapter()
+    with torch.no_grad():
+        for lin in m.lora_linears().values():
+            lin.lora_B["default"].weight.normal_(0.0, 0.02, generator=g)
+    return w
+
+
+def synth_batch_pixart(B, device, hw, pinned=False, seed=0, s_txt=PIXART_S_TXT, caption=4096):
+    g = torch.Generator().manual_seed(seed)
+    mask = torch.ones(B, s_txt)
+    for b in range(B):   # tokenizer padding on the right, a different length per sample
+        mask[b, 40 + int(torch.randint(0, s_txt - 40, (1,), generator=g)):] = 0
+    b_ = {"latent_batch": torch.randn(B, 4, hw[0], hw[1], generator=g).bfloat16(),
+          "prompt_embeds": torch.randn(B, s_txt, caption, generator=g).bfloat16(), "encoder_attention_mask": mask}
+    if pinned:
+        return {k: v.pin_memory() for k, v in b_.items()}
+    return {k: v.to(device) for k, v in b_.items()}
+
+
+def vae_conv_flops(block_out=(128, 256, 512, 512), layers=2, latent=16, H=1024, W=1024):
+    """Algorithmic FLOPs of one AutoencoderKL encode (~4.9 TF per 1024^2 image)."""
+    ch = block_out
+    fl = 2 * 27 * ch[0] * H * W
+    prev, h, w = ch[0], H, W
+    for i, c in enumerate(ch):
+        for l in range(layers):
+            cin = prev if l == 0 else c
+            fl += 2 * 9 * cin * c * h * w + 2 * 9 * c * c * h * w + (2 * cin * c * h * w if cin != c else 0)
+        prev = c
+        if i != len(ch) - 1:
+            h, w = h // 2, w // 2
+            fl += 2 * 9 * c * c * h * w
+    c, S = ch[-1], h * w
+    fl += 4 * (2 * 9 * c * c * S) + 4 * 2 * c * c * S + 2 * 2 * S * S * c
+    fl += 2 * 9 * c * 2 * latent * S
+    return fl
+
+
+def run_vae(args):
+    """`--config vae_encode` (the path BASELINE configs[3] runs on the fly): Flux AutoencoderKL encode ->
+    latent_dist.sample() -> scale_vae_latents_for_cache of B x 1024^2 images per step; e2e from pinned host pixels with the
+    cached latents read back to the host."""
+    from simpletuner_b200 import ops
+    from simpletuner_b200.vae.autoencoder import AutoencoderKL
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    B = args.batch or 4
+    res = 256 if args.tiny else 1024
+    with torch.device(device):
+        vae = AutoencoderKL()
+    g = torch.Generator(device=device).manual_seed(0)
+    with torch.no_grad():
+        for n, p in vae.named_parameters():
+            p.normal_(0.0, 0.02, generator=g) if p.dim() > 1 else (p.fill_(1.0) if "norm" in n and n.endswith("weight") else p.zero_())
+    px_dev = [(torch.rand(B, 3, res, res, device=device, generator=g) * 2 - 1).bfloat16() for _ in range(2)]
+    px_host = [(torch.rand(B, 3, res, res) * 2 - 1).bfloat16().pin_memory() for _ in range(2)]
+    out_host = torch.empty(B, 16, res // 8, res // 8, dtype=torch.bfloat16).pin_memory()
+
+    def region(fn, n):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    dev_step = lambda i: vae.encode_scaled(px_dev[i % 2])
+    e2e_step = lambda i: out_host.copy_(vae.encode_scaled(px_host[i % 2].to(device, non_blocking=True)))
+    for i in range(args.warmup):
+        dev_step(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    ms = region(dev_step, args.steps)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_step(0)
+    ms_e2e = region(e2e_step, args.steps)
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        tf_img = vae_conv_flops(H=res, W=res) * 1e-12
+        ach = tf_img * B / (ms / args.steps * 1e-3)
+        line = {"metric": "images/sec AutoencoderKL latent encode 1024^2 (VAE cache path)", "value": B * world * args.steps / (ms * 1e-3), "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init Flux AutoencoderKL, U(-1,1) pixels)",
+                "config": {"workload": f"Flux AutoencoderKL encode -> latent_dist.sample() -> scale_vae_latents_for_cache, {B} x {res}^2 images per step (caching/vae.py:1293-1355)",
+                           "config_name": "vae_encode", "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                           "l2_policy": "inputs larger than L2 (activations of one 1024^2 image: 0.27 GB at 128 channels)"},
+                "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 3 * res * res * 2,
+                        "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "tensor", "kernel": "whole encode (implicit-GEMM 3x3 convs dominate)", "achieved": round(ach, 1), "peak": peak_tf,
+                             "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4), "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})",
+                             "traffic": None},
+                "model_tflops": {"algorithmic_tf_per_image": round(tf_img, 2), "achieved_tflops_per_gpu": round(ach, 1)},
+                "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def batch_bytes(b):
     return int(sum(v.numel() * v.element_size() for v in b.values()))
 
@@ -456,6 +606,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     sd3 = args.config == "sd3_fullft"
+    pix = args.config == "pixart_lora"
     B = args.batch if args.batch else (8 if sd3 else 4)
     cfg_over = None
     hw, s_txt = 128, S_TXT
@@ -466,6 +617,8 @@ def run_b200(args):
         wrapper = build_sd3_fullft(device, seed=0, tiny=args.tiny)
         if args.dp == "auto":
             args.dp = "flat"     # CUDA-graph replay of fwd + bwd, then one flat 5 GB all-reduce; `--dp ddp` = torch DDP buckets (eager)
+    elif pix:
+        wrapper = build_pixart_lora(device, rank=32, seed=0, tiny=args.tiny)
     else:
         wrapper = build_model(device, cfg_over, rank=16, seed=0)
     if args.gradient_checkpointing:   # non-default: the reference's --gradient_checkpointing memory / time trade-off
@@ -482,7 +635,9 @@ def run_b200(args):
     if world > 1 and args.dp == "flat":
         from simpletuner_b200.training.dist import FlatGradSync
         grad_sync = FlatGradSync(params)
-    step = TrainStep(wrapper, opt, max_grad_norm=2.0, grad_clip_method="value", grad_sync=grad_sync)
+    accum = 4 if pix else 1      # BASELINE configs[4]: grad-accum = 4 (a "step" of the PixArt line is one optimizer step = 4 micro-batches)
+    step = TrainStep(wrapper, opt, max_grad_norm=(0.01 if pix else 2.0), grad_clip_method="value", grad_sync=grad_sync,
+                     gradient_accumulation_steps=accum)
     use_graph = args.graph == "on" or (args.graph == "auto" and sd3 and args.dp != "ddp")
     if use_graph:
         from simpletuner_b200.training.step import GraphedTrainStep
@@ -498,6 +653,12 @@ def run_b200(args):
         nb = len(bks)
         dev_batches = [synth_batch_sd3(B, device, bks[(i + rank) % nb], seed=100 + rank * 10 + i, **kw3) for i in range(nb)]
         host_batches = [synth_batch_sd3(B, device, bks[(i + rank) % nb], pinned=True, seed=200 + rank * 10 + i, **kw3) for i in range(nb)]
+    elif pix:
+        kwp = dict(s_txt=40, caption=96) if args.tiny else {}
+        bks = [(16, 16), (24, 16), (16, 24), (32, 32)] if args.tiny else PIXART_BUCKETS
+        nb = len(bks)
+        dev_batches = [synth_batch_pixart(B, device, bks[(i + 3 * rank) % nb], seed=100 + rank * 10 + i, **kwp) for i in range(nb)]
+        host_batches = [synth_batch_pixart(B, device, bks[(i + 3 * rank) % nb], pinned=True, seed=200 + rank * 10 + i, **kwp) for i in range(nb)]
     else:
         dev_batches = [synth_batch(B, device, seed=100 + rank * 10 + i, hw=hw, s_txt=s_txt, joint=joint, pooled=pooled) for i in range(2)]
         host_batches = [synth_batch(B, device, pinned=True, seed=200 + rank * 10 + i, hw=hw, s_txt=s_txt, joint=joint, pooled=pooled) for i in range(2)]
@@ -523,7 +684,8 @@ def run_b200(args):
 
     # ---- device-resident arm
     def dev_step(i):
-        step({k: v for k, v in dev_batches[i % nbat].items()})
+        for a_ in range(accum):
+            step({k: v for k, v in dev_batches[(i * accum + a_) % nbat].items()})
 
     for i in range(args.warmup):
         dev_step(i)
@@ -540,8 +702,9 @@ def run_b200(args):
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def e2e_step(i):
-        hb = host_batches[i % nbat]
-        ld = step({k: v.to(device, non_blocking=True) for k, v in hb.items()})
+        for a_ in range(accum):
+            hb = host_batches[(i * accum + a_) % nbat]
+            ld = step({k: v.to(device, non_blocking=True) for k, v in hb.items()})
         loss_host.copy_(ld, non_blocking=False)  # device->host read of the step's result (synchronises)
 
     for i in range(max(1, args.warmup // 2)):
@@ -551,13 +714,13 @@ def run_b200(args):
     # ---- per-kernel pass (extra step, outside both timed regions)
     # (every rank runs it: the step contains the DDP gradient all-reduce)
     eager_step = step.step if use_graph else step
-    kern = profile_kernels(lambda b: eager_step(b), dict(dev_batches[0])) if not sd3 else None
+    kern = profile_kernels(lambda b: eager_step(b), dict(dev_batches[0])) if not (sd3 or pix) else None
     barrier()
     mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        imgs = B * world * args.steps
+        imgs = B * world * args.steps * accum
         value = imgs / (ms_total * 1e-3)
         e2e_v = imgs / (ms_e2e * 1e-3)
         ms_step = ms_total / args.steps
@@ -580,6 +743,12 @@ def run_b200(args):
                     "avg_launch_ms": gb["avg_ms"], "tflop_per_launch": gb["tflop_per_launch"], "launches_per_step": gb["launches"]}
         tf_sample = TF_STEP_SAMPLE
         metric, workload = METRIC, WORKLOAD
+        if pix:
+            tf_sample = sum(pixart_tf_per_sample(hw_) for hw_ in PIXART_BUCKETS) / len(PIXART_BUCKETS)
+            metric = "images/sec PixArt-Sigma LoRA r32 bf16, mixed aspect buckets 512-1536, grad-accum 4"
+            workload = ("PixArt-Sigma XL (28 blocks, D=1152, 16x72 heads) LoRA rank 32 on attention projections, bf16, mixed aspect buckets "
+                        "512^2..1536^2 (latents 64x64 .. 192x192) + 300 caption tokens with random-length masks, epsilon prediction, "
+                        "one step = 4 micro-batches (grad-accum 4) + value-clip (0.01) + adamw_bf16")
         if sd3:
             tf_sample = sum(sd3_tf_per_sample(hw_) for hw_ in SD3_BUCKETS) / len(SD3_BUCKETS)
             metric = "images/sec SD3.5-medium full fine-tune bf16 512^2 buckets"
@@ -592,7 +761,8 @@ def run_b200(args):
             "data": "synthetic (random-init Flux.1-dev architecture; seeded N(0,1) cached latents + T5/CLIP embeds)",
             "config": {
                 "workload": workload, "config_name": args.config,
-                "global_batch": B * world, "per_gpu_batch": B, "seq_len": (S_IMG + S_TXT) if not sd3 else 1024 + SD3_S_TXT,
+                "global_batch": B * world * accum, "per_gpu_batch": B, "grad_accum": accum,
+                "seq_len": (S_IMG + S_TXT) if not (sd3 or pix) else (1024 + SD3_S_TXT if sd3 else "1024..9216 (+300 cross)"),
                 "parallelism": f"dp{world}", "grad_exchange": (None if world == 1 else args.dp), "cuda_graph": bool(use_graph),
                 "activation_recompute": ("every block re-run in backward (--gradient-checkpointing)" if args.gradient_checkpointing else
                                          "none (block-native minimal saves; reference default would recompute every block)"),
@@ -607,17 +777,17 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": roof,
             "model_tflops": {"algorithmic_tf_per_image": round(tf_sample, 2),
-                             "achieved_tflops_per_gpu": round(tf_sample * B / (ms_step * 1e-3), 1),
-                             "frac_of_peak": round(tf_sample * B / (ms_step * 1e-3) / peak_tf, 4)} if not args.tiny else None,
+                             "achieved_tflops_per_gpu": round(tf_sample * B * accum / (ms_step * 1e-3), 1),
+                             "frac_of_peak": round(tf_sample * B * accum / (ms_step * 1e-3) / peak_tf, 4)} if not args.tiny else None,
             "kernels": kern, "peak_mem_gb": round(mem_gb, 1),
         }
-        if sd3 and roof is None:
-            ach = tf_sample * B / (ms_step * 1e-3)
-            roof = {"bound": "tensor", "kernel": "whole step (GEMM + full-rank wgrad + attention), algorithmic 3x forward", "achieved": round(ach, 1),
+        if (sd3 or pix) and roof is None:
+            ach = tf_sample * B * accum / (ms_step * 1e-3)
+            roof = {"bound": "tensor", "kernel": "whole step, algorithmic FLOPs (SURVEY 8d counting)", "achieved": round(ach, 1),
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4), "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})",
                     "traffic": None}
             line["roofline"] = roof
-        if world == 1 and not args.no_eager_baseline and not args.tiny and not sd3:
+        if world == 1 and not args.no_eager_baseline and not args.tiny and not (sd3 or pix):
             try:   # informational: the reference's default eager path (SDPA + per-block checkpointing) on this GPU, same batch
                 torch.cuda.empty_cache()
                 ms_eager = time_eager_gpu(wrapper, device, dev_batches, opt)
@@ -628,7 +798,7 @@ def run_b200(args):
                             "gradient_checkpointing=true), same parameters / batch / optimizer; 3 timed steps after 2 warm-up"}
             except Exception as e:  # noqa
                 line["gpu_eager_baseline"] = {"error": str(e)[:300]}
-        if world == 1 and not args.no_cpu_baseline and not sd3:
+        if world == 1 and not args.no_cpu_baseline and not (sd3 or pix):
             try:
                 cb = cpu_baseline_sample()
                 line["cpu_baseline"] = {"value": cb["images_per_sec"], "unit": UNIT, "cores": cb["threads"], "kind": "port",
@@ -649,8 +819,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 4 for flux_lora, 8 for sd3_fullft)")
-    ap.add_argument("--config", default="flux_lora", choices=["flux_lora", "sd3_fullft"],
-                    help="flux_lora = BASELINE configs[1] (the headline metric); sd3_fullft = configs[2] (SD3.5-medium full fine-tune, DDP)")
+    ap.add_argument("--config", default="flux_lora", choices=["flux_lora", "sd3_fullft", "pixart_lora", "vae_encode"],
+                    help="flux_lora = BASELINE configs[1] (the headline metric); sd3_fullft = configs[2] (SD3.5-medium full fine-tune); "
+                         "pixart_lora = configs[4] (PixArt-Sigma LoRA r32, mixed buckets, grad-accum 4); vae_encode = the VAE cache path")
     ap.add_argument("--tiny", action="store_true", help="plumbing check on a toy config (not a benchmark value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the informational eager-torch GPU baseline (N=1 only)")
@@ -670,6 +841,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "vae_encode":
+        run_vae(args)
     else:
         run_b200(args)
 
