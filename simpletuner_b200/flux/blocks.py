@@ -96,8 +96,8 @@ def pack_lora(params: List[Optional[Tuple[torch.Tensor, torch.Tensor]]], n_out: 
     r = present[0][0].shape[0]
     rp = (r + 7) // 8 * 8   # rank padded with zero rows/columns so every TMA row stride is 16-byte aligned
     M = len(params)
-    if M * rp > 128:
-        raise NotImplementedError(f"fused LoRA group of {M} x rank {r} exceeds the 128-wide rank block")
+    if rp > 128:
+        raise NotImplementedError(f"LoRA rank {r} exceeds the 128-wide rank block of the weight-gradient kernel")
     a_stack = torch.zeros((M * rp, k_in), device=device, dtype=dtype)
     b_ext = torch.zeros((M * n_out, M * rp), device=device, dtype=dtype)
     members: List[Optional[int]] = []
@@ -153,17 +153,29 @@ def _lora_grads(pack: LoraPack, x: torch.Tensor, t_down: torch.Tensor, dy: torch
     """dA_stack [R, K] = T'^T x  (T' = dy B_ext, scaling already inside);  dB_ext^T [R, N] = T^T dy.
     With dropout dA_m contracts T'_m with the SAME masked copy of x the forward used (masks regenerated, not stored)."""
     R = pack.a_stack.shape[0]
-    if drop is None:
+    wide = R > 128        # ranks above 40: the fused q|k|v rank block no longer fits one 128-wide weight-gradient tile
+    if drop is None and not wide:
         d_a = ops.skinny_tn(t_up, x)        # [R, K] fp32
+    elif drop is None:
+        d_a = torch.zeros((R, x.shape[-1]), device=x.device, dtype=torch.float32)
+        for m, sl in _member_slices(pack):
+            ops.skinny_tn(t_up[:, :, sl], x, out=d_a[sl])
     else:
         d_a = torch.zeros((R, x.shape[-1]), device=x.device, dtype=torch.float32)
         xm = ops.dropout_expand(x, len(pack.members), drop.p, drop.seed, drop.stream)
         for m, sl in _member_slices(pack):
             ops.skinny_tn(t_up[:, :, sl], xm[m], out=d_a[sl])
         del xm
-    d_bt = ops.skinny_tn(t_down, dy)    # [R, N] fp32
-    out = []
     r, rp = pack.rank, (pack.rank_padded or pack.rank)
+    if not wide:
+        d_bt = ops.skinny_tn(t_down, dy)    # [R, N] fp32 (only the block diagonal is used)
+    else:                                   # per member, against its own n_out columns of dy only
+        d_bt = torch.zeros((R, dy.shape[-1]), device=x.device, dtype=torch.float32)
+        for m, sl in _member_slices(pack):
+            blk = torch.zeros((rp, pack.n_out), device=x.device, dtype=torch.float32)
+            ops.skinny_tn(t_down[:, :, sl], dy[:, :, m * pack.n_out:(m + 1) * pack.n_out], out=blk)
+            d_bt[sl, m * pack.n_out:(m + 1) * pack.n_out] = blk
+    out = []
     for m, idx in enumerate(pack.members):
         if idx is None:
             out.append((None, None))

@@ -429,8 +429,8 @@ class FluxTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
         if rank is None:
             raise ValueError("LoRA rank is required")
         lora_dropout = self._check_dropout_p(lora_dropout)
-        if not 1 <= rank <= 40:
-            raise NotImplementedError("fused LoRA path supports rank 1..40 (three fused projections share a 128-wide rank block)")
+        if not 1 <= rank <= 128:
+            raise NotImplementedError("fused LoRA path supports rank 1..128 (one 128-wide rank block per adapted Linear)")
         lora_alpha = float(lora_alpha) if lora_alpha is not None else float(rank)  # common.py:1090-1093
         targets = list(target_modules) if target_modules is not None else FLUX_LORA_TARGETS["all"]
         supported = set(FLUX_LORA_TARGETS["all"])

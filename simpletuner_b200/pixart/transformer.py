@@ -393,8 +393,8 @@ class PixArtTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
             target_modules = getattr(lora_config, "target_modules", target_modules)
             lora_dropout = getattr(lora_config, "lora_dropout", lora_dropout)
         lora_dropout = self._check_dropout_p(lora_dropout)
-        if not 1 <= rank <= 40:
-            raise NotImplementedError("fused LoRA path supports rank 1..40 (three fused projections share a 128-wide rank block)")
+        if not 1 <= rank <= 128:
+            raise NotImplementedError("fused LoRA path supports rank 1..128 (one 128-wide rank block per adapted Linear)")
         lora_alpha = float(lora_alpha) if lora_alpha is not None else float(rank)
         targets = list(target_modules) if target_modules is not None else PIXART_LORA_TARGETS
         n = 0

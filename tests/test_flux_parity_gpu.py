@@ -68,7 +68,7 @@ def test_lora_disabled_equals_base_model():
     assert torch.equal(b, c)
 
 
-@pytest.mark.parametrize("rank", [4, 32])
+@pytest.mark.parametrize("rank", [4, 32, 64, 128])
 def test_flux_step_parity_other_ranks(rank):
     # rank 4 is zero-padded to 8 inside the packed LoRA stacks; rank 32 -> a 96-wide fused q|k|v rank block
     _assert(FP.run_parity(cfg=FP.small_config(layers=1, single=1), rank=rank, seed=7))
