@@ -679,9 +679,13 @@ def run_b200(args):
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
         if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            per_rank_ms.append([round(float(t.item()) / n, 2) for t in every])   # evidence: which rank is the slow one
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    per_rank_ms = []
     # ---- device-resident arm
     def dev_step(i):
         for a_ in range(accum):
@@ -780,6 +784,9 @@ def run_b200(args):
                              "achieved_tflops_per_gpu": round(tf_sample * B * accum / (ms_step * 1e-3), 1),
                              "frac_of_peak": round(tf_sample * B * accum / (ms_step * 1e-3) / peak_tf, 4)} if not args.tiny else None,
             "kernels": kern, "peak_mem_gb": round(mem_gb, 1),
+            # ms/step of every rank for the device-resident region (the reported time is the max): independent replicas with
+            # no collective inside backward, so the spread is the GPUs' own power-capped clocks, not communication
+            "per_rank_ms_per_step": per_rank_ms[0] if per_rank_ms else None,
         }
         if (sd3 or pix) and roof is None:
             ach = tf_sample * B * accum / (ms_step * 1e-3)

@@ -29,6 +29,11 @@ import torch
 from .. import ops
 
 EPS = 1e-6
+# Keep the post-norm / post-RoPE q, k of every block for the backward instead of re-running the RMSNorm + RoPE pass there:
+# +2 B S D bytes per block (Flux.1-dev, B = 4: +13 GB over 57 blocks, 100 -> 113 GB of 180 GB) for one HBM-bound kernel less
+# per block in backward.  STB_SAVE_QK=0 restores the recompute (larger batches / buckets).
+import os as _os
+SAVE_QK = _os.environ.get("STB_SAVE_QK", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -238,10 +243,11 @@ def _qk_fwd(qkv, D, H, hd, img_plan: AttnPlan, txt_plan: Optional[AttnPlan], S_t
     return ops.qk_rmsnorm_rope_fwd(qkv, D, H, hd, img_plan.norm_q, img_plan.norm_k, tq, tk, S_txt, cos, sin, EPS)
 
 
-def _attn_core_bwd(qkv, o, d_o, lse, D, H, hd, img_plan, txt_plan, S_txt, cos, sin):
-    """Returns d_qkv [B, S, 3D] given d_o; recomputes q, k."""
+def _attn_core_bwd(qkv, o, d_o, lse, D, H, hd, img_plan, txt_plan, S_txt, cos, sin, qk=None):
+    """Returns d_qkv [B, S, 3D] given d_o.  `qk` = the (q, k) pair saved by the forward (180 GB of HBM: spending 2 B S D
+    bytes per block is cheaper than re-running the RMSNorm + RoPE pass in backward); recomputed when absent."""
     B, S, _ = qkv.shape
-    q, k = _qk_fwd(qkv, D, H, hd, img_plan, txt_plan, S_txt, cos, sin)
+    q, k = qk if qk is not None else _qk_fwd(qkv, D, H, hd, img_plan, txt_plan, S_txt, cos, sin)
     v = qkv[:, :, 2 * D:].unflatten(-1, (H, hd))
     d_qkv = torch.empty_like(qkv)
     dv = d_qkv[:, :, 2 * D:].unflatten(-1, (H, hd))
@@ -325,7 +331,9 @@ class DoubleBlockFn(torch.autograd.Function):
         q, k = _qk_fwd(qkv, D, H, hd, ia, ta, S_txt, cos, sin)
         v = qkv[:, :, 2 * D:].unflatten(-1, (H, hd))
         o, lse = ops.attn_fwd(q, k, v)
-        del q, k
+        keep_qk = SAVE_QK and q.data_ptr() != qkv.data_ptr()      # (views of qkv when the model has neither norm nor RoPE)
+        if not keep_qk:
+            del q, k
         o = o.view(B, S, D)
         h1 = torch.empty_like(h)
         h2 = torch.empty_like(h)
@@ -379,13 +387,15 @@ class DoubleBlockFn(torch.autograd.Function):
         keep = lambda t: t if t is not None else E
         ctx.save_for_backward(h, mod_img, mod_txt, keep(cos), keep(sin), qkv, o, lse, h1, keep(mlp_pre["txt"]), mlp_pre["img"],
                               keep(small["txt_t_qkv"]), keep(small["img_t_qkv"]), keep(small["txt_t_out"]), keep(small["img_t_out"]),
-                              keep(qkv2), keep(o2), keep(lse2), keep(small.get("a2_t_qkv")), keep(small.get("a2_t_out")))
+                              keep(qkv2), keep(o2), keep(lse2), keep(small.get("a2_t_qkv")), keep(small.get("a2_t_out")),
+                              q if keep_qk else E, k if keep_qk else E)
         return h2
 
     @staticmethod
     def backward(ctx, dh2):
         (h, mod_img, mod_txt, cos, sin, qkv, o, lse, h1, pre_txt, pre_img, t_qkv_txt, t_qkv_img, t_out_txt, t_out_img,
-         qkv2, o2, lse2, t_qkv_a2, t_out_a2) = ctx.saved_tensors
+         qkv2, o2, lse2, t_qkv_a2, t_out_a2, q_saved, k_saved) = ctx.saved_tensors
+        qk_saved = (q_saved, k_saved) if q_saved.numel() else None
         cos = cos if cos.numel() else None
         sin = sin if sin.numel() else None
         st = ctx.st
@@ -449,7 +459,8 @@ class DoubleBlockFn(torch.autograd.Function):
                 del nh2a
             del d_qkv2
         # ---- joint attention core
-        d_qkv = _attn_core_bwd(qkv, o, d_o, lse, D, H, hd, plans["img_attn"], plans["txt_attn"], S_txt, cos, sin)
+        d_qkv = _attn_core_bwd(qkv, o, d_o, lse, D, H, hd, plans["img_attn"], plans["txt_attn"], S_txt, cos, sin, qk=qk_saved)
+        del qk_saved, q_saved, k_saved
         dh = torch.empty_like(h)
         for name, sl, mod, base, pre, t_qkv, t_out in streams:
             ap = plans[name + "_attn"]
@@ -500,7 +511,8 @@ class SingleBlockFn(torch.autograd.Function):
         q, k = ops.qk_rmsnorm_rope_fwd(qkv, D, H, hd, ap.norm_q, ap.norm_k, None, None, 0, cos, sin, EPS)
         v = qkv[:, :, 2 * D:].unflatten(-1, (H, hd))
         o, lse = ops.attn_fwd(q, k, v)
-        del q, k
+        if not SAVE_QK:
+            del q, k
         o = o.view(B, S, D)
         pre = torch.empty((B, S, 4 * D), device=dev, dtype=torch.bfloat16)
         act = ops.gemm([nh], [mp.w1], mp.b1, epi=ops.EPI_GELU, aux=pre)
@@ -512,12 +524,15 @@ class SingleBlockFn(torch.autograd.Function):
         ctx.st = st
         ctx.pack = pk
         ctx.lora_present = [x is not None for x in lora]
-        ctx.save_for_backward(h, mod, cos, sin, qkv, o, lse, pre, t_qkv if t_qkv is not None else h.new_empty(0))
+        E = h.new_empty(0)
+        ctx.save_for_backward(h, mod, cos, sin, qkv, o, lse, pre, t_qkv if t_qkv is not None else E,
+                              q if SAVE_QK else E, k if SAVE_QK else E)
         return h_out
 
     @staticmethod
     def backward(ctx, dh_out):
-        h, mod, cos, sin, qkv, o, lse, pre, t_qkv = ctx.saved_tensors
+        h, mod, cos, sin, qkv, o, lse, pre, t_qkv, q_saved, k_saved = ctx.saved_tensors
+        qk_saved = (q_saved, k_saved) if q_saved.numel() else None
         st = ctx.st
         pk: Optional[LoraPack] = ctx.pack
         B, S, D = h.shape
@@ -529,8 +544,8 @@ class SingleBlockFn(torch.autograd.Function):
         d_o = ops.gemm([g], [mp.w2_t[:D]], None)
         d_pre = ops.gemm([g], [mp.w2_t[D:]], None, epi=ops.EPI_MUL_DGELU, aux=pre)
         del g
-        d_qkv = _attn_core_bwd(qkv, o, d_o, lse, D, H, hd, ap, None, 0, cos, sin)
-        del d_o
+        d_qkv = _attn_core_bwd(qkv, o, d_o, lse, D, H, hd, ap, None, 0, cos, sin, qk=qk_saved)
+        del d_o, qk_saved, q_saved, k_saved
         grads: List[Optional[torch.Tensor]] = [None] * 6
         # d_nh = d_pre W_mlp + d_qkv W_qkv (+ LoRA)  — one GEMM, two/three K-segments
         if pk is None:
