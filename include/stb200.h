@@ -183,11 +183,15 @@ int stb_flow_mse_loss(const void* pred_packed, const void* latents, const void* 
  *               doubles (Python floats): the derived fp32 scalars are formed exactly as the eager path forms them
  *   rnd       : optional device int32 [4][rnd_plane] 16-bit random integers in the reference's draw order (exp_avg, shift,
  *               p, shift) with per-tensor offsets rnd_off[T] — parity tests; NULL = counter-based generator keyed by `seed`
+ *   grad_clamp: > 0 fuses the default element clamp of the gradients (`grad_clip_method = "value"`, trainer.py:7188-7195)
+ *               into the read of `grad` (the stored gradient is left untouched); 0 = off
+ *   ema_shadow: optional device int64 [T] pointers to bf16 EMA shadows; with it the kernel also applies EMAModel.step's
+ *               `shadow -= ema_one_minus_decay * (shadow - p_new)` (helpers/training/ema.py:352-420); NULL = off
  * ------------------------------------------------------------------------------------------- */
 int stb_adamw_bf16_multi(const long long* ptrs, const long long* sizes, const float* decay, const int* blk_tensor,
                          const long long* blk_off, int num_blocks, int T, double beta1, double beta2, double step, double lr,
                          double eps, const int* rnd, const long long* rnd_off, long long rnd_plane, unsigned long long seed,
-                         void* stream);
+                         double grad_clamp, const long long* ema_shadow, double ema_one_minus_decay, void* stream);
 int stb_adamw_bf16_chunk(void);
 
 /* ---------------------------------------------------------------------------------------------

@@ -685,7 +685,7 @@ int stb_target_mse_loss(const void* pred_packed, const void* target, const float
 int stb_adamw_bf16_multi(const long long* ptrs, const long long* sizes, const float* decay, const int* blk_tensor,
                          const long long* blk_off, int num_blocks, int T, double beta1, double beta2, double step, double lr,
                          double eps, const int* rnd, const long long* rnd_off, long long rnd_plane, unsigned long long seed,
-                         void* stream) {
+                         double grad_clamp, const long long* ema_shadow, double ema_one_minus_decay, void* stream) {
   if (int r = check_device()) return r;
   if (!ptrs || !sizes || !decay || !blk_tensor || !blk_off || num_blocks < 1 || T < 1) return fail(STB_ERR_ARG, "adamw_bf16_multi: bad tables");
   if (!(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || eps < 0.0) return fail(STB_ERR_ARG, "adamw_bf16_multi: bad hyper-parameters");
@@ -693,8 +693,11 @@ int stb_adamw_bf16_multi(const long long* ptrs, const long long* sizes, const fl
   // are formed in double there and only then become the fp32 scalars of the eager kernels
   const float alpha1 = float(1.0 - beta1), alpha2 = float(1.0 - beta2);
   const float value = float(-lr * std::sqrt(1.0 - std::pow(beta2, step)));
+  if (!(grad_clamp >= 0.0) || !(ema_one_minus_decay >= 0.0 && ema_one_minus_decay <= 1.0))
+    return fail(STB_ERR_ARG, "adamw_bf16_multi: grad_clamp must be >= 0 (0 = off) and 1 - ema decay in [0, 1]");
   stb::adamw_bf16_multi_kernel<<<num_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      ptrs, sizes, decay, blk_tensor, blk_off, T, float(beta1), float(beta2), alpha1, alpha2, value, float(eps), rnd, rnd_off, rnd_plane, seed);
+      ptrs, sizes, decay, blk_tensor, blk_off, T, float(beta1), float(beta2), alpha1, alpha2, value, float(eps), rnd, rnd_off, rnd_plane, seed,
+      float(grad_clamp), ema_shadow, float(ema_one_minus_decay));
   STB_LAUNCH_CHECK("adamw_bf16_multi");
   return 0;
 }

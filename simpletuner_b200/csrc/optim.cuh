@@ -26,11 +26,17 @@ __device__ __forceinline__ float stochastic_bf16(float x, uint32_t rnd16) {
 constexpr int OPT_CHUNK = 256 * 8;   // elements per block
 
 // ptrs: [5][T] device pointers (p, grad, exp_avg, exp_avg_sq, shift), all bf16 with sizes[t] elements
+// Two neighbours of the optimizer step ride along, each an extra pass over the same tensors in the reference:
+//   grad_clamp > 0 : the default `grad_clip_method = "value"` element clamp (trainer.py:7188-7195, clip_grad_value_)
+//                    applied to the gradient as it is read (bf16 result of clamp(g, -c, c), NaN kept);
+//   ema != nullptr : EMAModel.step's foreach update `shadow -= (1 - decay) * (shadow - p_new)` (ema.py:352-420) on
+//                    bf16 shadows, rounding points of the two eager kernels kept (bf16 difference, then fma).
 __global__ void __launch_bounds__(256)
 adamw_bf16_multi_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ sizes, const float* __restrict__ decay,
                         const int* __restrict__ blk_tensor, const long long* __restrict__ blk_off, int T, float beta1,
                         float beta2, float alpha1, float alpha2, float value, float eps, const int* __restrict__ rnd,
-                        const long long* __restrict__ rnd_off, long long rnd_plane, unsigned long long seed) {
+                        const long long* __restrict__ rnd_off, long long rnd_plane, unsigned long long seed, float grad_clamp,
+                        const long long* __restrict__ ema, float ema_alpha) {
   const int t = blk_tensor[blockIdx.x];
   const long long n = sizes[t];
   const long long i0 = blk_off[blockIdx.x];
@@ -39,11 +45,17 @@ adamw_bf16_multi_kernel(const long long* __restrict__ ptrs, const long long* __r
   __nv_bfloat16* m = reinterpret_cast<__nv_bfloat16*>(ptrs[2 * T + t]);
   __nv_bfloat16* v = reinterpret_cast<__nv_bfloat16*>(ptrs[3 * T + t]);
   __nv_bfloat16* s = reinterpret_cast<__nv_bfloat16*>(ptrs[4 * T + t]);
+  __nv_bfloat16* e = ema ? reinterpret_cast<__nv_bfloat16*>(ema[t]) : nullptr;
   const float dec = decay[t];
   const long long roff = rnd_off ? rnd_off[t] : 0;
   // one element of the update, shared by the vector and the scalar path
+  auto clampg = [&](float gv) {
+    return (grad_clamp > 0.f && gv == gv) ? bf16r(fminf(fmaxf(gv, -grad_clamp), grad_clamp)) : gv;
+  };
+  auto ema_update = [&](float ev, float p_new) { return bf16r(fmaf(-ema_alpha, bf16r(__fsub_rn(ev, p_new)), ev)); };
   auto update = [&](long long i, float gv, float pv, float mv, float vv, float sv, float& p_o, float& m_o, float& v_o, float& s_o) {
     uint32_t r0, r1, r2, r3;
+    gv = clampg(gv);
     if (rnd) {
       r0 = uint32_t(rnd[0 * rnd_plane + roff + i]), r1 = uint32_t(rnd[1 * rnd_plane + roff + i]);
       r2 = uint32_t(rnd[2 * rnd_plane + roff + i]), r3 = uint32_t(rnd[3 * rnd_plane + roff + i]);
@@ -69,7 +81,7 @@ adamw_bf16_multi_kernel(const long long* __restrict__ ptrs, const long long* __r
     p_o = p1, m_o = m2, v_o = v2, s_o = s2;
   };
   const long long i_end = min(n, i0 + (long long)OPT_CHUNK);
-  const bool vec_ok = (((ptrs[0 * T + t] | ptrs[1 * T + t] | ptrs[2 * T + t] | ptrs[3 * T + t] | ptrs[4 * T + t]) & 15) == 0);
+  const bool vec_ok = (((ptrs[0 * T + t] | ptrs[1 * T + t] | ptrs[2 * T + t] | ptrs[3 * T + t] | ptrs[4 * T + t] | (ema ? ema[t] : 0)) & 15) == 0);
   const long long iv = i0 + (long long)threadIdx.x * 8;
   if (vec_ok && iv + 8 <= i_end) {
     // 16-byte accesses: the step is pure HBM streaming (5 reads + 4 writes of 2 B per parameter)
@@ -85,6 +97,13 @@ adamw_bf16_multi_kernel(const long long* __restrict__ ptrs, const long long* __r
     *reinterpret_cast<uint4*>(m + iv) = pack8(mo);
     *reinterpret_cast<uint4*>(v + iv) = pack8(vo);
     *reinterpret_cast<uint4*>(s + iv) = pack8(so);
+    if (e) {
+      float ev[8];
+      unpack8(*reinterpret_cast<const uint4*>(e + iv), ev);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ev[j] = ema_update(ev[j], po[j]);
+      *reinterpret_cast<uint4*>(e + iv) = pack8(ev);
+    }
   } else {
     for (long long i = iv; i < min(i_end, iv + 8); ++i) {
       float po, mo, vo, so;
@@ -94,6 +113,7 @@ adamw_bf16_multi_kernel(const long long* __restrict__ ptrs, const long long* __r
       m[i] = __float2bfloat16(mo);
       v[i] = __float2bfloat16(vo);
       s[i] = __float2bfloat16(so);
+      if (e) e[i] = __float2bfloat16(ema_update(__bfloat162float(e[i]), po));
     }
   }
 }

@@ -22,6 +22,7 @@ class EMAModel:
                  power: float = 2 / 3, ema_update_interval: Optional[int] = None):
         params = list(parameters)
         self.shadow_params: List[torch.Tensor] = [p.detach().clone() for p in params]
+        self._tracked = params        # identity of the tracked tensors: lets the optimizer kernel own the update (fused_plan)
         self.decay, self.min_decay = decay, min_decay
         self.update_after_step = update_after_step
         self.warmup_steps = max(0, int(warmup_steps))
@@ -44,19 +45,44 @@ class EMAModel:
             cur = (1 + step) / (10 + step)
         return max(min(cur, self.decay), self.min_decay)
 
-    @torch.no_grad()
-    def step(self, parameters: Iterable[torch.nn.Parameter], global_step: Optional[int] = None):
+    def begin_step(self, global_step: Optional[int] = None) -> Optional[float]:
+        """Bookkeeping half of `step`: advances the counter and returns this update's decay, or None when
+        `ema_update_interval` skips it.  Used by `step` and by AdamWBF16's fused update (the kernel applies the arithmetic)."""
         if global_step is not None and not should_update_ema(self.ema_update_interval, global_step):
-            return   # (global_step None = "always update": the reference would raise TypeError on `None % int`)
-        params = list(parameters)
-        if len(params) != len(self.shadow_params):
-            raise RuntimeError(f"EMA tracks {len(self.shadow_params)} parameters but {len(params)} were given.")
+            return None   # (global_step None = "always update": the reference would raise TypeError on `None % int`)
         if global_step is not None:      # periodic updates: the counter cannot be trusted (ema.py:381-385)
             self.optimization_step = global_step
         else:
             self.optimization_step += 1
         decay = self.get_decay(self.optimization_step)
         self.cur_decay_value = decay
+        return decay
+
+    def fused_plan(self, params: List[torch.Tensor]) -> Optional[List[torch.Tensor]]:
+        """Shadows in the order of `params` when the optimizer kernel can own the update: `params` are exactly the tracked
+        tensors, all trainable, with contiguous bf16 CUDA shadows.  None = use `step`."""
+        by_id = {id(p): s for p, s in zip(self._tracked, self.shadow_params)}
+        if len(params) != len(by_id) or any(id(p) not in by_id for p in params):
+            return None
+        out = [by_id[id(p)] for p in params]
+        ok = all(p.requires_grad and s.is_cuda and s.dtype == torch.bfloat16 and s.is_contiguous() and s.shape == p.shape
+                 for p, s in zip(params, out))
+        return out if ok else None
+
+    @torch.no_grad()
+    def step(self, parameters: Iterable[torch.nn.Parameter], global_step: Optional[int] = None):
+        params = list(parameters)
+        if len(params) != len(self.shadow_params):
+            raise RuntimeError(f"EMA tracks {len(self.shadow_params)} parameters but {len(params)} were given.")
+        decay = self.begin_step(global_step)
+        if decay is None:
+            return
+        self.apply(decay, params)
+
+    @torch.no_grad()
+    def apply(self, decay: float, params: Optional[List[torch.Tensor]] = None) -> None:
+        """The arithmetic half of `step` for an already-determined decay (default: the tensors given at construction)."""
+        params = self._tracked if params is None else params
         train = [(s, p) for s, p in zip(self.shadow_params, params) if p.requires_grad]
         frozen = [(s, p) for s, p in zip(self.shadow_params, params) if not p.requires_grad]
         if frozen:

@@ -67,6 +67,8 @@ class AdamWBF16(Optimizer):
                 # several steps ahead of the GPU; a slot is rewritten only after the copy that last used it has completed
                 "ptrs_host": [torch.empty((5, T), dtype=torch.int64).pin_memory() for _ in range(self._RING)],
                 "decay_host": [torch.empty((T,), dtype=torch.float32).pin_memory() for _ in range(self._RING)],
+                "ema_host": [torch.empty((T,), dtype=torch.int64).pin_memory() for _ in range(self._RING)],
+                "ema": torch.empty((T,), dtype=torch.int64, device=dev),
                 "copied": [None] * self._RING, "slot": 0,
                 "ptrs": torch.empty((5, T), dtype=torch.int64, device=dev),
                 "decay": torch.empty((T,), dtype=torch.float32, device=dev),
@@ -77,9 +79,17 @@ class AdamWBF16(Optimizer):
         return pl
 
     @torch.no_grad()
-    def step(self, zero_grad: bool = False, _rnd: Optional[torch.Tensor] = None):
+    def step(self, zero_grad: bool = False, _rnd: Optional[torch.Tensor] = None, *, grad_clamp: Optional[float] = None,
+             ema=None, ema_global_step: Optional[int] = None):
         """Performs a single optimization step.  `_rnd` (tests only): int32 [4, total] random 16-bit integers, tensors
-        concatenated in parameter order, replacing the internal generator."""
+        concatenated in parameter order, replacing the internal generator.
+        grad_clamp: fuse `clip_grad_value_(params, grad_clamp)` (the trainer's default clip, trainer.py:7188-7195) into the
+        gradient read.  ema (+ ema_global_step): a training.ema.EMAModel whose update (trainer.py:7352-7357) runs inside the
+        same kernel when it tracks exactly this group's tensors; otherwise `ema.step` runs after the launch."""
+        if grad_clamp is not None and not grad_clamp > 0:
+            grad_clamp = None
+        ema_decay = ema.begin_step(ema_global_step) if ema is not None else None
+        ema_done = ema is None or ema_decay is None
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             ps = [p for p in group["params"] if p.grad is not None]
@@ -122,6 +132,13 @@ class AdamWBF16(Optimizer):
                 ph[0, t], ph[1, t] = p.data_ptr(), p.grad.data_ptr()
                 ph[2, t], ph[3, t], ph[4, t] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), st["shift"].data_ptr()
                 dh[t] = decays[t]
+            shadows = ema.fused_plan(ps) if (not ema_done and len(self.param_groups) == 1) else None
+            if shadows is not None:
+                eh = pl["ema_host"][slot]
+                for t, sh in enumerate(shadows):
+                    eh[t] = sh.data_ptr()
+                pl["ema"].copy_(eh, non_blocking=True)
+                ema_done = True
             pl["ptrs"].copy_(ph, non_blocking=True)
             pl["decay"].copy_(dh, non_blocking=True)
             ev = pl["copied"][slot] or torch.cuda.Event()
@@ -136,7 +153,11 @@ class AdamWBF16(Optimizer):
             check(_lib.lib().stb_adamw_bf16_multi(
                 pl["ptrs"].data_ptr(), pl["sizes"].data_ptr(), pl["decay"].data_ptr(), pl["blk_tensor"].data_ptr(),
                 pl["blk_off"].data_ptr(), pl["num_blocks"], pl["T"], float(beta1), float(beta2), stepf, float(lr),
-                float(group["eps"]), rnd_ptr, pl["rnd_off"].data_ptr(), rnd_plane, C.c_ulonglong(seed), _stream()))
+                float(group["eps"]), rnd_ptr, pl["rnd_off"].data_ptr(), rnd_plane, C.c_ulonglong(seed),
+                float(grad_clamp or 0.0), pl["ema"].data_ptr() if shadows is not None else None,
+                float(1.0 - ema_decay) if shadows is not None else 0.0, _stream()))
             if zero_grad:
                 for p in ps:
                     p.grad.zero_()
+        if not ema_done:       # several groups / fp32 or frozen shadows: the two foreach kernels of EMAModel.step
+            ema.apply(ema_decay)

@@ -23,7 +23,7 @@ import torch
 
 class TrainStep:
     def __init__(self, model, optimizer: torch.optim.Optimizer, *, max_grad_norm: float = 2.0,
-                 grad_clip_method: str = "value", gradient_accumulation_steps: int = 1, grad_sync=None):
+                 grad_clip_method: str = "value", gradient_accumulation_steps: int = 1, grad_sync=None, ema=None):
         self.model = model            # simpletuner_b200.flux.model.Flux (or another family wrapper)
         self.optimizer = optimizer
         self.max_grad_norm = max_grad_norm
@@ -35,17 +35,24 @@ class TrainStep:
         self.grad_sync = grad_sync    # e.g. training.dist.FlatGradSync: called once per optimizer step, before the clip
         self.track_grad_norm = False  # True: keep the reference's logged `grad_norm` (inf-norm unless norm-clipping) as a device scalar
         self.grad_norm = None
+        self.ema = ema                # training.ema.EMAModel over the trainable tensors (trainer.py:7351-7357), or None
+        from .optim import AdamWBF16
+        self._fused_opt = isinstance(optimizer, AdamWBF16)   # clamp + EMA ride inside the one optimizer launch
 
     def _clip(self):
+        """Gradient clip (trainer.py:7138-7217).  Returns the clamp value when the element clamp is left to the optimizer
+        kernel (AdamWBF16 + `grad_clip_method = "value"`), else None."""
         clipping = self.max_grad_norm is not None and self.max_grad_norm > 0
         if self.track_grad_norm and (self.grad_clip_method != "norm" or not clipping):
             from .noise import max_grad_value       # trainer.py:7144-7147: self.grad_norm = self._max_grad_value()
             self.grad_norm = max_grad_value(self._params)
         if not clipping:
-            return
+            return None
+        if self.grad_clip_method == "value" and self._fused_opt:
+            return float(self.max_grad_norm)
         grads = [p.grad for p in self._params if p.grad is not None]
         if not grads:
-            return
+            return None
         if self.grad_clip_method == "value":
             torch._foreach_clamp_min_(grads, -self.max_grad_norm)
             torch._foreach_clamp_max_(grads, self.max_grad_norm)
@@ -55,6 +62,18 @@ class TrainStep:
                 self.grad_norm = gn
         else:
             raise ValueError(f"unknown grad_clip_method {self.grad_clip_method}")
+        return None
+
+    def _optimizer_step(self):
+        """clip -> optimizer.step -> EMA (trainer.py:7138-7239, 7351-7357); one launch for all three with AdamWBF16."""
+        clamp = self._clip()
+        gs = self.state["global_step"] + 1
+        if self._fused_opt:
+            self.optimizer.step(grad_clamp=clamp, ema=self.ema, ema_global_step=gs)
+        else:
+            self.optimizer.step()
+            if self.ema is not None:
+                self.ema.step(self._params, global_step=gs)
 
     def __call__(self, batch: Dict[str, Any]) -> torch.Tensor:
         """Runs one micro-step (and the optimizer step when the accumulation boundary is reached).
@@ -74,8 +93,7 @@ class TrainStep:
         if sync:
             if self.grad_sync is not None:
                 self.grad_sync()
-            self._clip()
-            self.optimizer.step()
+            self._optimizer_step()
             self.optimizer.zero_grad(set_to_none=True)
             den = getattr(self.model, "model", None)
             den = getattr(den, "module", den)
@@ -153,8 +171,7 @@ class GraphedTrainStep:
         st.state["micro_step"] += 1
         if st.grad_sync is not None:
             st.grad_sync()
-        st._clip()
-        st.optimizer.step()
+        st._optimizer_step()
         # NO zero_grad(set_to_none): the captured backward writes the same .grad tensors again on the next replay
         st.state["global_step"] += 1
         return ld

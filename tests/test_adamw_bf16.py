@@ -108,3 +108,70 @@ def test_optimizer_minimises_a_quadratic_with_internal_rng():
         w.grad = (2 * (w.float() - target) / w.numel() * 1000).bfloat16()   # scaled: this optimizer has no 1/sqrt(v) bias fix
         opt.step()
     assert float(((w.float() - target) ** 2).mean()) < 0.05 * first
+
+
+@pytest.mark.gpu
+def test_fused_value_clamp_and_ema_match_the_separate_eager_passes():
+    """One launch with grad_clamp + EMA == clip_grad_value_ -> step -> EMAModel.step (trainer.py:7188-7195, 7239,
+    7351-7357), bit for bit, with the same stochastic-rounding integers."""
+    from simpletuner_b200.training.ema import EMAModel
+    from simpletuner_b200.training.optim import AdamWBF16
+    dev = "cuda"
+    g = torch.Generator().manual_seed(5)
+    sizes = [4096, 1003, 8, 70001]
+    p0 = [torch.randn(n, generator=g).bfloat16() for n in sizes]
+
+    def make():
+        ps = [torch.nn.Parameter(t.clone().to(dev)) for t in p0]
+        opt = AdamWBF16(ps, lr=3e-3, weight_decay=0.0, seed=2)
+        for p_ in ps:
+            opt.state[p_].update(step=0.0, exp_avg=torch.zeros_like(p_), exp_avg_sq=torch.zeros_like(p_), shift=torch.zeros_like(p_),
+                                 accumulated_decay=0.0)
+        return ps, opt, EMAModel(ps, decay=0.97, ema_update_interval=2)
+
+    (pa, oa, ea), (pb, ob, eb) = make(), make()
+    clamp = 0.37                               # not a bf16 number: the clamp result itself rounds
+    for k in range(1, 5):
+        grads = [torch.randn(n, generator=g).bfloat16() for n in sizes]
+        grads[1][5] = float("nan") if k == 3 else grads[1][5]
+        rnd = torch.randint(0, 1 << 16, (4, sum(sizes)), generator=g, dtype=torch.int32).to(dev)
+        for p_, p2, gr in zip(pa, pb, grads):
+            p_.grad, p2.grad = gr.clone().to(dev), gr.clone().to(dev)
+        oa.step(_rnd=rnd, grad_clamp=clamp, ema=ea, ema_global_step=k)
+        torch.nn.utils.clip_grad_value_(pb, clamp)
+        ob.step(_rnd=rnd)
+        eb.step(pb, global_step=k)
+        torch.cuda.synchronize()
+        assert ea.optimization_step == eb.optimization_step and ea.cur_decay_value == eb.cur_decay_value
+        for i in range(len(sizes)):
+            assert torch.equal(pa[i].grad, grads[i].to(dev)) or k == 3            # the stored gradient is not modified
+            same = lambda x, y: torch.equal(torch.nan_to_num(x.float(), nan=7.0), torch.nan_to_num(y.float(), nan=7.0))
+            assert same(pa[i], pb[i]) and same(oa.state[pa[i]]["exp_avg"], ob.state[pb[i]]["exp_avg"]), (k, i)
+            assert same(ea.shadow_params[i], eb.shadow_params[i]), (k, i)
+    assert not torch.equal(ea.shadow_params[0], pa[0])                          # the shadows did move and lag the weights
+
+
+@pytest.mark.gpu
+def test_train_step_routes_clamp_and_ema_through_the_optimizer_launch():
+    from simpletuner_b200 import ops
+    from simpletuner_b200.training.ema import EMAModel
+    from simpletuner_b200.training.optim import AdamWBF16
+    from simpletuner_b200.training.step import TrainStep
+    w = torch.nn.Parameter(torch.ones(4096, device="cuda", dtype=torch.bfloat16))
+
+    class _M:
+        model = None
+        def prepare_batch(self, b, s): return b
+        def model_predict(self, b): return (w.float() * b["x"]).sum()
+        def loss_with_logs(self, b, out, apply_conditioning_mask=True): return out, {}
+
+    ema = EMAModel([w], decay=0.5)
+    step = TrainStep(_M(), AdamWBF16([w], lr=1e-2, seed=0), max_grad_norm=0.25, ema=ema)
+    n0 = ops.launch_count()
+    for _ in range(3):
+        step({"x": torch.full((4096,), 3.0, device="cuda")})
+    torch.cuda.synchronize()
+    assert ops.launch_count() - n0 == 3                                         # one library launch per optimizer step
+    assert ema.optimization_step == 3 and float((ema.shadow_params[0].float() - 1).abs().max()) > 0
+    # |g| = 3 clamped to 0.25: first-moment quirk (grad + 0.1 * 0.9 * m) keeps m bounded by the clamp, not by 3
+    assert float(step.optimizer.state[w]["exp_avg"].float().abs().max()) < 0.3
