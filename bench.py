@@ -95,7 +95,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ model
-def build_model(device, cfg_over=None, rank=16, seed=0):
+def build_model(device, cfg_over=None, rank=16, seed=0, target="all", dropout=0.0):
     from simpletuner_b200.flux.model import Flux, default_config
     from simpletuner_b200.flux.transformer import FluxTransformer2DModel
 
@@ -112,7 +112,7 @@ def build_model(device, cfg_over=None, rank=16, seed=0):
                 p.normal_(0.0, 0.01, generator=g)
             else:
                 p.normal_(0.0, 0.02, generator=g)
-    w = Flux(default_config(lora_rank=rank), transformer=m, device=device)
+    w = Flux(default_config(lora_rank=rank, flux_lora_target=target, lora_dropout=dropout), transformer=m, device=device)
     w.add_lora_adapter()
     with torch.no_grad():  # non-zero B so every LoRA gradient path does real work
         for lin in m.lora_linears().values():
@@ -620,7 +620,7 @@ def run_b200(args):
     elif pix:
         wrapper = build_pixart_lora(device, rank=32, seed=0, tiny=args.tiny)
     else:
-        wrapper = build_model(device, cfg_over, rank=16, seed=0)
+        wrapper = build_model(device, cfg_over, rank=16, seed=0, target=args.lora_target, dropout=args.lora_dropout)
     if args.gradient_checkpointing:   # non-default: the reference's --gradient_checkpointing memory / time trade-off
         wrapper._denoiser().enable_gradient_checkpointing()
     if world > 1 and args.dp == "ddp":
@@ -747,6 +747,11 @@ def run_b200(args):
                     "avg_launch_ms": gb["avg_ms"], "tflop_per_launch": gb["tflop_per_launch"], "launches_per_step": gb["launches"]}
         tf_sample = TF_STEP_SAMPLE
         metric, workload = METRIC, WORKLOAD
+        if not (pix or sd3) and (args.lora_target != "all" or args.lora_dropout):
+            n_t = len(wrapper._denoiser().lora_linears())
+            n_p = sum(p.numel() for p in wrapper._denoiser().parameters() if p.requires_grad)
+            workload = workload.replace("flux_lora_target=all, 266 targets, 26.1M trainable",
+                                        f"flux_lora_target={args.lora_target}, {n_t} targets, {n_p / 1e6:.1f}M trainable, lora_dropout={args.lora_dropout}")
         if pix:
             tf_sample = sum(pixart_tf_per_sample(hw_) for hw_ in PIXART_BUCKETS) / len(PIXART_BUCKETS)
             metric = "images/sec PixArt-Sigma LoRA r32 bf16, mixed aspect buckets 512-1536, grad-accum 4"
@@ -771,7 +776,7 @@ def run_b200(args):
                 "activation_recompute": ("every block re-run in backward (--gradient-checkpointing)" if args.gradient_checkpointing else
                                          "none (block-native minimal saves; reference default would recompute every block)"),
                 "host_syncs_in_step": 0, "l2_policy": "inputs larger than L2 (24 GB of weights + 16 MB fresh batch streamed every step)",
-                "lora_dropout": 0.0, "optimizer": ("adamw_bf16 (reference default; stochastic-rounding AdamW, one stb_adamw_bf16_multi launch)" if args.optimizer == "adamw_bf16"
+                "lora_dropout": float(args.lora_dropout) if not (pix or sd3) else 0.0, "optimizer": ("adamw_bf16 (reference default; stochastic-rounding AdamW, one stb_adamw_bf16_multi launch)" if args.optimizer == "adamw_bf16"
                               else "torch.optim.AdamW(fused) on bf16 LoRA params"),
                 "tiny": bool(args.tiny),
             },
@@ -839,6 +844,8 @@ def main():
     ap.add_argument("--dp", default="auto", choices=["auto", "flat", "ddp"],
                     help="gradient exchange for N > 1: flat = one NCCL all-reduce of all LoRA gradients after backward "
                          "(training.dist.FlatGradSync); ddp = torch DDP buckets overlapped with backward (the reference's mechanism)")
+    ap.add_argument("--lora-target", default="all", help="flux_lora_target preset (flux_lora only; headline = all)")
+    ap.add_argument("--lora-dropout", type=float, default=0.0, help="PEFT lora_dropout (flux_lora only; headline = 0.0)")
     ap.add_argument("--gradient-checkpointing", action="store_true",
                     help="re-run every block in backward like the reference's --gradient_checkpointing (not the headline config)")
     args = ap.parse_args()

@@ -212,6 +212,13 @@ int stb_target_mse_loss(const void* pred_packed, const void* target, const float
                         void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, int loss_type,
                         const float* huber_c, void* stream);
 
+/* GELU(tanh) outside a GEMM epilogue, for the adapters on the MLP projections (flux_lora_target "all+ffs", "context+ffs",
+ * "tiny" ...: reference flux/model.py:1272-1376; activation: flux/transformer.py:447, diffusers FeedForward
+ * "gelu-approximate").  mode 0: y = gelu(pre) (the activation the forward epilogue produced, re-created from the saved
+ * pre-activation); mode 1: y = g * gelu'(pre).  [B, S, D] views with element strides, D % 8 == 0. */
+int stb_gelu_tanh(const void* pre, long long p_b, long long p_s, const void* g, long long g_b, long long g_s, void* y,
+                  long long y_b, long long y_s, int B, int S, int D, int mode, void* stream);
+
 /* y[b, s, :] = gate[b, :] * x[b, s, :]  — gradient of `gate * linear(...)` w.r.t. the linear output
  * (flux/transformer.py:464, 584, 652), applied before the dgrad GEMM. */
 int stb_gate_mul(const void* x, long long x_b, long long x_s, const void* gate, long long g_b, void* y,

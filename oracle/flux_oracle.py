@@ -121,15 +121,21 @@ FLUX_LORA_TARGETS_ALL = ("to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "ad
 """flux_lora_target="all" (reference flux/model.py:1249-1262; to_qkv/add_qkv_proj only exist when fused)."""
 
 
+FLUX_LORA_TARGETS_FFS = FLUX_LORA_TARGETS_ALL + ("ff.net.0.proj", "ff.net.2", "ff_context.net.0.proj", "ff_context.net.2",
+                                                 "proj_mlp", "proj_out")
+"""flux_lora_target="all+ffs" (reference flux/model.py:1283-1301); "+embedder" adds x_embedder (:1320-1338)."""
+
+
 def lora_target_names(cfg: FluxConfig, targets=FLUX_LORA_TARGETS_ALL):
+    """PEFT's target_modules rule: a Linear is adapted when its qualified name equals a target or ends with ".<target>"
+    (so "proj_out" selects every single block's proj_out AND the model's final proj_out)."""
     names = []
-    for i in range(cfg.num_layers):
-        for n in targets:
-            names.append(f"transformer_blocks.{i}.attn.{n}")
-    for i in range(cfg.num_single_layers):
-        for n in targets:
-            if n in ("to_q", "to_k", "to_v"):
-                names.append(f"single_transformer_blocks.{i}.attn.{n}")
+    for key in flux_param_shapes(cfg):
+        if not key.endswith(".weight"):
+            continue
+        mod = key[: -len(".weight")]
+        if any(mod == t or mod.endswith("." + t) for t in targets) and len(flux_param_shapes(cfg)[key]) == 2:
+            names.append(mod)
     return names
 
 
@@ -138,12 +144,13 @@ def init_lora_params(cfg: FluxConfig, rank: int, seed: int = 1, dtype=torch.floa
     """PEFT default init: A ~ kaiming_uniform(a=sqrt(5)), B = 0; b_std > 0 gives a non-zero B so that
     gradients w.r.t. A are exercised."""
     g = torch.Generator().manual_seed(seed)
-    D = cfg.inner_dim
     out = {}
-    bound = 1.0 / math.sqrt(D)  # kaiming_uniform(a=sqrt(5)) on [r, D]: bound = sqrt(6/((1+5) D)) = 1/sqrt(D)
+    shapes = flux_param_shapes(cfg)
     for n in lora_target_names(cfg, targets):
-        out[n + ".lora_A.weight"] = ((torch.rand((rank, D), generator=g) * 2 - 1) * bound).to(dtype)
-        out[n + ".lora_B.weight"] = (b_std * torch.randn((D, rank), generator=g)).to(dtype)
+        n_out, k_in = shapes[n + ".weight"]
+        bound = 1.0 / math.sqrt(k_in)  # kaiming_uniform(a=sqrt(5)) on [r, K]: bound = sqrt(6/((1+5) K)) = 1/sqrt(K)
+        out[n + ".lora_A.weight"] = ((torch.rand((rank, k_in), generator=g) * 2 - 1) * bound).to(dtype)
+        out[n + ".lora_B.weight"] = (b_std * torch.randn((n_out, rank), generator=g)).to(dtype)
     return out
 
 
@@ -292,12 +299,11 @@ def flux_double_block(P, cfg, i, x, enc, temb, rope, lora, lora_scale):
     x = x + g_a.unsqueeze(1) * ao
     enc = enc + cg_a.unsqueeze(1) * eo
     nx = layer_norm_noaffine(x) * (1 + sc_m[:, None]) + sh_m[:, None]
-    ff = F.linear(F.gelu(F.linear(nx, P[p + "ff.net.0.proj.weight"], P[p + "ff.net.0.proj.bias"]), approximate="tanh"),
-                  P[p + "ff.net.2.weight"], P[p + "ff.net.2.bias"])
+    ff = linear(F.gelu(linear(nx, P, p + "ff.net.0.proj", lora, lora_scale), approximate="tanh"), P, p + "ff.net.2", lora, lora_scale)
     x = x + g_m.unsqueeze(1) * ff
     nenc = layer_norm_noaffine(enc) * (1 + csc_m[:, None]) + csh_m[:, None]
-    cff = F.linear(F.gelu(F.linear(nenc, P[p + "ff_context.net.0.proj.weight"], P[p + "ff_context.net.0.proj.bias"]), approximate="tanh"),
-                   P[p + "ff_context.net.2.weight"], P[p + "ff_context.net.2.bias"])
+    cff = linear(F.gelu(linear(nenc, P, p + "ff_context.net.0.proj", lora, lora_scale), approximate="tanh"), P,
+                 p + "ff_context.net.2", lora, lora_scale)
     enc = nan_to_num_(enc + cg_m.unsqueeze(1) * cff)
     return enc, x
 
@@ -309,9 +315,9 @@ def flux_single_block(P, cfg, i, x, temb, rope, lora, lora_scale):
     sh, sc, gate = mod.chunk(3, dim=1)
     nx = layer_norm_noaffine(x) * (1 + sc[:, None]) + sh[:, None]
     ao = flux_attention(P, cfg, p + "attn.", nx, None, rope, lora, lora_scale)
-    mlp = F.gelu(F.linear(nx, P[p + "proj_mlp.weight"], P[p + "proj_mlp.bias"]), approximate="tanh")
+    mlp = F.gelu(linear(nx, P, p + "proj_mlp", lora, lora_scale), approximate="tanh")
     h = torch.cat([ao, mlp], dim=2)
-    h = gate.unsqueeze(1) * F.linear(h, P[p + "proj_out.weight"], P[p + "proj_out.bias"])
+    h = gate.unsqueeze(1) * linear(h, P, p + "proj_out", lora, lora_scale)
     return nan_to_num_(x + h)
 
 
@@ -322,7 +328,7 @@ def flux_forward(P: Dict[str, Tensor], cfg: FluxConfig, hidden_states: Tensor, e
     """FluxTransformer2DModel.forward (reference flux/transformer.py:940-1515), default path only
     (no mask / TREAD / controlnet / token-wise timesteps).  timestep and guidance arrive divided by
     1000 and are multiplied back inside (reference :1003-1007, quirk Q8)."""
-    x = F.linear(hidden_states, P["x_embedder.weight"], P["x_embedder.bias"])
+    x = linear(hidden_states, P, "x_embedder", lora, lora_scale)
     t = timestep.to(torch.float32) * 1000
     g = guidance.to(torch.float32) * 1000 if guidance is not None else None
     temb = time_text_embed(P, cfg, t, g, pooled_projections)
@@ -342,7 +348,7 @@ def flux_forward(P: Dict[str, Tensor], cfg: FluxConfig, hidden_states: Tensor, e
     emb = F.linear(F.silu(temb).to(x.dtype), P["norm_out.linear.weight"], P["norm_out.linear.bias"])
     scale, shift = torch.chunk(emb, 2, dim=1)
     x = layer_norm_noaffine(x) * (1 + scale)[:, None, :] + shift[:, None, :]
-    return F.linear(x, P["proj_out.weight"], P["proj_out.bias"])
+    return linear(x, P, "proj_out", lora, lora_scale)
 
 
 # --------------------------------------------------------------------------------------------------

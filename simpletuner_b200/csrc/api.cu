@@ -718,6 +718,23 @@ int stb_gate_mul(const void* x, long long x_b, long long x_s, const void* gate, 
   return 0;
 }
 
+int stb_gelu_tanh(const void* pre, long long p_b, long long p_s, const void* g, long long g_b, long long g_s, void* y,
+                  long long y_b, long long y_s, int B, int S, int D, int mode, void* stream) {
+  if (int r = check_device()) return r;
+  if (mode != 0 && mode != 1) return fail(STB_ERR_ARG, "gelu_tanh: mode 0 (gelu) or 1 (g * gelu')");
+  if (!pre || !y || (mode == 1 && !g) || B < 1 || S < 1 || D < 8) return fail(STB_ERR_ARG, "gelu_tanh: bad arguments");
+  if ((D & 7) || !aligned16(pre) || !aligned16(y) || (p_s & 7) || (p_b & 7) || (y_s & 7) || (y_b & 7) ||
+      (mode == 1 && (!aligned16(g) || (g_s & 7) || (g_b & 7))))
+    return fail(STB_ERR_ARG, "gelu_tanh alignment");
+  const long long total = (long long)B * S * (D >> 3);
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
+  stb::gelu_tanh_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(pre), p_b, p_s, static_cast<const __nv_bfloat16*>(g), g_b, g_s,
+      static_cast<__nv_bfloat16*>(y), y_b, y_s, B, S, D, mode);
+  STB_LAUNCH_CHECK("gelu_tanh");
+  return 0;
+}
+
 static int dropout_args(const void* a, const void* b, int members, int B, int S, int K, float p) {
   if (!a || !b || members < 1 || members > 8 || B < 1 || S < 1 || K < 8 || (K & 7)) return fail(STB_ERR_ARG, "dropout: bad shape (K multiple of 8, 1..8 members)");
   if (!(p >= 0.f && p < 1.f)) return fail(STB_ERR_ARG, "dropout: p must be in [0, 1)");

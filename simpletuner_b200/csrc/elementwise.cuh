@@ -683,6 +683,42 @@ gate_mul_kernel(const __nv_bfloat16* __restrict__ x, long long x_b, long long x_
 
 
 // ------------------------------------------------------------------------------------------------
+// GELU(tanh) outside a GEMM epilogue — only the LoRA-on-MLP paths need it (flux_lora_target = "all+ffs" etc.,
+// reference flux/model.py:1283-1338):  mode 0: y = gelu(pre)  — re-creates the bf16 activation the forward GEMM's
+// EPI_GELU epilogue produced from the saved pre-activation (bit-identical: that epilogue applies gelu to the
+// bf16-rounded pre-activation too), as the input of the fc2 / proj_out adapter's weight gradient;
+// mode 1: y = g * gelu'(pre) — the dgrad through the activation when the LoRA dropout branch had to be added to the
+// un-activated gradient first.  x / g / y: [B, S, D] views (element strides), D % 8 == 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gelu_tanh_kernel(const __nv_bfloat16* __restrict__ pre, long long p_b, long long p_s, const __nv_bfloat16* __restrict__ g,
+                 long long g_b, long long g_s, __nv_bfloat16* __restrict__ y, long long y_b, long long y_s, int B, int S,
+                 int D, int mode) {
+  const int vec_per_row = D >> 3;
+  const long long total = (long long)B * S * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % vec_per_row) * 8;
+    const long long r = i / vec_per_row;
+    const int s = int(r % S);
+    const int b = int(r / S);
+    float xv[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(pre + b * p_b + s * p_s + c), xv);
+    if (mode == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = gelu_tanh(xv[j]);
+    } else {
+      float gv[8];
+      unpack8(*reinterpret_cast<const uint4*>(g + b * g_b + s * g_s + c), gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = gv[j] * gelu_tanh_grad(xv[j]);
+    }
+    *reinterpret_cast<uint4*>(y + b * y_b + s * y_s + c) = pack8(o);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
 // LoRA dropout (PEFT `lora_dropout`: result += lora_B(lora_A(dropout(x))) * scaling, reference common.py:1094-1117 with the
 // reference default lora_dropout = 0.1, field_registry/sections/lora.py:130-137).  Every adapted Linear owns its own
 // nn.Dropout, so the members of one fused projection group (to_q / to_k / to_v share the input x) need INDEPENDENT masks.

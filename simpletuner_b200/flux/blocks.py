@@ -159,7 +159,10 @@ def _lora_grads(pack: LoraPack, x: torch.Tensor, t_down: torch.Tensor, dy: torch
     With dropout dA_m contracts T'_m with the SAME masked copy of x the forward used (masks regenerated, not stored)."""
     R = pack.a_stack.shape[0]
     wide = R > 128        # ranks above 40: the fused q|k|v rank block no longer fits one 128-wide weight-gradient tile
-    if drop is None and not wide:
+    if isinstance(x, (tuple, list)):        # the adapted Linear reads cat(x, -1) (single-block proj_out): one product per part
+        assert drop is None and not wide
+        d_a = torch.cat([ops.skinny_tn(t_up, part) for part in x], 1)
+    elif drop is None and not wide:
         d_a = ops.skinny_tn(t_up, x)        # [R, K] fp32
     elif drop is None:
         d_a = torch.zeros((R, x.shape[-1]), device=x.device, dtype=torch.float32)
@@ -175,9 +178,9 @@ def _lora_grads(pack: LoraPack, x: torch.Tensor, t_down: torch.Tensor, dy: torch
     if not wide:
         d_bt = ops.skinny_tn(t_down, dy)    # [R, N] fp32 (only the block diagonal is used)
     else:                                   # per member, against its own n_out columns of dy only
-        d_bt = torch.zeros((R, dy.shape[-1]), device=x.device, dtype=torch.float32)
+        d_bt = torch.zeros((R, dy.shape[-1]), device=dy.device, dtype=torch.float32)
         for m, sl in _member_slices(pack):
-            blk = torch.zeros((rp, pack.n_out), device=x.device, dtype=torch.float32)
+            blk = torch.zeros((rp, pack.n_out), device=dy.device, dtype=torch.float32)
             ops.skinny_tn(t_down[:, :, sl], dy[:, :, m * pack.n_out:(m + 1) * pack.n_out], out=blk)
             d_bt[sl, m * pack.n_out:(m + 1) * pack.n_out] = blk
     out = []
@@ -230,6 +233,43 @@ def _linear_lora_dgrad(dy, w_t, pack: Optional[LoraPack], drop: Optional[LoraDro
     dx = ops.gemm([dy], [w_t], None, **kw)
     _lora_dgrad_dropout(dx, t_up, pack, drop)
     return dx, t_up
+
+
+def _pack1(a, b, n_out: int, k_in: int, scaling: float, device) -> Optional[LoraPack]:
+    """Pack of a single adapted Linear (MLP projections, proj_out, x_embedder)."""
+    return None if a is None else pack_lora([(a, b)], n_out, k_in, scaling, device)
+
+
+def _dgrad_through_gelu(dy, w_t, pack: Optional[LoraPack], drop: Optional[LoraDrop], pre):
+    """d_pre = (dy W (+ LoRA branch)) * gelu'(pre).  Returns (d_pre, T' or None).  Without dropout the LoRA branch is one more
+    K-segment and the activation gradient stays in the GEMM epilogue; with dropout the masked branch is added to the
+    un-activated gradient first."""
+    if pack is None or drop is None:
+        return _linear_lora_dgrad(dy, w_t, pack, None, epi=ops.EPI_MUL_DGELU, aux=pre)
+    d_act, t_up = _linear_lora_dgrad(dy, w_t, pack, drop)
+    return ops.mul_dgelu_tanh(d_act, pre, out=d_act), t_up
+
+
+class LoraLinearFn(torch.autograd.Function):
+    """y = x W^T + b + scaling * B A dropout(x) for an adapted Linear outside the block schedules (x_embedder,
+    flux_lora_target = "all+ffs+embedder", reference flux/model.py:1320-1338).  x carries no gradient (model input)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, scaling, drop, lora_a, lora_b):
+        pk = _pack1(lora_a, lora_b, w.shape[0], w.shape[1], scaling, x.device)
+        y, t = _linear_lora_fwd(x, w, b, pk, drop)
+        ctx.pack, ctx.drop = pk, drop
+        ctx.save_for_backward(x, t)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, t = ctx.saved_tensors
+        pk, drop = ctx.pack, ctx.drop
+        dy = dy if dy.stride(-1) == 1 else dy.contiguous()
+        t_up = ops.gemm([dy], [pk.b_ext_t])
+        (da, db), = _lora_grads(pk, x, t, dy, t_up, drop)
+        return None, None, None, None, None, da, db
 
 
 # ------------------------------------------------------------------------------------------------
@@ -286,6 +326,7 @@ class DoubleBlockFn(torch.autograd.Function):
       img : to_q.A, to_q.B, to_k.A, to_k.B, to_v.A, to_v.B, to_out.A, to_out.B            [0..7]
       txt : add_q.A, add_q.B, add_k.*, add_v.*, to_add_out.A, to_add_out.B               [8..15]
       attn2: to_q.A, to_q.B, to_k.*, to_v.*, to_out.A, to_out.B                          [16..23]
+      mlp : ff.net.0.proj.A, .B, ff.net.2.A, .B, ff_context.net.0.proj.A, .B, ff_context.net.2.A, .B   [24..31]
     """
 
     @staticmethod
@@ -300,8 +341,10 @@ class DoubleBlockFn(torch.autograd.Function):
         dev = h.device
         drop: Optional[LoraDrop] = st.get("lora_drop")
         dr = (lambda off: drop.at(off)) if drop is not None else (lambda off: None)
-        lora = list(lora) + [None] * (24 - len(lora))
+        n_lora_in = len(lora)
+        lora = list(lora) + [None] * (32 - len(lora))
         streams = (("txt", slice(0, S_txt), mod_txt, 8), ("img", slice(S_txt, S), mod_img, 0))
+        mlp_base = {"img": 24, "txt": 28}
 
         def lp(base, n_members, n_out, k_in):
             ps = []
@@ -373,28 +416,35 @@ class DoubleBlockFn(torch.autograd.Function):
             mp: MlpPlan = plans[name + "_mlp"]
             nh2 = ops.ln_modulate_fwd(h1[:, sl], mod[:, 3 * D:4 * D], mod[:, 4 * D:5 * D], EPS)
             pre = torch.empty((B, sl.stop - sl.start, 4 * D), device=dev, dtype=torch.bfloat16)
-            act = ops.gemm([nh2], [mp.w1], mp.b1, epi=ops.EPI_GELU, aux=pre)
+            mb = mlp_base[name]
+            pk1 = packs[name + "_fc1"] = _pack1(lora[mb], lora[mb + 1], 4 * D, D, scaling, dev)
+            pk2 = packs[name + "_fc2"] = _pack1(lora[mb + 2], lora[mb + 3], D, 4 * D, scaling, dev)
+            act, t = _linear_lora_fwd(nh2, mp.w1, mp.b1, pk1, dr(base + 3), epi=ops.EPI_GELU, aux=pre)
+            small[name + "_t_fc1"] = t
             del nh2
-            ops.gemm([act], [mp.w2], mp.b2, out=h2[:, sl], epi=ops.EPI_GATE_RES, gate=mod[:, 5 * D:6 * D],
-                     res=h1[:, sl], nan_to_num=(name == "txt" and nan_txt))
+            _, t = _linear_lora_fwd(act, mp.w2, mp.b2, pk2, dr(base + 4), out=h2[:, sl], epi=ops.EPI_GATE_RES,
+                                    gate=mod[:, 5 * D:6 * D], res=h1[:, sl], nan_to_num=(name == "txt" and nan_txt))
+            small[name + "_t_fc2"] = t
             del act
             mlp_pre[name] = pre
         ctx.st = st
         ctx.packs = packs
-        ctx.n_lora_in = st.get("_n_lora", 16)
+        ctx.n_lora_in = n_lora_in
         ctx.lora_present = [x is not None for x in lora]
         E = h.new_empty(0)
         keep = lambda t: t if t is not None else E
         ctx.save_for_backward(h, mod_img, mod_txt, keep(cos), keep(sin), qkv, o, lse, h1, keep(mlp_pre["txt"]), mlp_pre["img"],
                               keep(small["txt_t_qkv"]), keep(small["img_t_qkv"]), keep(small["txt_t_out"]), keep(small["img_t_out"]),
                               keep(qkv2), keep(o2), keep(lse2), keep(small.get("a2_t_qkv")), keep(small.get("a2_t_out")),
-                              q if keep_qk else E, k if keep_qk else E)
+                              q if keep_qk else E, k if keep_qk else E,
+                              keep(small.get("txt_t_fc1")), keep(small.get("txt_t_fc2")), keep(small.get("img_t_fc1")),
+                              keep(small.get("img_t_fc2")))
         return h2
 
     @staticmethod
     def backward(ctx, dh2):
         (h, mod_img, mod_txt, cos, sin, qkv, o, lse, h1, pre_txt, pre_img, t_qkv_txt, t_qkv_img, t_out_txt, t_out_img,
-         qkv2, o2, lse2, t_qkv_a2, t_out_a2, q_saved, k_saved) = ctx.saved_tensors
+         qkv2, o2, lse2, t_qkv_a2, t_out_a2, q_saved, k_saved, t_fc1_txt, t_fc2_txt, t_fc1_img, t_fc2_img) = ctx.saved_tensors
         qk_saved = (q_saved, k_saved) if q_saved.numel() else None
         cos = cos if cos.numel() else None
         sin = sin if sin.numel() else None
@@ -410,7 +460,8 @@ class DoubleBlockFn(torch.autograd.Function):
         dh2 = dh2.contiguous()
         streams = (("txt", slice(0, S_txt), mod_txt, 8, pre_txt, t_qkv_txt, t_out_txt),
                    ("img", slice(S_txt, S), mod_img, 0, pre_img, t_qkv_img, t_out_img))
-        grads: List[Optional[torch.Tensor]] = [None] * 24
+        mlp_t = {"txt": (28, t_fc1_txt, t_fc2_txt), "img": (24, t_fc1_img, t_fc2_img)}
+        grads: List[Optional[torch.Tensor]] = [None] * 32
         dh1 = torch.empty_like(h)
         d_o = torch.empty_like(o)
         for name, sl, mod, base, pre, t_qkv, t_out in streams:
@@ -422,9 +473,19 @@ class DoubleBlockFn(torch.autograd.Function):
             mp: MlpPlan = plans[name + "_mlp"]
             # ---- MLP branch: h2 = h1 + gate_mlp * fc2(gelu(fc1(LNmod(h1))))
             g2 = ops.gate_mul(dh2[:, sl], mod[:, 5 * D:6 * D])
-            d_pre = ops.gemm([g2], [mp.w2_t], None, epi=ops.EPI_MUL_DGELU, aux=pre)
+            mb, t_fc1, t_fc2 = mlp_t[name]
+            pk1, pk2 = packs.get(name + "_fc1"), packs.get(name + "_fc2")
+            d_pre, t_up = _dgrad_through_gelu(g2, mp.w2_t, pk2, dr(base + 4), pre)
+            if pk2 is not None:
+                act = ops.gelu_tanh(pre)
+                (grads[mb + 2], grads[mb + 3]), = _lora_grads(pk2, act, t_fc2, g2, t_up, dr(base + 4))
+                del act
             del g2
-            d_nh2 = ops.gemm([d_pre], [mp.w1_t], None)
+            d_nh2, t_up = _linear_lora_dgrad(d_pre, mp.w1_t, pk1, dr(base + 3))
+            if pk1 is not None:
+                nh2 = ops.ln_modulate_fwd(h1[:, sl], mod[:, 3 * D:4 * D], mod[:, 4 * D:5 * D], EPS)
+                (grads[mb], grads[mb + 1]), = _lora_grads(pk1, nh2, t_fc1, d_pre, t_up, dr(base + 3))
+                del nh2
             del d_pre
             ops.ln_modulate_bwd(d_nh2, h1[:, sl], mod[:, 4 * D:5 * D], add=dh2[:, sl], eps=EPS, out=dh1[:, sl])
             del d_nh2
@@ -490,7 +551,9 @@ class DoubleBlockFn(torch.autograd.Function):
 # Single-stream block
 # ------------------------------------------------------------------------------------------------
 class SingleBlockFn(torch.autograd.Function):
-    """h_out = FluxSingleTransformerBlock(h_in); LoRA order: to_q.A, to_q.B, to_k.A, to_k.B, to_v.A, to_v.B."""
+    """h_out = FluxSingleTransformerBlock(h_in); LoRA order: to_q.A, to_q.B, to_k.A, to_k.B, to_v.A, to_v.B,
+    proj_mlp.A, proj_mlp.B, proj_out.A, proj_out.B (the last four only for the "+ffs" / "tiny" / "nano" targets).
+    Dropout mask streams: q, k, v = 0..2, proj_mlp = 3, proj_out = 4 (over the logical cat[attn, mlp] input)."""
 
     @staticmethod
     def forward(ctx, h, mod, cos, sin, st, *lora):
@@ -500,12 +563,18 @@ class SingleBlockFn(torch.autograd.Function):
         ap: AttnPlan = plans["attn"]
         mp: MlpPlan = plans["mlp"]
         dev = h.device
+        n_lora_in = len(lora)
+        lora = list(lora) + [None] * (10 - len(lora))
+        scaling = st["lora_scaling"]
         ps = []
         for m in range(3):
             a, b = lora[2 * m], lora[2 * m + 1]
             ps.append(None if a is None else (a, b))
-        pk = pack_lora(ps, D, D, st["lora_scaling"], dev)
+        pk = pack_lora(ps, D, D, scaling, dev)
+        pk_mlp = _pack1(lora[6], lora[7], 4 * D, D, scaling, dev)
+        pk_out = _pack1(lora[8], lora[9], D, 5 * D, scaling, dev)
         drop: Optional[LoraDrop] = st.get("lora_drop")
+        dr = (lambda off: drop.at(off)) if drop is not None else (lambda off: None)
         nh = ops.ln_modulate_fwd(h, mod[:, 0:D], mod[:, D:2 * D], EPS)
         qkv, t_qkv = _linear_lora_fwd(nh, ap.w_qkv, ap.b_qkv, pk, drop)
         q, k = ops.qk_rmsnorm_rope_fwd(qkv, D, H, hd, ap.norm_q, ap.norm_k, None, None, 0, cos, sin, EPS)
@@ -515,59 +584,98 @@ class SingleBlockFn(torch.autograd.Function):
             del q, k
         o = o.view(B, S, D)
         pre = torch.empty((B, S, 4 * D), device=dev, dtype=torch.bfloat16)
-        act = ops.gemm([nh], [mp.w1], mp.b1, epi=ops.EPI_GELU, aux=pre)
+        act, t_mlp = _linear_lora_fwd(nh, mp.w1, mp.b1, pk_mlp, dr(3), epi=ops.EPI_GELU, aux=pre)
         del nh
         # proj_out(cat[attn, mlp]) as two K-segments of one GEMM; gate, residual, nan_to_num in the epilogue
-        h_out = ops.gemm([o, act], [mp.w2[:, :D], mp.w2[:, D:]], mp.b2, epi=ops.EPI_GATE_RES,
-                         gate=mod[:, 2 * D:3 * D], res=h, nan_to_num=True)
+        t_out = None
+        if pk_out is None:
+            h_out = ops.gemm([o, act], [mp.w2[:, :D], mp.w2[:, D:]], mp.b2, epi=ops.EPI_GATE_RES,
+                             gate=mod[:, 2 * D:3 * D], res=h, nan_to_num=True)
+        else:
+            if drop is None:
+                t_out = ops.gemm([o, act], [pk_out.a_stack[:, :D], pk_out.a_stack[:, D:]])
+            else:                       # one mask over the logical [B, S, 5D] input of the adapted Linear
+                t_out = _lora_down(torch.cat([o, act], 2), pk_out, dr(4))
+            h_out = ops.gemm([o, act, t_out], [mp.w2[:, :D], mp.w2[:, D:], pk_out.b_ext], mp.b2, epi=ops.EPI_GATE_RES,
+                             gate=mod[:, 2 * D:3 * D], res=h, nan_to_num=True)
         del act
         ctx.st = st
-        ctx.pack = pk
+        ctx.packs = (pk, pk_mlp, pk_out)
+        ctx.n_lora_in = n_lora_in
         ctx.lora_present = [x is not None for x in lora]
         E = h.new_empty(0)
-        ctx.save_for_backward(h, mod, cos, sin, qkv, o, lse, pre, t_qkv if t_qkv is not None else E,
-                              q if SAVE_QK else E, k if SAVE_QK else E)
+        keep = lambda t: t if t is not None else E
+        ctx.save_for_backward(h, mod, cos, sin, qkv, o, lse, pre, keep(t_qkv), q if SAVE_QK else E, k if SAVE_QK else E,
+                              keep(t_mlp), keep(t_out))
         return h_out
 
     @staticmethod
     def backward(ctx, dh_out):
-        h, mod, cos, sin, qkv, o, lse, pre, t_qkv, q_saved, k_saved = ctx.saved_tensors
+        h, mod, cos, sin, qkv, o, lse, pre, t_qkv, q_saved, k_saved, t_mlp, t_out = ctx.saved_tensors
         qk_saved = (q_saved, k_saved) if q_saved.numel() else None
         st = ctx.st
-        pk: Optional[LoraPack] = ctx.pack
+        pk, pk_mlp, pk_out = ctx.packs
         B, S, D = h.shape
         H, hd = st["H"], st["hd"]
         ap: AttnPlan = st["plans"]["attn"]
         mp: MlpPlan = st["plans"]["mlp"]
+        drop: Optional[LoraDrop] = st.get("lora_drop")
+        dr = (lambda off: drop.at(off)) if drop is not None else (lambda off: None)
         dh_out = dh_out.contiguous()
+        grads: List[Optional[torch.Tensor]] = [None] * 10
         g = ops.gate_mul(dh_out, mod[:, 2 * D:3 * D])
-        d_o = ops.gemm([g], [mp.w2_t[:D]], None)
-        d_pre = ops.gemm([g], [mp.w2_t[D:]], None, epi=ops.EPI_MUL_DGELU, aux=pre)
+        if pk_out is None:
+            d_o = ops.gemm([g], [mp.w2_t[:D]], None)
+            d_pre = ops.gemm([g], [mp.w2_t[D:]], None, epi=ops.EPI_MUL_DGELU, aux=pre)
+        else:
+            t_up = ops.gemm([g], [pk_out.b_ext_t])
+            act = ops.gelu_tanh(pre)
+            if drop is None:
+                d_o = ops.gemm([g, t_up], [mp.w2_t[:D], pk_out.a_stack_t[:D]], None)
+                d_pre = ops.gemm([g, t_up], [mp.w2_t[D:], pk_out.a_stack_t[D:]], None, epi=ops.EPI_MUL_DGELU, aux=pre)
+                (grads[8], grads[9]), = _lora_grads(pk_out, (o, act), t_out, g, t_up, None)
+            else:
+                d_cat = ops.gemm([g], [mp.w2_t], None)
+                _lora_dgrad_dropout(d_cat, t_up, pk_out, dr(4))
+                d_o = d_cat[:, :, :D].contiguous()
+                d_pre = ops.mul_dgelu_tanh(d_cat[:, :, D:], pre)
+                del d_cat
+                (grads[8], grads[9]), = _lora_grads(pk_out, torch.cat([o, act], 2), t_out, g, t_up, dr(4))
+            del act, t_up
         del g
         d_qkv = _attn_core_bwd(qkv, o, d_o, lse, D, H, hd, ap, None, 0, cos, sin, qk=qk_saved)
         del d_o, qk_saved, q_saved, k_saved
-        grads: List[Optional[torch.Tensor]] = [None] * 6
-        # d_nh = d_pre W_mlp + d_qkv W_qkv (+ LoRA)  — one GEMM, two/three K-segments
-        if pk is None:
+        # d_nh = d_pre W_mlp + d_qkv W_qkv (+ LoRA branches as one more K-segment)
+        t_ups, a_ts = [], []
+        t_up_qkv = t_up_mlp = None
+        if pk is not None:
+            t_up_qkv = ops.gemm([d_qkv], [pk.b_ext_t])
+            t_ups.append(t_up_qkv); a_ts.append(pk.a_stack_t)
+        if pk_mlp is not None:
+            t_up_mlp = ops.gemm([d_pre], [pk_mlp.b_ext_t])
+            t_ups.append(t_up_mlp); a_ts.append(pk_mlp.a_stack_t)
+        if not t_ups or drop is not None:
             d_nh = ops.gemm([d_pre, d_qkv], [mp.w1_t, ap.w_qkv_t], None)
-        else:
-            drop: Optional[LoraDrop] = st.get("lora_drop")
-            t_up = ops.gemm([d_qkv], [pk.b_ext_t])
-            if drop is None:
-                d_nh = ops.gemm([d_pre, d_qkv, t_up], [mp.w1_t, ap.w_qkv_t, pk.a_stack_t], None)
-            else:
-                d_nh = ops.gemm([d_pre, d_qkv], [mp.w1_t, ap.w_qkv_t], None)
-                _lora_dgrad_dropout(d_nh, t_up, pk, drop)
+            if pk is not None:
+                _lora_dgrad_dropout(d_nh, t_up_qkv, pk, drop)
+            if pk_mlp is not None:
+                _lora_dgrad_dropout(d_nh, t_up_mlp, pk_mlp, dr(3))
+        elif len(t_ups) == 1:
+            d_nh = ops.gemm([d_pre, d_qkv, t_ups[0]], [mp.w1_t, ap.w_qkv_t, a_ts[0]], None)
+        else:                           # the GEMM takes three K-segments: both rank blocks travel as one
+            d_nh = ops.gemm([d_pre, d_qkv, torch.cat(t_ups, 2)], [mp.w1_t, ap.w_qkv_t, torch.cat(a_ts, 1)], None)
+        if t_ups:
             nh = ops.ln_modulate_fwd(h, mod[:, 0:D], mod[:, D:2 * D], EPS)
-            for m, (da, db) in enumerate(_lora_grads(pk, nh, t_qkv, d_qkv, t_up, drop)):
-                grads[2 * m], grads[2 * m + 1] = da, db
+            if pk is not None:
+                for m, (da, db) in enumerate(_lora_grads(pk, nh, t_qkv, d_qkv, t_up_qkv, drop)):
+                    grads[2 * m], grads[2 * m + 1] = da, db
+            if pk_mlp is not None:
+                (grads[6], grads[7]), = _lora_grads(pk_mlp, nh, t_mlp, d_pre, t_up_mlp, dr(3))
             del nh
         del d_pre, d_qkv
         dh = ops.ln_modulate_bwd(d_nh, h, mod[:, D:2 * D], add=dh_out, eps=EPS)
-        for i, present in enumerate(ctx.lora_present):
-            if not present:
-                grads[i] = None
-        return (dh, None, None, None, None, *grads)
+        out = [grads[i] if ctx.lora_present[i] else None for i in range(ctx.n_lora_in)]
+        return (dh, None, None, None, None, *out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -575,27 +683,35 @@ class SingleBlockFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 class TailFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, mod, st):
-        """h [B, S, D] joint buffer; mod [B, 2D] = (scale | shift) (AdaLayerNormContinuous chunk order)."""
+    def forward(ctx, h, mod, st, *lora):
+        """h [B, S, D] joint buffer; mod [B, 2D] = (scale | shift) (AdaLayerNormContinuous chunk order).  lora: the final
+        proj_out's (A, B) — PEFT's suffix rule makes the "proj_out" target of "all+ffs" select it too."""
         D = h.shape[2]
         S_txt = st["S_txt"]
         x = h[:, S_txt:]
         nx = ops.ln_modulate_fwd(x, mod[:, D:2 * D], mod[:, 0:D], EPS)
-        out = ops.gemm([nx], [st["w_proj"]], st["b_proj"])
-        ctx.st = st
-        ctx.save_for_backward(h, mod)
+        a, b = (lora[0], lora[1]) if len(lora) >= 2 else (None, None)
+        pk = _pack1(a, b, st["w_proj"].shape[0], D, st.get("lora_scaling", 1.0), h.device)
+        out, t = _linear_lora_fwd(nx, st["w_proj"], st["b_proj"], pk, st.get("lora_drop"))
+        ctx.st, ctx.pack, ctx.n_lora_in = st, pk, len(lora)
+        ctx.save_for_backward(h, mod, t if t is not None else h.new_empty(0))
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        h, mod = ctx.saved_tensors
-        st = ctx.st
+        h, mod, t = ctx.saved_tensors
+        st, pk = ctx.st, ctx.pack
         D = h.shape[2]
         S_txt = st["S_txt"]
-        d_nx = ops.gemm([d_out.contiguous()], [st["w_proj_t"]], None)
+        d_out = d_out.contiguous()
+        d_nx, t_up = _linear_lora_dgrad(d_out, st["w_proj_t"], pk, st.get("lora_drop"))
+        lg = [None] * ctx.n_lora_in
+        if pk is not None:
+            nx = ops.ln_modulate_fwd(h[:, S_txt:], mod[:, D:2 * D], mod[:, 0:D], EPS)
+            (lg[0], lg[1]), = _lora_grads(pk, nx, t, d_out, t_up, st.get("lora_drop"))
         dh = torch.zeros_like(h) if S_txt > 0 else torch.empty_like(h)
         ops.ln_modulate_bwd(d_nx, h[:, S_txt:], mod[:, 0:D], add=None, eps=EPS, out=dh[:, S_txt:])
-        return dh, None, None
+        return (dh, None, None, *lg)
 
 
 class FlowLossFn(torch.autograd.Function):

@@ -89,6 +89,11 @@ class Flux:
             raise NotImplementedError(f"lora_type={g('lora_type')!r} (LyCORIS) is not supported by the libstb200 path")
         if g("use_dora", False):
             raise NotImplementedError("DoRA is not supported by the libstb200 path")
+        from .transformer import FLUX_LORA_TARGETS
+        tgt = g("flux_lora_target", "all") or "all"
+        if tgt not in FLUX_LORA_TARGETS:       # "ai-toolkit" (adaLN linears) / "controlnet" stay on the reference module
+            raise NotImplementedError(f"flux_lora_target={tgt!r} is not supported by the libstb200 path "
+                                      f"(supported: {sorted(FLUX_LORA_TARGETS)})")
         if g("flux_attention_masked_training", False):
             raise NotImplementedError("flux_attention_masked_training is not supported by the libstb200 Flux path (quirk Q2)")
         if g("tread_config", None):

@@ -31,14 +31,29 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .blocks import AttnPlan, DoubleBlockFn, LoraDrop, MlpPlan, SingleBlockFn, TailFn, _t
+from .blocks import AttnPlan, DoubleBlockFn, LoraDrop, LoraLinearFn, MlpPlan, SingleBlockFn, TailFn, _t
 
+_ATTN = ["to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_out.0", "to_add_out"]
+_FFS = ["ff.net.0.proj", "ff.net.2", "ff_context.net.0.proj", "ff_context.net.2", "proj_mlp", "proj_out"]
 FLUX_LORA_TARGETS = {
-    # reference flux/model.py:1235-1383 (names that exist un-fused)
-    "all": ["to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_out.0", "to_add_out"],
-    "mmdit": ["to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_out.0", "to_add_out"],
+    # reference flux/model.py:1235-1383 (names that exist un-fused; PEFT selects a Linear whose qualified name equals a
+    # target or ends with ".<target>", so "proj_out" covers every single block's proj_out and the model's final proj_out)
+    "all": _ATTN,
+    "mmdit": _ATTN,
     "context": ["add_q_proj", "add_k_proj", "add_v_proj", "to_add_out"],
+    "context+ffs": ["add_q_proj", "add_k_proj", "add_v_proj", "to_add_out", "ff_context.net.0.proj", "ff_context.net.2"],
+    "all+ffs": _ATTN + _FFS,
+    "all+ffs+embedder": ["x_embedder"] + _ATTN + _FFS,
+    "tiny": ["single_transformer_blocks.7.proj_out", "single_transformer_blocks.20.proj_out"],
+    "nano": ["single_transformer_blocks.7.proj_out"],
 }
+# Linears the block schedules can adapt; "ai-toolkit" additionally adapts the adaLN linears (norm.linear, norm1.linear,
+# norm1_context.linear), whose gradients need d loss / d modulation — not produced by the LoRA schedules
+_ADAPTABLE_SUFFIXES = tuple("." + t for t in (_ATTN + _FFS))
+
+
+def _peft_match(name: str, targets) -> bool:
+    return any(name == t or name.endswith("." + t) for t in targets)
 
 
 class _Weight(nn.Module):
@@ -185,6 +200,9 @@ class FluxTransformerBlock(nn.Module):
               "lora_drop": getattr(self, "_lora_drop", None)}
         a = self.attn
         lora = _lora_list([a.to_q, a.to_k, a.to_v, a.to_out[0], a.add_q_proj, a.add_k_proj, a.add_v_proj, a.to_add_out])
+        mlp = _lora_list([self.ff.net[0].proj, self.ff.net[2], self.ff_context.net[0].proj, self.ff_context.net[2]])
+        if any(t is not None for t in mlp):
+            lora = lora + [None] * 8 + mlp          # [16..23] = the SD3.5 second attention, unused here
         return DoubleBlockFn.apply(h, mod_img, mod_txt, cos, sin, st, *lora)
 
 
@@ -215,7 +233,11 @@ class FluxSingleTransformerBlock(nn.Module):
         st = {"H": self.heads, "hd": self.head_dim, "plans": self.plans(), "lora_scaling": lora_scaling,
               "lora_drop": getattr(self, "_lora_drop", None)}
         a = self.attn
-        return SingleBlockFn.apply(h, mod, cos, sin, st, *_lora_list([a.to_q, a.to_k, a.to_v]))
+        lora = _lora_list([a.to_q, a.to_k, a.to_v])
+        mlp = _lora_list([self.proj_mlp, self.proj_out])
+        if any(t is not None for t in mlp):
+            lora = lora + mlp
+        return SingleBlockFn.apply(h, mod, cos, sin, st, *lora)
 
 
 class _TimestepEmbedding(nn.Module):
@@ -433,16 +455,16 @@ class FluxTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
             raise NotImplementedError("fused LoRA path supports rank 1..128 (one 128-wide rank block per adapted Linear)")
         lora_alpha = float(lora_alpha) if lora_alpha is not None else float(rank)  # common.py:1090-1093
         targets = list(target_modules) if target_modules is not None else FLUX_LORA_TARGETS["all"]
-        supported = set(FLUX_LORA_TARGETS["all"])
         n = 0
+        chosen = []
         for name, mod in self.named_modules():
-            if not isinstance(mod, Linear):
+            if not isinstance(mod, Linear) or not _peft_match(name, targets):
                 continue
-            short = ".".join(name.split(".attn.")[-1:]) if ".attn." in name else None
-            if short is None or short not in targets:
-                continue
-            if short not in supported:
-                raise NotImplementedError(f"LoRA target {short} is not supported by the fused path")
+            if not (name.endswith(_ADAPTABLE_SUFFIXES) or name in ("proj_out", "x_embedder")):
+                raise NotImplementedError(f"LoRA target {name} is not supported by the fused path (adaLN / embedder linears: "
+                                          "use the reference module, e.g. for flux_lora_target=ai-toolkit)")
+            chosen.append(mod)
+        for mod in chosen:
             mod.add_lora(rank, lora_alpha, adapter_name)
             n += 1
         if n == 0:
@@ -514,7 +536,17 @@ class FluxTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
         dev = hidden_states.device
         # joint hidden buffer: [text | image]
         h = torch.empty((B, S_txt + S_img, D), device=dev, dtype=dt)
-        ops.gemm([hidden_states.to(dt).contiguous()], [self.x_embedder.weight], self.x_embedder.bias, out=h[:, S_txt:])
+        blocks = list(self.transformer_blocks) + list(self.single_transformer_blocks)
+        self._begin_lora_dropout(blocks + [self.proj_out, self.x_embedder])      # one mask-stream slot each
+        xa, xb = self.x_embedder.lora_tensors()
+        if xa is None or not torch.is_grad_enabled():
+            ops.gemm([hidden_states.to(dt).contiguous()], [self.x_embedder.weight], self.x_embedder.bias, out=h[:, S_txt:])
+            if xa is not None:          # inference with the adapter attached
+                h[:, S_txt:] += F.linear(F.linear(hidden_states.to(dt), xa), xb) * self._lora_scaling
+        else:
+            y = LoraLinearFn.apply(hidden_states.to(dt).contiguous(), self.x_embedder.weight, self.x_embedder.bias,
+                                   self._lora_scaling, getattr(self.x_embedder, "_lora_drop", None), xa, xb)
+            h[:, S_txt:].copy_(y)       # autograd routes the image rows of dh to the adapter
         ops.gemm([encoder_hidden_states.to(dt).contiguous()], [self.context_embedder.weight], self.context_embedder.bias,
                  out=h[:, :S_txt])
         # reference :1003-1007 — timestep / guidance arrive in [0,1] and are scaled by 1000 here
@@ -530,7 +562,6 @@ class FluxTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
             img_ids = img_ids[0]
         cos, sin = self._rope(txt_ids, img_ids, dev)[:2]
         scaling = self._lora_scaling
-        self._begin_lora_dropout(list(self.transformer_blocks) + list(self.single_transformer_blocks))
         for i, blk in enumerate(self.transformer_blocks):
             h = self._run_block(i, blk, h, silu_temb, cos, sin, S_txt, scaling)
         for i, blk in enumerate(self.single_transformer_blocks):
@@ -539,7 +570,10 @@ class FluxTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
             self._tail_plan = {"w_proj": self.proj_out.weight.detach(), "b_proj": self.proj_out.bias.detach(),
                                "w_proj_t": _t(self.proj_out.weight.detach())}
         mod = self.norm_out.linear(silu_temb)
-        out = TailFn.apply(h, mod, {"S_txt": S_txt, **self._tail_plan})
+        pa, pb = self.proj_out.lora_tensors()
+        tail_lora = () if pa is None else (pa, pb)
+        out = TailFn.apply(h, mod, {"S_txt": S_txt, "lora_scaling": scaling, "lora_drop": getattr(self.proj_out, "_lora_drop", None),
+                                    **self._tail_plan}, *tail_lora)
         if not return_dict:
             return (out,)
         return SimpleNamespace(sample=out)

@@ -323,6 +323,29 @@ def gate_mul(x, gate, out=None):
     return out
 
 
+def gelu_tanh(pre, out=None):
+    """out = gelu_tanh(pre) for a [B, S, D] view — the activation EPI_GELU produced, re-created from the saved pre-activation."""
+    _chk(pre, "pre")
+    B, S, D = pre.shape
+    if out is None:
+        out = torch.empty((B, S, D), device=pre.device, dtype=torch.bfloat16)
+    check(_lib.lib().stb_gelu_tanh(pre.data_ptr(), pre.stride(0), pre.stride(1), None, 0, 0, out.data_ptr(), out.stride(0),
+                                   out.stride(1), B, S, D, 0, _stream()))
+    return out
+
+
+def mul_dgelu_tanh(g, pre, out=None):
+    """out = g * gelu_tanh'(pre)  ([B, S, D] views; out may alias g)."""
+    _chk(pre, "pre"); _chk(g, "g")
+    B, S, D = pre.shape
+    assert g.shape == pre.shape
+    if out is None:
+        out = torch.empty((B, S, D), device=pre.device, dtype=torch.bfloat16)
+    check(_lib.lib().stb_gelu_tanh(pre.data_ptr(), pre.stride(0), pre.stride(1), g.data_ptr(), g.stride(0), g.stride(1),
+                                   out.data_ptr(), out.stride(0), out.stride(1), B, S, D, 1, _stream()))
+    return out
+
+
 def dropout_expand(x, members: int, p: float, seed: int, stream0: int):
     """x [B, S, K] (view) -> [members, B, S, K]: x * keep_m / (1 - p) with an independent counter-based mask per member."""
     _chk(x, "x")

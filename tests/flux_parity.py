@@ -44,7 +44,7 @@ def make_batch(B, Hh, Ww, S_txt, cfg, seed=0, C=16):
     }
 
 
-def build_cuda_model(cfg, P, lora, rank, device="cuda"):
+def build_cuda_model(cfg, P, lora, rank, device="cuda", target="all"):
     from simpletuner_b200.flux.model import Flux, default_config
     from simpletuner_b200.flux.transformer import FluxTransformer2DModel
 
@@ -58,7 +58,7 @@ def build_cuda_model(cfg, P, lora, rank, device="cuda"):
     assert not unexpected, unexpected
     assert not missing, missing
     m.to(device)
-    wrapper = Flux(default_config(lora_rank=rank), transformer=m, device=torch.device(device))
+    wrapper = Flux(default_config(lora_rank=rank, flux_lora_target=target), transformer=m, device=torch.device(device))
     if lora is not None:
         wrapper.add_lora_adapter()
         with torch.no_grad():
@@ -68,13 +68,17 @@ def build_cuda_model(cfg, P, lora, rank, device="cuda"):
     return wrapper
 
 
-def run_parity(cfg=None, B=2, Hh=16, Ww=16, S_txt=64, rank=16, seed=0, device="cuda", checkpoint=False, interval=None):
-    """Returns a dict of measured deviations (and asserts nothing)."""
+def run_parity(cfg=None, B=2, Hh=16, Ww=16, S_txt=64, rank=16, seed=0, device="cuda", checkpoint=False, interval=None,
+               target="all"):
+    """Returns a dict of measured deviations (and asserts nothing).  `target` = the reference's flux_lora_target."""
+    from simpletuner_b200.flux.transformer import FLUX_LORA_TARGETS
     cfg = cfg or small_config()
     P = {k: v.bfloat16().float() for k, v in O.init_flux_params(cfg, seed=seed).items()}
-    L = {k: v.bfloat16().float() for k, v in O.init_lora_params(cfg, rank, seed=seed + 1, b_std=0.02).items()}
+    L = {k: v.bfloat16().float() for k, v in O.init_lora_params(cfg, rank, seed=seed + 1, b_std=0.02,
+                                                                targets=tuple(FLUX_LORA_TARGETS[target])).items()}
     batch = make_batch(B, Hh, Ww, S_txt, cfg, seed=seed + 2)
-    w = build_cuda_model(cfg, P, L, rank, device)
+    w = build_cuda_model(cfg, P, L, rank, device, target=target)
+    assert set(w._denoiser().lora_linears()) == set(O.lora_target_names(cfg, tuple(FLUX_LORA_TARGETS[target])))
     if checkpoint:   # reference --gradient_checkpointing (+ interval): selected blocks are re-run in backward
         w._denoiser().enable_gradient_checkpointing()
         if interval:

@@ -82,3 +82,32 @@ def test_flux_gradient_checkpointing_matches():
         res = FP.run_parity(**kw)
         assert res["noisy_bit_exact"] and res["loss_rel_err"] <= FP.LOSS_RTOL and res["pred_cos"] >= FP.PRED_COS \
             and res["grad_cos_min"] >= FP.GRAD_COS, (kw, res)
+
+
+@pytest.mark.parametrize("target,rank", [("all+ffs", 16), ("all+ffs+embedder", 8), ("context+ffs", 16), ("context", 16), ("all+ffs", 64)])
+def test_flux_step_parity_lora_targets(target, rank):
+    """flux_lora_target presets beyond "all" (reference flux/model.py:1263-1376): adapters on the feed-forward projections,
+    the single blocks' proj_mlp / proj_out (input = cat[attn, mlp]), the final proj_out (PEFT suffix rule) and x_embedder."""
+    res = FP.run_parity(cfg=FP.small_config(layers=2, single=2), rank=rank, seed=11, target=target, B=2, Hh=20, Ww=12, S_txt=40)
+    if target == "all+ffs":
+        assert res["n_lora_tensors"] == 2 * (2 * 12 + 2 * 5 + 1)
+    _assert(res)
+
+
+def test_flux_tiny_target_adapts_only_the_named_single_blocks():
+    from oracle import flux_oracle as O
+    from simpletuner_b200.flux.transformer import FLUX_LORA_TARGETS
+    cfg = FP.small_config(layers=1, single=9)
+    assert O.lora_target_names(cfg, tuple(FLUX_LORA_TARGETS["tiny"])) == ["single_transformer_blocks.7.proj_out"]   # 20 does not exist here
+    res = FP.run_parity(cfg=cfg, rank=16, seed=13, target="tiny")
+    assert res["n_lora_tensors"] == 2
+    _assert(res)
+
+
+def test_unsupported_lora_targets_raise():
+    from simpletuner_b200.flux.model import Flux, default_config
+    with pytest.raises(NotImplementedError):
+        Flux.validate_config(default_config(flux_lora_target="ai-toolkit"))
+    w = FP.build_cuda_model(FP.small_config(layers=1, single=1), {k: v for k, v in __import__("oracle.flux_oracle", fromlist=["x"]).init_flux_params(FP.small_config(layers=1, single=1)).items()}, None, 8)
+    with pytest.raises(NotImplementedError):
+        w._denoiser().add_adapter(rank=8, target_modules=["norm1.linear"])

@@ -50,9 +50,11 @@ def _masks_for_flux(den, cfg, B, S_img, S_txt, p):
     D = cfg.num_attention_heads * cfg.attention_head_dim
     masks = {}
 
-    def grab(shape_S, drop, members):
-        ones = torch.ones(B, shape_S, D, device="cuda", dtype=torch.bfloat16)
+    def grab(shape_S, drop, members, K=D):
+        ones = torch.ones(B, shape_S, K, device="cuda", dtype=torch.bfloat16)
         return ops.dropout_expand(ones, members, drop.p, drop.seed, drop.stream).float().cpu()
+
+    adapted = set(den.lora_linears())
 
     for i, blk in enumerate(den.transformer_blocks):
         drop = blk._lora_drop
@@ -64,24 +66,41 @@ def _masks_for_flux(den, cfg, B, S_img, S_txt, p):
         m = grab(S_txt, drop.at(8), 3)
         masks[pre + "add_q_proj"], masks[pre + "add_k_proj"], masks[pre + "add_v_proj"] = m[0], m[1], m[2]
         masks[pre + "to_add_out"] = grab(S_txt, drop.at(14), 1)[0]
+        blk_name = f"transformer_blocks.{i}."
+        for nm, S_, off, K in (("ff.net.0.proj", S_img, 3, D), ("ff.net.2", S_img, 4, 4 * D),
+                               ("ff_context.net.0.proj", S_txt, 11, D), ("ff_context.net.2", S_txt, 12, 4 * D)):
+            if blk_name + nm in adapted:
+                masks[blk_name + nm] = grab(S_, drop.at(off), 1, K)[0]
     for j, blk in enumerate(den.single_transformer_blocks):
         drop = blk._lora_drop
         pre = f"single_transformer_blocks.{j}.attn."
         m = grab(S_img + S_txt, drop, 3)
         masks[pre + "to_q"], masks[pre + "to_k"], masks[pre + "to_v"] = m[0], m[1], m[2]
+        blk_name = f"single_transformer_blocks.{j}."
+        if blk_name + "proj_mlp" in adapted:
+            masks[blk_name + "proj_mlp"] = grab(S_img + S_txt, drop.at(3), 1)[0]
+        if blk_name + "proj_out" in adapted:
+            masks[blk_name + "proj_out"] = grab(S_img + S_txt, drop.at(4), 1, 5 * D)[0]
+    if "proj_out" in adapted:
+        masks["proj_out"] = grab(S_img, den.proj_out._lora_drop, 1)[0]
+    if "x_embedder" in adapted:
+        masks["x_embedder"] = grab(S_img, den.x_embedder._lora_drop, 1, cfg.in_channels)[0]
     return masks
 
 
-def test_flux_step_parity_with_lora_dropout_replayed_into_the_oracle():
+@pytest.mark.parametrize("target", ["all", "all+ffs+embedder"])
+def test_flux_step_parity_with_lora_dropout_replayed_into_the_oracle(target):
     from oracle import flux_oracle as O
+    from simpletuner_b200.flux.transformer import FLUX_LORA_TARGETS
 
     p = 0.1
     cfg = FP.small_config(layers=1, single=1)
     rank, B, Hh, Ww, S_txt = 16, 2, 16, 16, 64
     P = {k: v.bfloat16().float() for k, v in O.init_flux_params(cfg, seed=0).items()}
-    L = {k: v.bfloat16().float() for k, v in O.init_lora_params(cfg, rank, seed=1, b_std=0.02).items()}
+    L = {k: v.bfloat16().float() for k, v in O.init_lora_params(cfg, rank, seed=1, b_std=0.02,
+                                                                targets=tuple(FLUX_LORA_TARGETS[target])).items()}
     batch = FP.make_batch(B, Hh, Ww, S_txt, cfg, seed=2)
-    w = FP.build_cuda_model(cfg, P, None, rank)
+    w = FP.build_cuda_model(cfg, P, None, rank, target=target)
     w.config.lora_dropout = p
     w.add_lora_adapter()
     den = w._denoiser()
@@ -128,7 +147,7 @@ def test_flux_step_parity_with_lora_dropout_replayed_into_the_oracle():
             gmin_nomask = min(gmin_nomask, float(cos(g, Ln[f"{name}.{which}.weight"].grad.flatten(), dim=0)))
     res["grad_cos_min"] = gmin
     res["grad_cos_min_vs_unmasked_oracle"] = gmin_nomask
-    FP.record("flux_lora_dropout_0.1", res)
+    FP.record(f"flux_lora_dropout_0.1[{target}]", res)
     print("[lora-dropout]", res)
     # the masks matter: against the oracle WITHOUT them the LoRA gradients are visibly off (cos ~ sqrt(1 - p))
     assert res["dropout_effect"] > 1e-4 and res["grad_cos_min_vs_unmasked_oracle"] < 0.99, res
