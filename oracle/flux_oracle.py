@@ -161,12 +161,19 @@ def init_lora_params(cfg: FluxConfig, rank: int, seed: int = 1, dtype=torch.floa
 # `lora_B(lora_A(dropout(x)))` with one nn.Dropout per adapted Linear; the CUDA path draws its masks from its own
 # counter-based generator, so parity tests materialise those masks and replay them here.
 DROPOUT_MASKS: Optional[Dict[str, Tensor]] = None
+# LyCORIS LoKr settings used when the adapter dict carries `<linear>.lokr_w1` entries (reference documentation/LYCORIS.md default)
+LOKR: Dict[str, float] = {"linear_dim": 10000, "linear_alpha": 1, "multiplier": 1.0}
 
 
 def linear(x: Tensor, P: Dict[str, Tensor], name: str, lora: Optional[Dict[str, Tensor]] = None,
            lora_scale: float = 1.0) -> Tensor:
     """nn.Linear, optionally wrapped by PEFT lora.Linear (reference common.py:1094-1117):
     result = base(x) + lora_B(lora_A(dropout(x))) * scaling   (dropout = identity unless DROPOUT_MASKS replays a mask)."""
+    if lora is not None and (name + ".lokr_w1") in lora:
+        # LyCORIS LoKr (oracle/lokr_oracle.py): the adapted weight is rebuilt, y = linear(x, W + kron(w1, w2) * scale)
+        from .lokr_oracle import lokr_linear
+        return lokr_linear(x, P[name + ".weight"], P.get(name + ".bias"), lora, name, LOKR["linear_dim"], LOKR["linear_alpha"],
+                           LOKR.get("multiplier", 1.0))
     y = F.linear(x, P[name + ".weight"], P.get(name + ".bias"))
     if lora is not None and (name + ".lora_A.weight") in lora:
         a = lora[name + ".lora_A.weight"]

@@ -125,6 +125,38 @@ def pack_lora(params: List[Optional[Tuple[torch.Tensor, torch.Tensor]]], n_out: 
 
 
 @dataclass
+class LokrPack:
+    """LyCORIS LoKr members of one fused projection group (simpletuner_b200/lycoris.py).  The adapted weights are already
+    inside the plan's projection matrices, so forward / dgrad are adapter-free; only the factor gradients need the pack."""
+    members: List[Optional[Tuple[torch.Tensor, torch.Tensor, float]]]   # (w1 [a, c], w2 [b, d], scale * multiplier)
+    n_out: int
+    k_in: int
+
+
+def make_pack(params, n_out: int, k_in: int, scaling: float, device, lokr_scales=None, **kw):
+    """LoRA pack (pack_lora) or, when `lokr_scales[m]` is set for the present members, a LokrPack."""
+    if lokr_scales is not None and any(s is not None for s in lokr_scales):
+        mem = [None if p is None else (p[0], p[1], float(sc)) for p, sc in zip(params, lokr_scales)]
+        return LokrPack(mem, n_out, k_in) if any(m is not None for m in mem) else None
+    return pack_lora(params, n_out, k_in, scaling, device, **kw)
+
+
+def _lokr_grads(pack: LokrPack, x: torch.Tensor, dy: torch.Tensor):
+    """Factor gradients through delta W = kron(w1, w2) * scale: the full weight gradient of the group (one MN-major tcgen05
+    GEMM, dy^T x), contracted per member against the other Kronecker factor."""
+    from ..lycoris import lokr_factor_grads
+    dW = ops.wgrad_full(dy, x)                       # [members * n_out, K] bf16
+    out = []
+    for m, mem in enumerate(pack.members):
+        if mem is None:
+            out.append((None, None))
+            continue
+        w1, w2, sc = mem
+        out.append(lokr_factor_grads(dW[m * pack.n_out:(m + 1) * pack.n_out], w1, w2, sc))
+    return out
+
+
+@dataclass
 class LoraDrop:
     """PEFT `lora_dropout` state of one forward pass: probability, the step's seed and the first mask stream of the block
     (every adapted Linear of the model owns one stream, so q / k / v of one fused group draw independent masks)."""
@@ -157,6 +189,9 @@ def _lora_grads(pack: LoraPack, x: torch.Tensor, t_down: torch.Tensor, dy: torch
                 drop: Optional[LoraDrop] = None):
     """dA_stack [R, K] = T'^T x  (T' = dy B_ext, scaling already inside);  dB_ext^T [R, N] = T^T dy.
     With dropout dA_m contracts T'_m with the SAME masked copy of x the forward used (masks regenerated, not stored)."""
+    if isinstance(pack, LokrPack):
+        assert drop is None and not isinstance(x, (tuple, list))
+        return _lokr_grads(pack, x, dy)
     R = pack.a_stack.shape[0]
     wide = R > 128        # ranks above 40: the fused q|k|v rank block no longer fits one 128-wide weight-gradient tile
     if isinstance(x, (tuple, list)):        # the adapted Linear reads cat(x, -1) (single-block proj_out): one product per part
@@ -217,7 +252,7 @@ def _lora_dgrad_dropout(dx: torch.Tensor, t_up: torch.Tensor, pack: LoraPack, dr
 # ------------------------------------------------------------------------------------------------
 def _linear_lora_fwd(x, w, b, pack: Optional[LoraPack], drop: Optional[LoraDrop] = None, **kw):
     """y = x W^T + b (+ T B_ext^T as an extra K-segment).  Returns (y, T or None)."""
-    if pack is None:
+    if pack is None or isinstance(pack, LokrPack):
         return ops.gemm([x], [w], b, **kw), None
     t = _lora_down(x, pack, drop)
     return ops.gemm([x, t], [w, pack.b_ext], b, **kw), t
@@ -225,7 +260,7 @@ def _linear_lora_fwd(x, w, b, pack: Optional[LoraPack], drop: Optional[LoraDrop]
 
 def _linear_lora_dgrad(dy, w_t, pack: Optional[LoraPack], drop: Optional[LoraDrop] = None, **kw):
     """dx = dy W (+ (dy B_ext) A_stack).  Returns (dx, T' or None)."""
-    if pack is None:
+    if pack is None or isinstance(pack, LokrPack):
         return ops.gemm([dy], [w_t], None, **kw), None
     t_up = ops.gemm([dy], [pack.b_ext_t])
     if drop is None:
@@ -235,16 +270,16 @@ def _linear_lora_dgrad(dy, w_t, pack: Optional[LoraPack], drop: Optional[LoraDro
     return dx, t_up
 
 
-def _pack1(a, b, n_out: int, k_in: int, scaling: float, device) -> Optional[LoraPack]:
+def _pack1(a, b, n_out: int, k_in: int, scaling: float, device, lokr_scale=None):
     """Pack of a single adapted Linear (MLP projections, proj_out, x_embedder)."""
-    return None if a is None else pack_lora([(a, b)], n_out, k_in, scaling, device)
+    return None if a is None else make_pack([(a, b)], n_out, k_in, scaling, device, [lokr_scale])
 
 
 def _dgrad_through_gelu(dy, w_t, pack: Optional[LoraPack], drop: Optional[LoraDrop], pre):
     """d_pre = (dy W (+ LoRA branch)) * gelu'(pre).  Returns (d_pre, T' or None).  Without dropout the LoRA branch is one more
     K-segment and the activation gradient stays in the GEMM epilogue; with dropout the masked branch is added to the
     un-activated gradient first."""
-    if pack is None or drop is None:
+    if pack is None or drop is None or isinstance(pack, LokrPack):
         return _linear_lora_dgrad(dy, w_t, pack, None, epi=ops.EPI_MUL_DGELU, aux=pre)
     d_act, t_up = _linear_lora_dgrad(dy, w_t, pack, drop)
     return ops.mul_dgelu_tanh(d_act, pre, out=d_act), t_up
@@ -346,12 +381,15 @@ class DoubleBlockFn(torch.autograd.Function):
         streams = (("txt", slice(0, S_txt), mod_txt, 8), ("img", slice(S_txt, S), mod_img, 0))
         mlp_base = {"img": 24, "txt": 28}
 
+        ls = st.get("lokr_scales")                   # per (A, B) pair of the flat list: LoKr scale, or None for LoRA
+        lsc = (lambda i: ls[i // 2] if ls is not None and i // 2 < len(ls) else None)
+
         def lp(base, n_members, n_out, k_in):
             ps = []
             for m in range(n_members):
                 a, b = lora[base + 2 * m], lora[base + 2 * m + 1]
                 ps.append(None if a is None else (a, b))
-            return pack_lora(ps, n_out, k_in, scaling, dev)
+            return make_pack(ps, n_out, k_in, scaling, dev, [lsc(base + 2 * m) for m in range(n_members)])
 
         def mod_shift_scale(name, mod):
             if name == "txt" and pre_only:
@@ -417,8 +455,8 @@ class DoubleBlockFn(torch.autograd.Function):
             nh2 = ops.ln_modulate_fwd(h1[:, sl], mod[:, 3 * D:4 * D], mod[:, 4 * D:5 * D], EPS)
             pre = torch.empty((B, sl.stop - sl.start, 4 * D), device=dev, dtype=torch.bfloat16)
             mb = mlp_base[name]
-            pk1 = packs[name + "_fc1"] = _pack1(lora[mb], lora[mb + 1], 4 * D, D, scaling, dev)
-            pk2 = packs[name + "_fc2"] = _pack1(lora[mb + 2], lora[mb + 3], D, 4 * D, scaling, dev)
+            pk1 = packs[name + "_fc1"] = _pack1(lora[mb], lora[mb + 1], 4 * D, D, scaling, dev, lsc(mb))
+            pk2 = packs[name + "_fc2"] = _pack1(lora[mb + 2], lora[mb + 3], D, 4 * D, scaling, dev, lsc(mb + 2))
             act, t = _linear_lora_fwd(nh2, mp.w1, mp.b1, pk1, dr(base + 3), epi=ops.EPI_GELU, aux=pre)
             small[name + "_t_fc1"] = t
             del nh2
@@ -570,9 +608,13 @@ class SingleBlockFn(torch.autograd.Function):
         for m in range(3):
             a, b = lora[2 * m], lora[2 * m + 1]
             ps.append(None if a is None else (a, b))
-        pk = pack_lora(ps, D, D, scaling, dev)
-        pk_mlp = _pack1(lora[6], lora[7], 4 * D, D, scaling, dev)
-        pk_out = _pack1(lora[8], lora[9], D, 5 * D, scaling, dev)
+        ls = st.get("lokr_scales")
+        lsc = (lambda i: ls[i // 2] if ls is not None and i // 2 < len(ls) else None)
+        pk = make_pack(ps, D, D, scaling, dev, [lsc(0), lsc(2), lsc(4)])
+        pk_mlp = _pack1(lora[6], lora[7], 4 * D, D, scaling, dev, lsc(6))
+        pk_out = _pack1(lora[8], lora[9], D, 5 * D, scaling, dev, lsc(8))
+        if isinstance(pk_out, LokrPack):
+            raise NotImplementedError("LoKr on the single blocks' proj_out is not part of the LyCORIS presets supported here")
         drop: Optional[LoraDrop] = st.get("lora_drop")
         dr = (lambda off: drop.at(off)) if drop is not None else (lambda off: None)
         nh = ops.ln_modulate_fwd(h, mod[:, 0:D], mod[:, D:2 * D], EPS)
@@ -648,23 +690,24 @@ class SingleBlockFn(torch.autograd.Function):
         # d_nh = d_pre W_mlp + d_qkv W_qkv (+ LoRA branches as one more K-segment)
         t_ups, a_ts = [], []
         t_up_qkv = t_up_mlp = None
-        if pk is not None:
+        is_lora = lambda q: q is not None and not isinstance(q, LokrPack)
+        if is_lora(pk):
             t_up_qkv = ops.gemm([d_qkv], [pk.b_ext_t])
             t_ups.append(t_up_qkv); a_ts.append(pk.a_stack_t)
-        if pk_mlp is not None:
+        if is_lora(pk_mlp):
             t_up_mlp = ops.gemm([d_pre], [pk_mlp.b_ext_t])
             t_ups.append(t_up_mlp); a_ts.append(pk_mlp.a_stack_t)
         if not t_ups or drop is not None:
             d_nh = ops.gemm([d_pre, d_qkv], [mp.w1_t, ap.w_qkv_t], None)
-            if pk is not None:
+            if is_lora(pk):
                 _lora_dgrad_dropout(d_nh, t_up_qkv, pk, drop)
-            if pk_mlp is not None:
+            if is_lora(pk_mlp):
                 _lora_dgrad_dropout(d_nh, t_up_mlp, pk_mlp, dr(3))
         elif len(t_ups) == 1:
             d_nh = ops.gemm([d_pre, d_qkv, t_ups[0]], [mp.w1_t, ap.w_qkv_t, a_ts[0]], None)
         else:                           # the GEMM takes three K-segments: both rank blocks travel as one
             d_nh = ops.gemm([d_pre, d_qkv, torch.cat(t_ups, 2)], [mp.w1_t, ap.w_qkv_t, torch.cat(a_ts, 1)], None)
-        if t_ups:
+        if pk is not None or pk_mlp is not None:
             nh = ops.ln_modulate_fwd(h, mod[:, 0:D], mod[:, D:2 * D], EPS)
             if pk is not None:
                 for m, (da, db) in enumerate(_lora_grads(pk, nh, t_qkv, d_qkv, t_up_qkv, drop)):

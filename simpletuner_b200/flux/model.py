@@ -75,6 +75,26 @@ class Flux:
                                             target_modules=FLUX_LORA_TARGETS[c.flux_lora_target],
                                             lora_dropout=getattr(c, "lora_dropout", 0.0))
 
+    def add_lycoris_adapter(self, lycoris_config):
+        """trainer.py:3390-3505 (`lora_type = "lycoris"`): LycorisNetwork.apply_preset + create_lycoris + apply_to.  Takes the
+        parsed `lycoris_config.json` (or its path); returns the network whose `.parameters()` the optimizer trains."""
+        from .. import lycoris as LY
+        if isinstance(lycoris_config, str):
+            import json
+            with open(lycoris_config, "r") as f:
+                lycoris_config = json.load(f)
+        cfg = dict(lycoris_config)
+        multiplier = int(cfg.pop("multiplier", 1))
+        linear_dim = int(cfg.pop("linear_dim", 4))
+        linear_alpha = int(cfg.pop("linear_alpha", 1))
+        preset = cfg.pop("apply_preset", None)
+        if preset:
+            LY.LycorisNetwork.apply_preset(preset)
+        net = LY.create_lycoris(self._denoiser(), multiplier, linear_dim, linear_alpha, **cfg)
+        net.apply_to()
+        self.lycoris_wrapped_network = net
+        return net
+
     # ------------------------------------------------------------------------------------------
     @classmethod
     def validate_config(cls, c) -> None:
@@ -85,8 +105,18 @@ class Flux:
             raise NotImplementedError("controlnet training is not supported by the libstb200 path")
         if str(g("model_type", "lora")) not in ("lora",):
             raise NotImplementedError(f"model_type={g('model_type')!r}: only LoRA training runs on the libstb200 path")
-        if str(g("lora_type", "standard") or "standard").lower() not in ("standard",):
-            raise NotImplementedError(f"lora_type={g('lora_type')!r} (LyCORIS) is not supported by the libstb200 path")
+        lt = str(g("lora_type", "standard") or "standard").lower()
+        if lt == "lycoris":
+            cfg = g("lycoris_config", None)
+            if isinstance(cfg, str):
+                import json
+                with open(cfg, "r") as f:
+                    cfg = json.load(f)
+            if isinstance(cfg, dict):       # only LoKr (the reference's documented default) runs here
+                from ..lycoris import validate_lycoris_config
+                validate_lycoris_config(cfg)
+        elif lt != "standard":
+            raise NotImplementedError(f"lora_type={g('lora_type')!r} is not supported by the libstb200 path")
         if g("use_dora", False):
             raise NotImplementedError("DoRA is not supported by the libstb200 path")
         from .transformer import FLUX_LORA_TARGETS

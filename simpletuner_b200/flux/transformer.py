@@ -76,6 +76,7 @@ class Linear(nn.Module):
         self.lora_B: Optional[nn.ModuleDict] = None
         self.scaling: Dict[str, float] = {}
         self.lora_enabled = True
+        self.__dict__["lokr"] = None   # simpletuner_b200.lycoris.LokrModule (owned by the LycorisNetwork, not a sub-module)
 
     def add_lora(self, rank: int, alpha: float, adapter_name: str = "default", init_lora_weights: bool = True):
         dt = self.weight.dtype
@@ -90,10 +91,22 @@ class Linear(nn.Module):
         self.lora_B = nn.ModuleDict({adapter_name: b})
         self.scaling[adapter_name] = alpha / rank
 
+    _lokr_capable = False           # set on the Linears of Attention / FeedForward modules (the LyCORIS preset targets)
+
     def lora_tensors(self, adapter_name: str = "default"):
+        """The two trainable tensors the block schedules differentiate: LoRA (A, B) or the LoKr factors (w1, w2)."""
+        if self.lokr is not None:
+            return self.lokr.factors()
         if self.lora_A is None or not self.lora_enabled:
             return None, None
         return self.lora_A[adapter_name].weight, self.lora_B[adapter_name].weight
+
+    def lokr_scale(self) -> Optional[float]:
+        return None if self.lokr is None else self.lokr.scale * self.lokr.multiplier
+
+    def effective_weight(self) -> torch.Tensor:
+        """The weight the projection GEMMs read: W, or W + kron(w1, w2) * scale with a LoKr adapter (rebuilt per step)."""
+        return self.weight.detach() if self.lokr is None else self.lokr.effective_weight()
 
     def forward(self, x):  # small-M helper path (embedders / conditioning MLPs on [B, D] vectors)
         if self.weight.requires_grad and torch.is_grad_enabled():
@@ -127,6 +140,11 @@ class FluxAttention(nn.Module):
             self.norm_added_k = RMSNormWeight(head_dim, dtype)
             self.to_out = nn.ModuleList([Linear(dim, dim, dtype=dtype), nn.Identity()])
             self.to_add_out = Linear(dim, dim, dtype=dtype)
+        for m in self.modules():
+            if isinstance(m, Linear):
+                m._lokr_capable = True
+
+    _lycoris_class_name = "Attention"       # diffusers class name the LyCORIS presets select (documentation/LYCORIS.md)
 
 
 class _AdaNorm(nn.Module):
@@ -147,14 +165,19 @@ class _FeedForward(nn.Module):
     def __init__(self, dim, dtype):
         super().__init__()
         self.net = nn.ModuleList([_GELUProj(dim, 4 * dim, dtype), nn.Identity(), Linear(4 * dim, dim, dtype=dtype)])
+        self.net[0].proj._lokr_capable = True
+        self.net[2]._lokr_capable = True
+
+    _lycoris_class_name = "FeedForward"
 
 
 def _attn_plan(q: Linear, k: Linear, v: Linear, out: Optional[Linear], nq, nk) -> AttnPlan:
-    w_qkv = torch.cat([q.weight.detach(), k.weight.detach(), v.weight.detach()], 0).contiguous()
+    w_qkv = torch.cat([q.effective_weight(), k.effective_weight(), v.effective_weight()], 0).contiguous()
     b_qkv = torch.cat([q.bias.detach(), k.bias.detach(), v.bias.detach()], 0).contiguous()
     p = AttnPlan(w_qkv, b_qkv, _t(w_qkv), norm_q=nq.weight.detach(), norm_k=nk.weight.detach())
     if out is not None:
-        p.w_out, p.b_out, p.w_out_t = out.weight.detach(), out.bias.detach(), _t(out.weight.detach())
+        w_o = out.effective_weight()
+        p.w_out, p.b_out, p.w_out_t = w_o, out.bias.detach(), _t(w_o)
     return p
 
 
@@ -164,6 +187,12 @@ def _lora_list(linears: Sequence[Linear]) -> List[Optional[torch.Tensor]]:
         a, b = lin.lora_tensors()
         out += [a, b]
     return out
+
+
+def _lokr_scales(linears: Sequence[Optional[Linear]]) -> Optional[List[Optional[float]]]:
+    """Per (A, B) slot of the flat adapter list: the LoKr scale of that Linear (None = LoRA / not adapted)."""
+    sc = [None if lin is None else lin.lokr_scale() for lin in linears]
+    return sc if any(x is not None for x in sc) else None
 
 
 class FluxTransformerBlock(nn.Module):
@@ -182,8 +211,9 @@ class FluxTransformerBlock(nn.Module):
     def plans(self):
         if self._plans is None:
             a = self.attn
-            mk = lambda ff: MlpPlan(ff.net[0].proj.weight.detach(), ff.net[0].proj.bias.detach(), _t(ff.net[0].proj.weight.detach()),
-                                    ff.net[2].weight.detach(), ff.net[2].bias.detach(), _t(ff.net[2].weight.detach()))
+            def mk(ff):
+                w1, w2 = ff.net[0].proj.effective_weight(), ff.net[2].effective_weight()
+                return MlpPlan(w1, ff.net[0].proj.bias.detach(), _t(w1), w2, ff.net[2].bias.detach(), _t(w2))
             self._plans = {
                 "img_attn": _attn_plan(a.to_q, a.to_k, a.to_v, a.to_out[0], a.norm_q, a.norm_k),
                 "txt_attn": _attn_plan(a.add_q_proj, a.add_k_proj, a.add_v_proj, a.to_add_out, a.norm_added_q, a.norm_added_k),
@@ -199,8 +229,11 @@ class FluxTransformerBlock(nn.Module):
         st = {"S_txt": S_txt, "H": self.heads, "hd": self.head_dim, "plans": self.plans(), "lora_scaling": lora_scaling,
               "lora_drop": getattr(self, "_lora_drop", None)}
         a = self.attn
-        lora = _lora_list([a.to_q, a.to_k, a.to_v, a.to_out[0], a.add_q_proj, a.add_k_proj, a.add_v_proj, a.to_add_out])
-        mlp = _lora_list([self.ff.net[0].proj, self.ff.net[2], self.ff_context.net[0].proj, self.ff_context.net[2]])
+        attn_l = [a.to_q, a.to_k, a.to_v, a.to_out[0], a.add_q_proj, a.add_k_proj, a.add_v_proj, a.to_add_out]
+        mlp_l = [self.ff.net[0].proj, self.ff.net[2], self.ff_context.net[0].proj, self.ff_context.net[2]]
+        lora = _lora_list(attn_l)
+        mlp = _lora_list(mlp_l)
+        st["lokr_scales"] = _lokr_scales(attn_l + [None] * 4 + mlp_l)
         if any(t is not None for t in mlp):
             lora = lora + [None] * 8 + mlp          # [16..23] = the SD3.5 second attention, unused here
         return DoubleBlockFn.apply(h, mod_img, mod_txt, cos, sin, st, *lora)
@@ -234,6 +267,7 @@ class FluxSingleTransformerBlock(nn.Module):
               "lora_drop": getattr(self, "_lora_drop", None)}
         a = self.attn
         lora = _lora_list([a.to_q, a.to_k, a.to_v])
+        st["lokr_scales"] = _lokr_scales([a.to_q, a.to_k, a.to_v])
         mlp = _lora_list([self.proj_mlp, self.proj_out])
         if any(t is not None for t in mlp):
             lora = lora + mlp
@@ -435,6 +469,12 @@ class FluxTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
         self.invalidate_plans()
         return out
 
+    def after_optimizer_step(self):
+        """TrainStep hook: with a LyCORIS LoKr network attached the projection layouts embed W + kron(w1, w2) and must follow
+        the factors the optimizer just updated."""
+        if getattr(self, "_lycoris_network", None) is not None:
+            self.invalidate_plans()
+
     def lora_linears(self) -> Dict[str, Linear]:
         return {n: m for n, m in self.named_modules() if isinstance(m, Linear) and m.lora_A is not None}
 
@@ -450,6 +490,8 @@ class FluxTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
             lora_dropout = getattr(lora_config, "lora_dropout", lora_dropout)
         if rank is None:
             raise ValueError("LoRA rank is required")
+        if getattr(self, "_lycoris_network", None) is not None:
+            raise NotImplementedError("a LyCORIS network is attached: PEFT LoRA and LoKr adapters cannot be mixed on this path")
         lora_dropout = self._check_dropout_p(lora_dropout)
         if not 1 <= rank <= 128:
             raise NotImplementedError("fused LoRA path supports rank 1..128 (one 128-wide rank block per adapted Linear)")
