@@ -120,6 +120,52 @@ def build_model(device, cfg_over=None, rank=16, seed=0, target="all", dropout=0.
     return w
 
 
+LYCORIS_DEFAULT = {"algo": "lokr", "multiplier": 1.0, "linear_dim": 10000, "linear_alpha": 1, "factor": 10,
+                   "apply_preset": {"target_module": ["Attention", "FeedForward"],
+                                    "module_algo_map": {"Attention": {"factor": 10}, "FeedForward": {"factor": 4}}}}
+"""The reference's documented LyCORIS config (documentation/LYCORIS.md:24-47)."""
+
+
+def build_flux_lokr(device, cfg_over=None, seed=0):
+    """BASELINE configs[3]: Flux.1-dev + LyCORIS LoKr, latents encoded on the fly by the (random-init) Flux AutoencoderKL."""
+    from simpletuner_b200.flux.model import Flux, default_config
+    from simpletuner_b200.flux.transformer import FluxTransformer2DModel
+    from simpletuner_b200.vae.autoencoder import AutoencoderKL
+
+    kw = dict(FLUX_DEV)
+    kw.update(cfg_over or {})
+    with torch.device(device):
+        m = FluxTransformer2DModel(**kw)
+        vae = AutoencoderKL()
+    g = torch.Generator(device=device).manual_seed(seed)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if name.endswith("norm_q.weight") or name.endswith("norm_k.weight") or "norm_added" in name:
+                p.fill_(1.0)
+            elif name.endswith(".bias"):
+                p.normal_(0.0, 0.01, generator=g)
+            else:
+                p.normal_(0.0, 0.02, generator=g)
+        for n, p in vae.named_parameters():
+            p.normal_(0.0, 0.02, generator=g) if p.dim() > 1 else (p.fill_(1.0) if "norm" in n and n.endswith("weight") else p.zero_())
+    w = Flux(default_config(lora_type="lycoris"), transformer=m, device=device)
+    net = w.add_lycoris_adapter(json.loads(json.dumps(LYCORIS_DEFAULT)))
+    net.to(device)
+    with torch.no_grad():   # non-zero w2 so the w1 gradient path does real work (LyCORIS initialises w2 = 0)
+        for lora in net.loras:
+            lora.lokr_w2.normal_(0.0, 0.01, generator=g)
+    m.invalidate_plans()
+    return w, net, vae
+
+
+def lokr_extra_tf_per_sample():
+    """One more weight-gradient GEMM (2 * tokens * N * K) per LoKr-adapted Linear, per image."""
+    D = 3072
+    dbl = 2 * (S_IMG * (4 * D * D + 2 * 4 * D * D) + S_TXT * (4 * D * D + 2 * 4 * D * D))   # q,k,v,out + fc1,fc2 per stream
+    sgl = 2 * (S_IMG + S_TXT) * 3 * D * D
+    return (19 * dbl + 38 * sgl) * 1e-12
+
+
 def synth_batch(B, device, pinned=False, seed=0, hw=128, s_txt=S_TXT, joint=4096, pooled=768):
     g = torch.Generator().manual_seed(seed)
     b = {"latent_batch": torch.randn(B, 16, hw, hw, generator=g).bfloat16(),
@@ -607,7 +653,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=device)
     sd3 = args.config == "sd3_fullft"
     pix = args.config == "pixart_lora"
-    B = args.batch if args.batch else (8 if sd3 else 4)
+    lokr = args.config == "flux_lokr"
+    B = args.batch if args.batch else (8 if sd3 else (2 if lokr else 4))
     cfg_over = None
     hw, s_txt = 128, S_TXT
     if args.tiny:  # plumbing check only (never a bench value)
@@ -619,6 +666,8 @@ def run_b200(args):
             args.dp = "flat"     # CUDA-graph replay of fwd + bwd, then one flat 5 GB all-reduce; `--dp ddp` = torch DDP buckets (eager)
     elif pix:
         wrapper = build_pixart_lora(device, rank=32, seed=0, tiny=args.tiny)
+    elif lokr:
+        wrapper, lokr_net, vae = build_flux_lokr(device, cfg_over, seed=0)
     else:
         wrapper = build_model(device, cfg_over, rank=16, seed=0, target=args.lora_target, dropout=args.lora_dropout)
     if args.gradient_checkpointing:   # non-default: the reference's --gradient_checkpointing memory / time trade-off
@@ -626,6 +675,8 @@ def run_b200(args):
     if world > 1 and args.dp == "ddp":
         wrap_ddp(wrapper, device_ids=[local_rank])
     params = [p for p in wrapper._denoiser().parameters() if p.requires_grad]
+    if lokr:
+        params = list(lokr_net.parameters())
     if args.optimizer == "adamw_bf16":   # the reference's default optimizer, one libstb200 launch per step
         from simpletuner_b200.training.optim import AdamWBF16
         opt = AdamWBF16(params, lr=1e-4, weight_decay=1e-2, eps=1e-6, seed=1234 + rank)
@@ -662,6 +713,23 @@ def run_b200(args):
     else:
         dev_batches = [synth_batch(B, device, seed=100 + rank * 10 + i, hw=hw, s_txt=s_txt, joint=joint, pooled=pooled) for i in range(2)]
         host_batches = [synth_batch(B, device, pinned=True, seed=200 + rank * 10 + i, hw=hw, s_txt=s_txt, joint=joint, pooled=pooled) for i in range(2)]
+    if lokr:
+        # on-the-fly VAE encode (BASELINE configs[3]): the batch carries PIXELS; every step encodes them to latents first
+        # (vae.encode -> latent_dist.sample() -> scale_vae_latents_for_cache, caching/vae.py:1293-1355) inside the timed region
+        res = hw * 8
+        gpx = torch.Generator().manual_seed(300 + rank)
+        for bl, pin in ((dev_batches, False), (host_batches, True)):
+            for b in bl:
+                px = (torch.rand(B, 3, res, res, generator=gpx) * 2 - 1).bfloat16()
+                b.pop("latent_batch")
+                b["pixels"] = px.pin_memory() if pin else px.to(device)
+        inner_step = step
+
+        def step(batch):      # noqa: F811 — the user-facing call of this config: pixels in, loss out
+            batch = dict(batch)
+            batch["latent_batch"] = vae.encode_scaled(batch.pop("pixels"))
+            return inner_step(batch)
+        step.check_finite = inner_step.check_finite
     nbat = len(dev_batches)
 
     def barrier():
@@ -758,6 +826,18 @@ def run_b200(args):
             workload = ("PixArt-Sigma XL (28 blocks, D=1152, 16x72 heads) LoRA rank 32 on attention projections, bf16, mixed aspect buckets "
                         "512^2..1536^2 (latents 64x64 .. 192x192) + 300 caption tokens with random-length masks, epsilon prediction, "
                         "one step = 4 micro-batches (grad-accum 4) + value-clip (0.01) + adamw_bf16")
+        if lokr:
+            n_t = len(lokr_net.loras)
+            n_p = sum(p.numel() for p in lokr_net.parameters())
+            metric = "images/sec Flux.1-dev LyCORIS LoKr bf16 1024^2, on-the-fly VAE encode"
+            workload = (f"Flux.1-dev LyCORIS LoKr (documentation/LYCORIS.md default: linear_dim 10000 = full-matrix w2, factor 10 on Attention / "
+                        f"4 on FeedForward; {n_t} adapted Linears, {n_p / 1e6:.1f}M trainable) bf16, 1024^2 PIXELS [B,3,1024,1024] + T5 [B,512,4096]; "
+                        "train step = AutoencoderKL encode + sample + scale (on the fly) + prepare_batch + fwd + loss + bwd (full weight "
+                        "gradient of every adapted Linear, contracted to the Kronecker factors) + value-clip + adamw_bf16 + per-step "
+                        "rebuild of W + kron(w1, w2)")
+            # fwd 1x + dgrad 1x as LoRA-free model, + one more weight-gradient GEMM per adapted Linear (attention + FF of the double
+            # blocks, q/k/v of the single blocks) + the VAE encode
+            tf_sample = TF_STEP_SAMPLE + lokr_extra_tf_per_sample() + vae_conv_flops(H=1024, W=1024) * 1e-12
         if sd3:
             tf_sample = sum(sd3_tf_per_sample(hw_) for hw_ in SD3_BUCKETS) / len(SD3_BUCKETS)
             metric = "images/sec SD3.5-medium full fine-tune bf16 512^2 buckets"
@@ -831,7 +911,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 4 for flux_lora, 8 for sd3_fullft)")
-    ap.add_argument("--config", default="flux_lora", choices=["flux_lora", "sd3_fullft", "pixart_lora", "vae_encode"],
+    ap.add_argument("--config", default="flux_lora", choices=["flux_lora", "sd3_fullft", "pixart_lora", "vae_encode", "flux_lokr"],
                     help="flux_lora = BASELINE configs[1] (the headline metric); sd3_fullft = configs[2] (SD3.5-medium full fine-tune); "
                          "pixart_lora = configs[4] (PixArt-Sigma LoRA r32, mixed buckets, grad-accum 4); vae_encode = the VAE cache path")
     ap.add_argument("--tiny", action="store_true", help="plumbing check on a toy config (not a benchmark value)")

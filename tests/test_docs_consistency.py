@@ -1,5 +1,5 @@
 """CPU: the written claims that are cheap to verify mechanically — symbol counts quoted in the docs, and that every
-`profiles/r01/...` artefact the docs cite is committed."""
+`profiles/rNN/...` artefact the docs cite is committed."""
 import re
 from pathlib import Path
 
@@ -18,11 +18,16 @@ def test_symbol_counts_in_docs_match_the_abi():
 
 def test_cited_profile_files_exist():
     missing = []
-    for doc in ("DESIGN.md", "README.md", "profiles/r01/README.md"):
+    for doc in ("DESIGN.md", "README.md", "INTEGRATION.md", "profiles/r01/README.md", "profiles/r02/README.md"):
         text = (ROOT / doc).read_text()
-        for m in re.finditer(r"profiles/r01/([A-Za-z0-9_.\-]+\.(?:json|jsonl|csv|log|txt))", text):
-            if not (ROOT / "profiles" / "r01" / m.group(1)).exists():
-                missing.append((doc, m.group(1)))
+        for m in re.finditer(r"profiles/(r0[12])/([A-Za-z0-9_.\-]+\.(?:json|jsonl|csv|log|txt))", text):
+            if not (ROOT / "profiles" / m.group(1) / m.group(2)).exists():
+                missing.append((doc, m.group(1), m.group(2)))
+        if doc.startswith("profiles/"):      # a round's own README may cite its artefacts by bare file name
+            rnd = doc.split("/")[1]
+            for m in re.finditer(r"`([A-Za-z0-9_.\-]+\.(?:json|jsonl|csv|log|txt))`", text):
+                if not (ROOT / "profiles" / rnd / m.group(1)).exists():
+                    missing.append((doc, rnd, m.group(1)))
     assert not missing, missing
 
 
