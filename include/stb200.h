@@ -212,6 +212,22 @@ int stb_target_mse_loss(const void* pred_packed, const void* target, const float
                         void* dpred_packed, float grad_scale, int B, int C, int Hh, int Ww, int layout, int loss_type,
                         const float* huber_c, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * LyCORIS LoKr (lora_type = "lycoris", algo = "lokr": helpers/training/trainer.py:3390-3505; module attributes lokr_w1 /
+ * lokr_w2 / org_weight as used by helpers/training/peft_init.py:34-38; algorithm from the third-party lycoris-lora, setup.py:319):
+ *   delta W = kron(w1 [a, c], w2 [b, d]) * scale on a Linear of shape [a*b, c*d];  y = linear(x, W + delta W).
+ *   stb_lokr_rebuild     : out = bf16(W + delta W) (row stride out_row_stride) and, when out_t != NULL, its transpose
+ *                          (row stride out_t_row_stride) in the same pass — once per optimizer step, straight into the fused
+ *                          q|k|v / dgrad layouts the GEMMs read.
+ *   stb_lokr_factor_grads: dw1 [a, c], dw2 [b, d] (fp32, overwritten) from the full weight gradient dW [a*b, c*d] (bf16):
+ *                          dw1[i,k] = scale * sum_{j,l} dW[ib+j, kd+l] w2[j,l];  dw2[j,l] = scale * sum_{i,k} dW[ib+j, kd+l] w1[i,k]
+ *                          — what autograd computes through torch.kron in the reference.  d % 8 == 0.
+ * ------------------------------------------------------------------------------------------- */
+int stb_lokr_rebuild(const void* W, long long w_row_stride, const void* w1, const void* w2, float scale, void* out,
+                     long long out_row_stride, void* out_t, long long out_t_row_stride, int a, int b, int c, int d, void* stream);
+int stb_lokr_factor_grads(const void* dW, long long dw_row_stride, const void* w1, const void* w2, float scale, float* dw1,
+                          float* dw2, int a, int b, int c, int d, void* stream);
+
 /* GELU(tanh) outside a GEMM epilogue, for the adapters on the MLP projections (flux_lora_target "all+ffs", "context+ffs",
  * "tiny" ...: reference flux/model.py:1272-1376; activation: flux/transformer.py:447, diffusers FeedForward
  * "gelu-approximate").  mode 0: y = gelu(pre) (the activation the forward epilogue produced, re-created from the saved

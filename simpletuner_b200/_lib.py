@@ -136,6 +136,8 @@ SYMBOLS = {
     "stb_adamw_bf16_multi": (_I, [_P, _P, _P, _P, _P, _I, _I, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, _LL, C.c_ulonglong, C.c_double, _P, C.c_double, _P]),
     "stb_adamw_bf16_chunk": (_I, []),
     "stb_gate_mul": (_I, [_P, _LL, _LL, _P, _LL, _P, _LL, _LL, _I, _I, _I, _P]),
+    "stb_lokr_rebuild": (_I, [_P, _LL, _P, _P, C.c_float, _P, _LL, _P, _LL, _I, _I, _I, _I, _P]),
+    "stb_lokr_factor_grads": (_I, [_P, _LL, _P, _P, C.c_float, _P, _P, _I, _I, _I, _I, _P]),
     "stb_gelu_tanh": (_I, [_P, _LL, _LL, _P, _LL, _LL, _P, _LL, _LL, _I, _I, _I, _I, _P]),
     "stb_dropout_expand": (_I, [_P, _LL, _LL, _P, _I, _I, _I, _I, _F, C.c_uint, C.c_uint, _P]),
     "stb_dropout_accum": (_I, [_P, _P, _LL, _LL, _I, _I, _I, _I, _F, C.c_uint, C.c_uint, _P]),

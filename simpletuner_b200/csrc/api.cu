@@ -15,6 +15,7 @@
 #include <string>
 #include <unordered_map>
 
+#include <climits>
 #include "../../include/stb200.h"
 #include "attn_bwd.cuh"
 #include "attn_bwd128.cuh"
@@ -24,6 +25,7 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "wgrad_full.cuh"
+#include "lokr.cuh"
 #include "vae.cuh"
 #include "wgrad.cuh"
 
@@ -715,6 +717,39 @@ int stb_gate_mul(const void* x, long long x_b, long long x_s, const void* gate, 
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
   stb::gate_mul_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_b, x_s, static_cast<const __nv_bfloat16*>(gate), g_b, static_cast<__nv_bfloat16*>(y), y_b, y_s, B, S, D);
   STB_LAUNCH_CHECK("gate_mul");
+  return 0;
+}
+
+int stb_lokr_rebuild(const void* W, long long w_row_stride, const void* w1, const void* w2, float scale, void* out,
+                     long long out_row_stride, void* out_t, long long out_t_row_stride, int a, int b, int c, int d, void* stream) {
+  if (int r = check_device()) return r;
+  if (!W || !w1 || !w2 || !out || a < 1 || b < 1 || c < 1 || d < 1) return fail(STB_ERR_ARG, "lokr_rebuild: bad arguments");
+  const long long N = (long long)a * b, K = (long long)c * d;
+  if (N > INT_MAX || K > INT_MAX) return fail(STB_ERR_ARG, "lokr_rebuild: shape too large");
+  if (!aligned16(W) || !aligned16(out) || (out_t && !aligned16(out_t))) return fail(STB_ERR_ARG, "lokr_rebuild: pointers must be 16-byte aligned");
+  dim3 grid((unsigned)((K + stb::LOKR_TILE - 1) / stb::LOKR_TILE), (unsigned)((N + stb::LOKR_TILE - 1) / stb::LOKR_TILE));
+  stb::lokr_rebuild_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(W), w_row_stride, static_cast<const __nv_bfloat16*>(w1), static_cast<const __nv_bfloat16*>(w2),
+      scale, static_cast<__nv_bfloat16*>(out), out_row_stride, static_cast<__nv_bfloat16*>(out_t), out_t_row_stride, (int)N, (int)K, b, c, d);
+  STB_LAUNCH_CHECK("lokr_rebuild");
+  return 0;
+}
+
+int stb_lokr_factor_grads(const void* dW, long long dw_row_stride, const void* w1, const void* w2, float scale, float* dw1,
+                          float* dw2, int a, int b, int c, int d, void* stream) {
+  if (int r = check_device()) return r;
+  if (!dW || !w1 || !w2 || !dw1 || !dw2 || a < 1 || b < 1 || c < 1 || d < 8) return fail(STB_ERR_ARG, "lokr_factor_grads: bad arguments");
+  if ((d & 7) || (dw_row_stride & 7) || !aligned16(dW) || !aligned16(w2) || !aligned16(dw2))
+    return fail(STB_ERR_ARG, "lokr_factor_grads: d and the dW row stride must be multiples of 8, pointers 16-byte aligned");
+  if ((long long)a * c * 4 > 48 * 1024) return fail(STB_ERR_ARG, "lokr_factor_grads: a * c too large for the partial-sum buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  STB_CUDA(cudaMemsetAsync(dw1, 0, sizeof(float) * (size_t)a * c, st));
+  const long long vecs = ((long long)b * d) / 8;
+  const int grid = (int)((vecs + 255) / 256);
+  stb::lokr_factor_grad_kernel<<<grid, 256, sizeof(float) * (size_t)a * c, st>>>(
+      static_cast<const __nv_bfloat16*>(dW), dw_row_stride, static_cast<const __nv_bfloat16*>(w1), static_cast<const __nv_bfloat16*>(w2),
+      scale, dw1, dw2, a, b, c, d);
+  STB_LAUNCH_CHECK("lokr_factor_grads");
   return 0;
 }
 

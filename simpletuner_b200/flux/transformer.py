@@ -171,13 +171,41 @@ class _FeedForward(nn.Module):
     _lycoris_class_name = "FeedForward"
 
 
+def _fill_weight(lin: Linear, out: torch.Tensor, out_t: torch.Tensor) -> None:
+    """Write `lin`'s effective weight and its transpose into (slices of) a plan's layouts; with a LoKr adapter both come out of
+    one `stb_lokr_rebuild` pass over W."""
+    if lin.lokr is None:
+        out.copy_(lin.weight.detach())
+        out_t.copy_(lin.weight.detach().t())
+    else:
+        lin.lokr.rebuild_into(out, out_t)
+
+
+def _weight_pair(lin: Linear) -> Tuple[torch.Tensor, torch.Tensor]:
+    if lin.lokr is None:
+        w = lin.weight.detach()
+        return w, _t(w)
+    w = torch.empty_like(lin.weight)
+    w_t = torch.empty((lin.in_features, lin.out_features), device=w.device, dtype=w.dtype)
+    _fill_weight(lin, w, w_t)
+    return w, w_t
+
+
 def _attn_plan(q: Linear, k: Linear, v: Linear, out: Optional[Linear], nq, nk) -> AttnPlan:
-    w_qkv = torch.cat([q.effective_weight(), k.effective_weight(), v.effective_weight()], 0).contiguous()
     b_qkv = torch.cat([q.bias.detach(), k.bias.detach(), v.bias.detach()], 0).contiguous()
-    p = AttnPlan(w_qkv, b_qkv, _t(w_qkv), norm_q=nq.weight.detach(), norm_k=nk.weight.detach())
+    if q.lokr is None and k.lokr is None and v.lokr is None:
+        w_qkv = torch.cat([q.weight.detach(), k.weight.detach(), v.weight.detach()], 0).contiguous()
+        w_qkv_t = _t(w_qkv)
+    else:
+        n, kin = q.out_features, q.in_features
+        w_qkv = torch.empty((3 * n, kin), device=q.weight.device, dtype=q.weight.dtype)
+        w_qkv_t = torch.empty((kin, 3 * n), device=q.weight.device, dtype=q.weight.dtype)
+        for m, lin in enumerate((q, k, v)):
+            _fill_weight(lin, w_qkv[m * n:(m + 1) * n], w_qkv_t[:, m * n:(m + 1) * n])
+    p = AttnPlan(w_qkv, b_qkv, w_qkv_t, norm_q=nq.weight.detach(), norm_k=nk.weight.detach())
     if out is not None:
-        w_o = out.effective_weight()
-        p.w_out, p.b_out, p.w_out_t = w_o, out.bias.detach(), _t(w_o)
+        p.w_out, p.w_out_t = _weight_pair(out)
+        p.b_out = out.bias.detach()
     return p
 
 
@@ -212,8 +240,8 @@ class FluxTransformerBlock(nn.Module):
         if self._plans is None:
             a = self.attn
             def mk(ff):
-                w1, w2 = ff.net[0].proj.effective_weight(), ff.net[2].effective_weight()
-                return MlpPlan(w1, ff.net[0].proj.bias.detach(), _t(w1), w2, ff.net[2].bias.detach(), _t(w2))
+                (w1, w1_t), (w2, w2_t) = _weight_pair(ff.net[0].proj), _weight_pair(ff.net[2])
+                return MlpPlan(w1, ff.net[0].proj.bias.detach(), w1_t, w2, ff.net[2].bias.detach(), w2_t)
             self._plans = {
                 "img_attn": _attn_plan(a.to_q, a.to_k, a.to_v, a.to_out[0], a.norm_q, a.norm_k),
                 "txt_attn": _attn_plan(a.add_q_proj, a.add_k_proj, a.add_v_proj, a.to_add_out, a.norm_added_q, a.norm_added_k),

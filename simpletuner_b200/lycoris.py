@@ -94,7 +94,17 @@ class LokrModule(nn.Module):
     def effective_weight(self) -> torch.Tensor:
         """org_weight + kron(w1, w2) * scale * multiplier, rounded once to the weight dtype."""
         w = self._org.weight
+        if w.is_cuda:
+            return self.rebuild_into(torch.empty_like(w))
         return (w.float() + self.delta_weight()).to(w.dtype)
+
+    @torch.no_grad()
+    def rebuild_into(self, out: torch.Tensor, out_t: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One `stb_lokr_rebuild` pass: the adapted weight (and its transpose) written straight into (slices of) the fused
+        projection / dgrad layouts."""
+        from . import ops
+        return ops.lokr_rebuild(self._org.weight.detach(), self.lokr_w1.detach().contiguous(), self.w2().detach().contiguous(),
+                                self.scale * self.multiplier, out, out_t)
 
 
 class LycorisNetwork(nn.Module):
@@ -231,7 +241,11 @@ def create_lycoris(module: nn.Module, multiplier: float = 1.0, linear_dim: int =
 def lokr_factor_grads(dW: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, scale: float):
     """(d w1, d w2) from the full weight gradient dW [a b, c d] (see the module docstring)."""
     (a, c), (b, d) = w1.shape, w2.shape
-    g = dW.view(a, b, c, d).float()
+    if dW.is_cuda and d % 8 == 0 and dW.stride(0) % 8 == 0 and dW.stride(1) == 1 and a * c * 4 <= 48 * 1024:
+        from . import ops
+        dw1, dw2 = ops.lokr_factor_grads(dW, w1.detach().contiguous(), w2.detach().contiguous(), scale)
+        return dw1.to(w1.dtype), dw2.to(w2.dtype)
+    g = dW.reshape(a, b, c, d).float()
     dw1 = torch.einsum("ajcl,jl->ac", g, w2.float()) * scale
     dw2 = torch.einsum("ajcl,ac->jl", g, w1.float()) * scale
     return dw1.to(w1.dtype), dw2.to(w2.dtype)

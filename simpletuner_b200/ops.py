@@ -323,6 +323,33 @@ def gate_mul(x, gate, out=None):
     return out
 
 
+def lokr_rebuild(W, w1, w2, scale: float, out, out_t=None):
+    """out = bf16(W + kron(w1, w2) * scale) (and its transpose into out_t): row-strided 2-D views (fused projection layouts)."""
+    for t, nm in ((W, "W"), (w1, "w1"), (w2, "w2"), (out, "out")):
+        _chk(t, nm)
+    (a, c), (b, d) = w1.shape, w2.shape
+    assert W.shape == (a * b, c * d) and out.shape == W.shape and w1.is_contiguous() and w2.is_contiguous()
+    if out_t is not None:
+        _chk(out_t, "out_t")
+        assert out_t.shape == (c * d, a * b)
+    check(_lib.lib().stb_lokr_rebuild(W.data_ptr(), W.stride(0), w1.data_ptr(), w2.data_ptr(), float(scale), out.data_ptr(),
+                                      out.stride(0), _ptr(out_t), out_t.stride(0) if out_t is not None else 0, a, b, c, d, _stream()))
+    return out
+
+
+def lokr_factor_grads(dW, w1, w2, scale: float):
+    """(dw1 [a, c], dw2 [b, d]) fp32 from the full weight gradient dW [a b, c d] (bf16 view with unit inner stride)."""
+    for t, nm in ((dW, "dW"), (w1, "w1"), (w2, "w2")):
+        _chk(t, nm)
+    (a, c), (b, d) = w1.shape, w2.shape
+    assert dW.shape == (a * b, c * d) and w1.is_contiguous() and w2.is_contiguous()
+    dw1 = torch.empty((a, c), device=dW.device, dtype=torch.float32)
+    dw2 = torch.empty((b, d), device=dW.device, dtype=torch.float32)
+    check(_lib.lib().stb_lokr_factor_grads(dW.data_ptr(), dW.stride(0), w1.data_ptr(), w2.data_ptr(), float(scale),
+                                           dw1.data_ptr(), dw2.data_ptr(), a, b, c, d, _stream()))
+    return dw1, dw2
+
+
 def gelu_tanh(pre, out=None):
     """out = gelu_tanh(pre) for a [B, S, D] view — the activation EPI_GELU produced, re-created from the saved pre-activation."""
     _chk(pre, "pre")

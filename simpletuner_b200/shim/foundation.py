@@ -124,6 +124,12 @@ class B200FoundationMixin:
             raise NotImplementedError(f"libstb200 computes in bf16; weight_dtype={dtype}")
         step_cls = spec.step()
         step_cls.validate_config(self.config)                      # raises NotImplementedError on unsupported options
+        if str(getattr(self.config, "lora_type", "standard") or "standard").lower() == "lycoris":
+            # trainer.py:3391 calls the third-party `lycoris.create_lycoris` on the trained component; that wrapper only knows
+            # torch.nn modules.  Only with `install_lycoris()` (which routes B200 denoisers to simpletuner_b200.lycoris) may
+            # the swap happen for a LyCORIS run — and only for the families whose block schedules carry LoKr.
+            if not _LYCORIS_ROUTED or self.B200_FAMILY != "flux":
+                raise NotImplementedError("LyCORIS run: call simpletuner_b200.shim.install_lycoris() first (Flux LoKr only)")
         den = spec.denoiser()(**kwargs)
         missing, unexpected = den.load_state_dict(ref.state_dict(), strict=False)
         missing = [k for k in missing if "lora_" not in k]
@@ -184,6 +190,38 @@ def make_b200_family(reference_cls: type, family: str) -> type:
     if family not in FAMILIES:
         raise KeyError(f"unknown family {family!r}; known: {sorted(FAMILIES)}")
     return type(reference_cls.__name__ + "B200", (B200FoundationMixin, reference_cls), {"B200_FAMILY": family})
+
+
+_LYCORIS_ROUTED = False
+
+
+def install_lycoris(lycoris_module=None):
+    """Route `lycoris.create_lycoris` / `LycorisNetwork.apply_preset` (trainer.py:202, 3391-3497) to simpletuner_b200.lycoris
+    when the trained component is a libstb200 denoiser; every other module still reaches the third-party implementation.
+    `lycoris_module`: the imported `lycoris` package (default: import it)."""
+    global _LYCORIS_ROUTED
+    from .. import lycoris as b200_lycoris
+
+    if lycoris_module is None:
+        import importlib
+        lycoris_module = importlib.import_module("lycoris")
+    orig_create = lycoris_module.create_lycoris
+    orig_net = lycoris_module.LycorisNetwork
+    orig_preset = orig_net.apply_preset
+
+    def create_lycoris(module, *a, **k):
+        if type(module).__module__.startswith("simpletuner_b200."):
+            return b200_lycoris.create_lycoris(module, *a, **k)
+        return orig_create(module, *a, **k)
+
+    def apply_preset(preset):
+        b200_lycoris.LycorisNetwork.apply_preset(preset)      # both sides see the preset; the one that builds the network uses it
+        return orig_preset(preset)
+
+    lycoris_module.create_lycoris = create_lycoris
+    orig_net.apply_preset = staticmethod(apply_preset)
+    _LYCORIS_ROUTED = True
+    return create_lycoris
 
 
 def install(families: Optional[Sequence[str]] = None) -> Dict[str, type]:

@@ -590,3 +590,79 @@ CHECKS.update({
     "colsum2": lambda: check_colsum2(),
     "colsum2_small": lambda: check_colsum2(B=1, S=7, D=64),
 })
+
+
+# --------------------------------------------------------------------------------------------- LyCORIS LoKr + stand-alone GELU
+def check_lokr_rebuild(a=8, b=48, c=4, d=40, scale=0.5, fused=True):
+    """out = bf16(W + kron(w1, w2) * scale) and its transpose, written into slices of larger (fused q|k|v style) buffers."""
+    N, K = a * b, c * d
+    W, w1, w2 = _rand(N, K, seed=61) * 0.05, _rand(a, c, seed=62), _rand(b, d, seed=63) * 0.05
+    ref = (W.float() + torch.kron(w1.float(), w2.float()) * scale).bfloat16()
+    if fused:
+        big, big_t = torch.zeros(3 * N, K, device="cuda", dtype=torch.bfloat16), torch.zeros(K, 3 * N, device="cuda", dtype=torch.bfloat16)
+        out, out_t = big[N:2 * N], big_t[:, N:2 * N]
+    else:
+        out, out_t = torch.empty(N, K, device="cuda", dtype=torch.bfloat16), None
+    ops.lokr_rebuild(W, w1, w2, scale, out, out_t)
+    torch.cuda.synchronize()
+    # fp32 association differs (scale * w1 first), so a rare bf16 rounding tie may land on the neighbouring value
+    close = lambda x, y: float((x != y).float().mean()) < 2e-3 and bool(torch.allclose(x.float(), y.float(), rtol=2 ** -7, atol=1e-6))
+    ok = close(out, ref)
+    if fused:
+        ok = ok and bool(torch.equal(out_t, out.t())) and float(big[:N].abs().sum() + big[2 * N:].abs().sum() + big_t[:, :N].abs().sum()) == 0.0
+    return {"name": f"lokr_rebuild_{a}x{b}_{c}x{d}", "ok": ok, "max_err": float((out.float() - ref.float()).abs().max())}
+
+
+def check_lokr_factor_grads(a=8, b=48, c=4, d=40, scale=0.5, strided=True):
+    N, K = a * b, c * d
+    w1, w2 = _rand(a, c, seed=64), _rand(b, d, seed=65)
+    g_full = _rand(N + 8, K + 16, seed=66)
+    dW = g_full[4:4 + N, 8:8 + K] if strided else g_full[:N, :K].contiguous()
+    g4 = dW.float().view(a, b, c, d) if not strided else dW.float().reshape(a, b, c, d)
+    r1 = torch.einsum("ajcl,jl->ac", g4, w2.float()) * scale
+    r2 = torch.einsum("ajcl,ac->jl", g4, w1.float()) * scale
+    d1, d2 = ops.lokr_factor_grads(dW, w1, w2, scale)
+    torch.cuda.synchronize()
+    x1 = _report("lokr_dw1", d1, r1, atol=float(r1.abs().max()) * 1e-4, rtol=1e-4)
+    x2 = _report("lokr_dw2", d2, r2, atol=float(r2.abs().max()) * 1e-4, rtol=1e-4)
+    return {"name": f"lokr_factor_grads_{a}x{b}_{c}x{d}", "ok": x1["ok"] and x2["ok"], "max_err": max(x1["max_err"], x2["max_err"])}
+
+
+def check_gelu_tanh(B=2, S=77, D=640):
+    import torch.nn.functional as F
+    pf, gf = _rand(B, S + 2, D + 8, seed=71), _rand(B, S, D, seed=72)
+    pre = pf[:, 1:S + 1, :D]
+    act = ops.gelu_tanh(pre)
+    ref = F.gelu(pre.float(), approximate="tanh")
+    r1 = _report("gelu", act, ref, atol=2e-2, rtol=1.6e-2)
+    x = pre.float().requires_grad_(True)
+    (F.gelu(x, approximate="tanh") * gf.float()).sum().backward()
+    out = ops.mul_dgelu_tanh(gf, pre)
+    r2 = _report("dgelu", out, x.grad, atol=3e-2, rtol=1.6e-2)
+    inplace = gf.clone()
+    ops.mul_dgelu_tanh(inplace, pre, out=inplace)
+    torch.cuda.synchronize()
+    return {"name": f"gelu_tanh_B{B}_S{S}_D{D}", "ok": r1["ok"] and r2["ok"] and bool(torch.equal(inplace, out)), "max_err": max(r1["max_err"], r2["max_err"])}
+
+
+def check_gelu_matches_gemm_epilogue(B=1, S=256, N=512, K=128):
+    """ops.gelu_tanh(pre) must be BIT-identical to the activation EPI_GELU wrote next to `pre` (the LoRA-on-fc2 weight gradient
+    re-creates the activation from the saved pre-activation)."""
+    x, w, bias = _rand(B, S, K, seed=73), _rand(N, K, seed=74) * 0.2, _rand(N, seed=75)
+    pre = torch.empty(B, S, N, device="cuda", dtype=torch.bfloat16)
+    act = ops.gemm([x], [w], bias, epi=E.EPI_GELU, aux=pre)
+    again = ops.gelu_tanh(pre)
+    torch.cuda.synchronize()
+    return {"name": "gelu_matches_gemm_epilogue", "ok": bool(torch.equal(act, again)), "max_err": float((act.float() - again.float()).abs().max())}
+
+
+CHECKS.update({
+    "lokr_rebuild_fused_slices": lambda: check_lokr_rebuild(),
+    "lokr_rebuild_plain_ragged": lambda: check_lokr_rebuild(a=3, b=37, c=5, d=13, scale=1.0, fused=False),
+    "lokr_rebuild_flux_attn": lambda: check_lokr_rebuild(a=8, b=384, c=8, d=384, scale=1.0),
+    "lokr_factor_grads": lambda: check_lokr_factor_grads(),
+    "lokr_factor_grads_flux_ff": lambda: check_lokr_factor_grads(a=4, b=3072, c=4, d=768, scale=1.0, strided=False),
+    "lokr_factor_grads_tiny": lambda: check_lokr_factor_grads(a=2, b=3, c=2, d=8, strided=False),
+    "gelu_tanh": lambda: check_gelu_tanh(),
+    "gelu_matches_gemm_epilogue": lambda: check_gelu_matches_gemm_epilogue(),
+})

@@ -78,7 +78,6 @@ def test_unsupported_options_fall_back_to_the_reference_class(over, needle):
     fam = make_b200_family(RefFlux, "flux")(_cfg(**over), "cpu")
     fam.load_model()
     assert fam._b200 is None and needle in fam._b200_fallback_reason
-    assert not getattr(fam.model, "_is_b200_swapped", False)
     # every step method now runs the REFERENCE implementation
     fam.prepare_batch({"x": 1}, {})
     fam.model_predict({"x": 1})
@@ -174,3 +173,41 @@ def test_x_prediction_fixup_replaces_the_prediction_and_loss_repacks():
     assert torch.equal(packed, Flux._pack(out["model_prediction"]))
     untouched = W().model_predict(pb)
     assert f._packed_for_loss(untouched) is untouched["_packed_prediction"]
+
+
+def test_install_lycoris_routes_b200_denoisers_and_leaves_other_modules_alone():
+    """trainer.py:3391-3497 calls `lycoris.create_lycoris(component, multiplier, linear_dim, linear_alpha, **cfg)`; with the
+    route installed a libstb200 denoiser gets simpletuner_b200.lycoris, anything else the third-party implementation."""
+    import types
+
+    from simpletuner_b200 import lycoris as LY
+    from simpletuner_b200.shim import foundation as F
+
+    calls = []
+
+    class _Net:
+        @staticmethod
+        def apply_preset(p):
+            calls.append(("preset", p))
+
+    fake = types.SimpleNamespace(create_lycoris=lambda m, *a, **k: calls.append(("third-party", type(m).__name__)) or "tp",
+                                 LycorisNetwork=_Net)
+    old = F._LYCORIS_ROUTED
+    try:
+        F.install_lycoris(fake)
+        assert F._LYCORIS_ROUTED
+        fake.LycorisNetwork.apply_preset({"target_module": ["Attention"], "module_algo_map": {"Attention": {"factor": 4}}})
+        assert calls[-1][0] == "preset" and LY.LycorisNetwork._preset["target_module"] == ["Attention"]
+        assert fake.create_lycoris(torch.nn.Linear(4, 4), 1.0, 8, 1, algo="lokr") == "tp" and calls[-1] == ("third-party", "Linear")
+        net = fake.create_lycoris(_ref_flux(), 1.0, 10000, 1, algo="lokr", factor=4)
+        assert isinstance(net, LY.LycorisNetwork) and len(net.loras) == 11 and net.loras[0].shape == ((4, 64), (4, 64))
+        # a LyCORIS run swaps to the B200 classes only when routed, and only LoKr
+        fam = make_b200_family(RefFlux, "flux")(_cfg(lora_type="lycoris", lycoris_config={"algo": "lokr", "linear_dim": 10000}), "cpu")
+        fam.load_model()
+        assert fam._b200 is not None, fam._b200_fallback_reason
+        fam = make_b200_family(RefFlux, "flux")(_cfg(lora_type="lycoris", lycoris_config={"algo": "loha"}), "cpu")
+        fam.load_model()
+        assert fam._b200 is None and "lokr" in fam._b200_fallback_reason
+    finally:
+        F._LYCORIS_ROUTED = old
+        LY.LycorisNetwork._preset = {"target_module": ["Attention", "FeedForward"], "module_algo_map": {}}
