@@ -56,7 +56,7 @@ def test_flux_lora_loss_curve_matches_oracle_training():
         torch.manual_seed(1000 + k); torch.cuda.manual_seed(1000 + k)
         # --- CUDA step (the optimizer consumes the replayed integers)
         orig = opt.step
-        opt.step = lambda zero_grad=False, _r=rnd.cuda().contiguous(): orig(zero_grad=zero_grad, _rnd=_r)
+        opt.step = lambda zero_grad=False, _r=rnd.cuda().contiguous(), **kw: orig(zero_grad=zero_grad, _rnd=_r, **kw)
         captured = {}
         prep0 = w.prepare_batch
 
