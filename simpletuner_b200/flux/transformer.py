@@ -236,19 +236,37 @@ class FluxTransformerBlock(nn.Module):
         self.ff_context = _FeedForward(dim, dtype)
         self._plans = None
 
+    def _plan_linears(self):
+        a = self.attn
+        return {"img_attn": (a.to_q, a.to_k, a.to_v, a.to_out[0]), "txt_attn": (a.add_q_proj, a.add_k_proj, a.add_v_proj, a.to_add_out),
+                "img_mlp": (self.ff.net[0].proj, self.ff.net[2]), "txt_mlp": (self.ff_context.net[0].proj, self.ff_context.net[2])}
+
     def plans(self):
         if self._plans is None:
-            a = self.attn
-            def mk(ff):
-                (w1, w1_t), (w2, w2_t) = _weight_pair(ff.net[0].proj), _weight_pair(ff.net[2])
-                return MlpPlan(w1, ff.net[0].proj.bias.detach(), w1_t, w2, ff.net[2].bias.detach(), w2_t)
-            self._plans = {
-                "img_attn": _attn_plan(a.to_q, a.to_k, a.to_v, a.to_out[0], a.norm_q, a.norm_k),
-                "txt_attn": _attn_plan(a.add_q_proj, a.add_k_proj, a.add_v_proj, a.to_add_out, a.norm_added_q, a.norm_added_k),
-                "img_mlp": mk(self.ff),
-                "txt_mlp": mk(self.ff_context),
-            }
-        return self._plans
+            self._plans = {}
+        pl = self._plans
+        a = self.attn
+
+        def mk(ff):
+            (w1, w1_t), (w2, w2_t) = _weight_pair(ff.net[0].proj), _weight_pair(ff.net[2])
+            return MlpPlan(w1, ff.net[0].proj.bias.detach(), w1_t, w2, ff.net[2].bias.detach(), w2_t)
+
+        if "img_attn" not in pl:
+            pl["img_attn"] = _attn_plan(a.to_q, a.to_k, a.to_v, a.to_out[0], a.norm_q, a.norm_k)
+        if "txt_attn" not in pl:
+            pl["txt_attn"] = _attn_plan(a.add_q_proj, a.add_k_proj, a.add_v_proj, a.to_add_out, a.norm_added_q, a.norm_added_k)
+        if "img_mlp" not in pl:
+            pl["img_mlp"] = mk(self.ff)
+        if "txt_mlp" not in pl:
+            pl["txt_mlp"] = mk(self.ff_context)
+        return pl
+
+    def drop_adapted_plans(self):
+        """LoKr: only the layouts that embed an adapted weight follow the optimizer; the rest stay as built."""
+        if self._plans:
+            for key, lins in self._plan_linears().items():
+                if any(l.lokr is not None for l in lins):
+                    self._plans.pop(key, None)
 
     def forward(self, h, silu_temb, cos, sin, S_txt, lora_scaling):
         D = self.dim
@@ -281,13 +299,20 @@ class FluxSingleTransformerBlock(nn.Module):
 
     def plans(self):
         if self._plans is None:
-            a = self.attn
-            self._plans = {
-                "attn": _attn_plan(a.to_q, a.to_k, a.to_v, None, a.norm_q, a.norm_k),
-                "mlp": MlpPlan(self.proj_mlp.weight.detach(), self.proj_mlp.bias.detach(), _t(self.proj_mlp.weight.detach()),
-                               self.proj_out.weight.detach(), self.proj_out.bias.detach(), _t(self.proj_out.weight.detach())),
-            }
-        return self._plans
+            self._plans = {}
+        pl = self._plans
+        a = self.attn
+        if "attn" not in pl:
+            pl["attn"] = _attn_plan(a.to_q, a.to_k, a.to_v, None, a.norm_q, a.norm_k)
+        if "mlp" not in pl:
+            pl["mlp"] = MlpPlan(self.proj_mlp.weight.detach(), self.proj_mlp.bias.detach(), _t(self.proj_mlp.weight.detach()),
+                                self.proj_out.weight.detach(), self.proj_out.bias.detach(), _t(self.proj_out.weight.detach()))
+        return pl
+
+    def drop_adapted_plans(self):
+        a = self.attn
+        if self._plans and any(l.lokr is not None for l in (a.to_q, a.to_k, a.to_v)):
+            self._plans.pop("attn", None)
 
     def forward(self, h, silu_temb, cos, sin, lora_scaling):
         mod = self.norm.linear(silu_temb)
@@ -501,7 +526,8 @@ class FluxTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
         """TrainStep hook: with a LyCORIS LoKr network attached the projection layouts embed W + kron(w1, w2) and must follow
         the factors the optimizer just updated."""
         if getattr(self, "_lycoris_network", None) is not None:
-            self.invalidate_plans()
+            for blk in list(self.transformer_blocks) + list(self.single_transformer_blocks):
+                blk.drop_adapted_plans()
 
     def lora_linears(self) -> Dict[str, Linear]:
         return {n: m for n, m in self.named_modules() if isinstance(m, Linear) and m.lora_A is not None}

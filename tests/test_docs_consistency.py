@@ -20,12 +20,12 @@ def test_cited_profile_files_exist():
     missing = []
     for doc in ("DESIGN.md", "README.md", "INTEGRATION.md", "profiles/r01/README.md", "profiles/r02/README.md"):
         text = (ROOT / doc).read_text()
-        for m in re.finditer(r"profiles/(r0[12])/([A-Za-z0-9_.\-]+\.(?:json|jsonl|csv|log|txt))", text):
+        for m in re.finditer(r"profiles/(r0[12])/([A-Za-z0-9_.\-]+\.(?:jsonl|json|csv|log|txt))", text):
             if not (ROOT / "profiles" / m.group(1) / m.group(2)).exists():
                 missing.append((doc, m.group(1), m.group(2)))
         if doc.startswith("profiles/"):      # a round's own README may cite its artefacts by bare file name
             rnd = doc.split("/")[1]
-            for m in re.finditer(r"`([A-Za-z0-9_.\-]+\.(?:json|jsonl|csv|log|txt))`", text):
+            for m in re.finditer(r"`([A-Za-z0-9_.\-]+\.(?:jsonl|json|csv|log|txt))`", text):
                 if not (ROOT / "profiles" / rnd / m.group(1)).exists():
                     missing.append((doc, rnd, m.group(1)))
     assert not missing, missing
