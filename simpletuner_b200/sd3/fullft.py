@@ -37,14 +37,6 @@ def _ln(x, zero):
     return ops.ln_modulate_fwd(x, zero, zero, EPS)
 
 
-def _rms_weight_grads(d_post: torch.Tensor, x_pre: torch.Tensor, eps: float = EPS) -> torch.Tensor:
-    """d/dw of y = x * rsqrt(mean(x^2) + eps) * w for one stream: d_post, x_pre [B, S, H, hd] -> [hd] (fp32).
-    (diffusers RMSNorm: fp32 statistics; SD3 has no RoPE, so d_post is already the gradient w.r.t. y.)"""
-    xf = x_pre.float()
-    xhat = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
-    return (d_post.float() * xhat).sum(dim=(0, 1, 2))
-
-
 class JointBlockFullFn(torch.autograd.Function):
     """h_out = JointTransformerBlock(h) with gradients for every parameter.
 

@@ -22,5 +22,47 @@ elif which == "attn":
     for _ in range(3):
         o, lse = ops.attn_fwd(q, k, v)
         ops.attn_bwd(q, k, v, o, do, lse)
+elif which == "wgrad_full":          # Flux feed-forward weight gradient (LoKr / full fine-tune): [12288, 3072] from 2 x 4608 tokens
+    dy = torch.randn(2, 4608, 12288, device="cuda").bfloat16()
+    x = torch.randn(2, 4608, 3072, device="cuda").bfloat16()
+    for _ in range(3):
+        ops.wgrad_full(dy, x)
+elif which == "conv":                # VAE encoder level 0: 3x3, 128 -> 128 channels at 1024^2 (one image)
+    x = torch.randn(1, 1024, 1024, 128, device="cuda").bfloat16()
+    w9 = (torch.randn(128, 9 * 128, device="cuda") * 0.02).bfloat16()
+    b = torch.zeros(128, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.conv3x3_nhwc(x, w9, b)
+elif which == "optim":               # one launch: value clip + AdamW-bf16 + EMA over 532 LoRA tensors (26.1 M parameters)
+    from simpletuner_b200.training.ema import EMAModel
+    from simpletuner_b200.training.optim import AdamWBF16
+    ps = [torch.nn.Parameter(torch.randn(16, 3072, device="cuda").bfloat16()) for _ in range(266)] + \
+         [torch.nn.Parameter(torch.randn(3072, 16, device="cuda").bfloat16()) for _ in range(266)]
+    opt, ema = AdamWBF16(ps, lr=1e-4, seed=0), EMAModel(ps)
+    for k in range(4):
+        for p in ps:
+            p.grad = torch.randn_like(p)
+        opt.step(grad_clamp=2.0, ema=ema, ema_global_step=k + 1)
+elif which == "optim_big":           # the same kernel on full-fine-tune sized tensors (2.4 G parameters is too much here: 0.6 G)
+    from simpletuner_b200.training.optim import AdamWBF16
+    ps = [torch.nn.Parameter(torch.randn(3072, 12288, device="cuda").bfloat16()) for _ in range(16)]
+    opt = AdamWBF16(ps, lr=1e-4, seed=0)
+    for k in range(3):
+        for p in ps:
+            p.grad = torch.randn_like(p)
+        opt.step(grad_clamp=2.0)
+elif which == "lokr":                # LoKr rebuild + factor gradients of one Flux feed-forward projection [12288, 3072], factor 4
+    W = (torch.randn(12288, 3072, device="cuda") * 0.02).bfloat16()
+    w1 = torch.randn(4, 4, device="cuda").bfloat16()
+    w2 = (torch.randn(3072, 768, device="cuda") * 0.02).bfloat16()
+    out, out_t = torch.empty_like(W), torch.empty(3072, 12288, device="cuda", dtype=torch.bfloat16)
+    dW = torch.randn(12288, 3072, device="cuda").bfloat16()
+    for _ in range(3):
+        ops.lokr_rebuild(W, w1, w2, 1.0, out, out_t)
+        ops.lokr_factor_grads(dW, w1, w2, 1.0)
+elif which == "gelu":
+    pre = torch.randn(4, 4608, 12288, device="cuda").bfloat16()
+    for _ in range(3):
+        ops.gelu_tanh(pre)
 torch.cuda.synchronize()
 print("done", which)
