@@ -761,6 +761,15 @@ def run_b200(args):
 
     for i in range(args.warmup):
         dev_step(i)
+    if os.environ.get("STB_NCU_RANGE"):
+        # `ncu --profile-from-start off ...`: exactly ONE device-resident step inside the profiler range (launch list for
+        # profiles/); numbers printed under a profiler are never bench values, so nothing is printed
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        dev_step(args.warmup)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

@@ -22,3 +22,7 @@ cap gelu "gelu_tanh_kernel" gelu 1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_vae.csv python bench.py --config vae_encode --steps 1 --warmup 3 > gpurun_out/r02_launches_vae.log 2>&1
 python tools/summarize_launches.py gpurun_out/r02_launches_vae.csv 12 > gpurun_out/r02_launches_vae_summary.txt 2>&1
 tail -14 gpurun_out/r02_launches_vae_summary.txt
+# launch list of exactly one device-resident Flux step (profiler range inside bench.py)
+STB_NCU_RANGE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_flux_step.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-eager-baseline > gpurun_out/r02_launches_flux_step.log 2>&1
+python tools/summarize_launches.py gpurun_out/r02_launches_flux_step.csv 40 > gpurun_out/r02_launches_flux_step_summary.txt 2>&1
+head -30 gpurun_out/r02_launches_flux_step_summary.txt
