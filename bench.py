@@ -386,6 +386,110 @@ def run_vae(args):
         dist.destroy_process_group()
 
 
+def run_text(args):
+    """`--config text_encode`: the embed path of `FluxPipeline.encode_prompt` — T5-XXL encoder (24 layers,
+    d_model 4096, 64 heads, d_ff 10240, 512 tokens) + CLIP-L text model (12 layers, 768, 77 tokens) — on token ids; a step
+    encodes B prompts.  e2e: pinned host token ids in, embeddings read back to the host (what the text-embed cache stores)."""
+    from simpletuner_b200 import ops
+    from simpletuner_b200.text import CLIPTextModel, T5EncoderModel, encode_token_ids
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    B = args.batch or 16
+    kw5 = dict(vocab_size=512, d_model=256, d_kv=64, d_ff=512, num_layers=2, num_heads=4) if args.tiny else {}
+    kwc = dict(vocab_size=512, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2) if args.tiny else {}
+    with torch.device(device):
+        t5, clip = T5EncoderModel(**kw5), CLIPTextModel(**kwc)
+    g = torch.Generator(device=device).manual_seed(0)
+    with torch.no_grad():
+        for m in (t5, clip):
+            for n, p in m.named_parameters():
+                if "layer_norm" in n and n.endswith("weight"):
+                    p.fill_(1.0)
+                elif n.endswith("bias"):
+                    p.zero_()
+                else:
+                    p.normal_(0.0, 0.02, generator=g)
+    c5, cc = t5.config, clip.config
+    S5, Sc = 512, 77
+    gh = torch.Generator().manual_seed(1 + rank)
+    host = [(torch.randint(3, cc.vocab_size - 1, (B, Sc), generator=gh).pin_memory(), torch.randint(0, c5.vocab_size, (B, S5), generator=gh).pin_memory())
+            for _ in range(2)]
+    for ci, _ in host:
+        ci[:, -1] = cc.vocab_size - 1
+    dev = [(a.to(device), b.to(device)) for a, b in host]
+    out_e = torch.empty(B, S5, c5.d_model, dtype=torch.bfloat16).pin_memory()
+    out_p = torch.empty(B, cc.hidden_size, dtype=torch.bfloat16).pin_memory()
+
+    def region(fn, n):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def dev_step(i):
+        return encode_token_ids(clip, t5, *dev[i % 2])
+
+    def e2e_step(i):
+        ci, ti = host[i % 2]
+        e, p_, _, _ = encode_token_ids(clip, t5, ci.to(device, non_blocking=True), ti.to(device, non_blocking=True))
+        out_e.copy_(e, non_blocking=True)
+        out_p.copy_(p_)
+
+    for i in range(args.warmup):
+        dev_step(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    ms = region(dev_step, args.steps)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_step(0)
+    ms_e2e = region(e2e_step, args.steps)
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+        inner5 = c5.num_heads * c5.d_kv
+        tf_prompt = (c5.num_layers * (2 * S5 * (4 * c5.d_model * inner5 + 3 * c5.d_model * c5.d_ff) + 4 * S5 * S5 * inner5)
+                     + cc.num_hidden_layers * (2 * Sc * (4 * cc.hidden_size ** 2 + 2 * cc.hidden_size * cc.intermediate_size) + 4 * Sc * Sc * cc.hidden_size)) * 1e-12
+        ach = tf_prompt * B / (ms / args.steps * 1e-3)
+        line = {"metric": "prompts/sec Flux text-embed path (T5-XXL encoder 512 tokens + CLIP-L pooled)", "value": B * world * args.steps / (ms * 1e-3),
+                "unit": "prompts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic (random-init T5 v1.1 XXL / CLIP-L architectures, random token ids)",
+                "config": {"workload": f"FluxPipeline.encode_prompt compute (flux/pipeline.py:1085, 1127): {B} prompts per step, T5 encoder "
+                                       f"{c5.num_layers} x d{c5.d_model} on {S5} tokens + CLIP text {cc.num_hidden_layers} x d{cc.hidden_size} on {Sc} tokens",
+                           "config_name": "text_encode", "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                           "l2_policy": "inputs larger than L2 (9.5 GB of T5 weights streamed every step)", "tiny": bool(args.tiny)},
+                "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "prompts/s", "h2d_bytes_per_step": B * (S5 + Sc) * 8,
+                        "d2h_bytes_per_step": (out_e.numel() + out_p.numel()) * 2, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "tensor", "kernel": "whole encode (T5 projections / feed-forward GEMMs dominate)", "achieved": round(ach, 1),
+                             "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
+                             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})", "traffic": None},
+                "model_tflops": {"algorithmic_tf_per_prompt": round(tf_prompt, 3), "achieved_tflops_per_gpu": round(ach, 1)},
+                "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def batch_bytes(b):
     return int(sum(v.numel() * v.element_size() for v in b.values()))
 
@@ -920,7 +1024,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 4 for flux_lora, 8 for sd3_fullft)")
-    ap.add_argument("--config", default="flux_lora", choices=["flux_lora", "sd3_fullft", "pixart_lora", "vae_encode", "flux_lokr"],
+    ap.add_argument("--config", default="flux_lora", choices=["flux_lora", "sd3_fullft", "pixart_lora", "vae_encode", "flux_lokr", "text_encode"],
                     help="flux_lora = BASELINE configs[1] (the headline metric); sd3_fullft = configs[2] (SD3.5-medium full fine-tune); "
                          "pixart_lora = configs[4] (PixArt-Sigma LoRA r32, mixed buckets, grad-accum 4); vae_encode = the VAE cache path")
     ap.add_argument("--tiny", action="store_true", help="plumbing check on a toy config (not a benchmark value)")
@@ -946,6 +1050,8 @@ def main():
         run_reference(args)
     elif args.config == "vae_encode":
         run_vae(args)
+    elif args.config == "text_encode":
+        run_text(args)
     else:
         run_b200(args)
 

@@ -45,7 +45,10 @@ enum stb_gemm_epilogue {
   STB_EPI_GELU = 1,      /* D = gelu_tanh(acc + bias); aux (optional, written) = acc + bias    */
   STB_EPI_GATE_RES = 2,  /* D = res + gate[b, n] * (acc + bias); nan_to_num optional           */
   STB_EPI_MUL_DGELU = 3, /* D = acc * gelu_tanh'(aux[b, s, n])      (aux read)                 */
-  STB_EPI_ADD_RES = 4    /* D = acc + bias + res                                               */
+  STB_EPI_ADD_RES = 4,   /* D = acc + bias + res                                               */
+  STB_EPI_MUL = 5,       /* D = bf16(acc + bias) * aux[b, s, n]  (aux read) — T5 gated-GELU feed-forward, transformers
+                            T5DenseGatedActDense (called through flux/pipeline.py:1085)             */
+  STB_EPI_QUICK_GELU = 6 /* D = y * sigmoid(1.702 y), y = bf16(acc + bias) — CLIP text MLP (flux/pipeline.py:1127) */
 };
 
 typedef struct {
@@ -88,6 +91,12 @@ typedef struct {
   void* o;
   long long o_b, o_s, o_h;
   float* lse;
+  /* optional additive logit bias shared by the batch (forward / inference only; text encoders: T5 relative position bias
+   * T5Attention.compute_bias, CLIP causal mask — transformers classes called at flux/pipeline.py:1085, 1127):
+   * logit = scale * q.k + bias[h * bias_h + sq * bias_q + sk], bf16, -inf = masked; NULL = none.  Every query row must
+   * keep at least one finite logit among its first 128 keys. */
+  const void* bias;
+  long long bias_h, bias_q;
 } stb_attn_fwd_args;
 int stb_attn_fwd(const stb_attn_fwd_args* args, void* stream);
 
@@ -227,6 +236,12 @@ int stb_lokr_rebuild(const void* W, long long w_row_stride, const void* w1, cons
                      long long out_row_stride, void* out_t, long long out_t_row_stride, int a, int b, int c, int d, void* stream);
 int stb_lokr_factor_grads(const void* dW, long long dw_row_stride, const void* w1, const void* w2, float scale, float* dw1,
                           float* dw2, int a, int b, int c, int d, void* stream);
+
+/* T5LayerNorm (RMS norm without mean subtraction or bias; transformers T5LayerNorm.forward, the text encoder the reference
+ * runs at flux/pipeline.py:1085):  out = w * bf16(x * rsqrt(mean_d(x^2) + eps)), statistics in fp32.
+ * x / out: [B, S, D] views (element strides, D contiguous, D % 8 == 0); w: bf16 [D]. */
+int stb_rmsnorm_fwd(const void* x, long long x_b, long long x_s, const void* w, void* out, long long o_b, long long o_s,
+                    int B, int S, int D, float eps, void* stream);
 
 /* GELU(tanh) outside a GEMM epilogue, for the adapters on the MLP projections (flux_lora_target "all+ffs", "context+ffs",
  * "tiny" ...: reference flux/model.py:1272-1376; activation: flux/transformer.py:447, diffusers FeedForward

@@ -85,6 +85,7 @@ class AttnFwdArgs(C.Structure):
         ("o", C.c_void_p),
         ("o_b", C.c_longlong), ("o_s", C.c_longlong), ("o_h", C.c_longlong),
         ("lse", C.c_void_p),
+        ("bias", C.c_void_p), ("bias_h", C.c_longlong), ("bias_q", C.c_longlong),
     ]
 
 
@@ -138,6 +139,7 @@ SYMBOLS = {
     "stb_gate_mul": (_I, [_P, _LL, _LL, _P, _LL, _P, _LL, _LL, _I, _I, _I, _P]),
     "stb_lokr_rebuild": (_I, [_P, _LL, _P, _P, C.c_float, _P, _LL, _P, _LL, _I, _I, _I, _I, _P]),
     "stb_lokr_factor_grads": (_I, [_P, _LL, _P, _P, C.c_float, _P, _P, _I, _I, _I, _I, _P]),
+    "stb_rmsnorm_fwd": (_I, [_P, _LL, _LL, _P, _P, _LL, _LL, _I, _I, _I, C.c_float, _P]),
     "stb_gelu_tanh": (_I, [_P, _LL, _LL, _P, _LL, _LL, _P, _LL, _LL, _I, _I, _I, _I, _P]),
     "stb_dropout_expand": (_I, [_P, _LL, _LL, _P, _I, _I, _I, _I, _F, C.c_uint, C.c_uint, _P]),
     "stb_dropout_accum": (_I, [_P, _P, _LL, _LL, _I, _I, _I, _I, _F, C.c_uint, C.c_uint, _P]),

@@ -331,10 +331,10 @@ int stb_gemm_bf16(const stb_gemm_args* a, void* stream) {
   if ((a->epi == STB_EPI_GATE_RES || a->epi == STB_EPI_ADD_RES) &&
       (!a->res || !aligned16(a->res) || (a->res_row_stride & 7) || (a->res_batch_stride & 7)))
     return fail(STB_ERR_ARG, "res must be given, 16-byte aligned, strides multiple of 8");
-  if (a->epi == STB_EPI_MUL_DGELU && !a->aux) return fail(STB_ERR_ARG, "MUL_DGELU needs aux");
+  if ((a->epi == STB_EPI_MUL_DGELU || a->epi == STB_EPI_MUL) && !a->aux) return fail(STB_ERR_ARG, "MUL_DGELU / MUL need aux");
   if (a->aux && (!aligned16(a->aux) || (a->aux_row_stride & 7) || (a->aux_batch_stride & 7)))
     return fail(STB_ERR_ARG, "aux must be 16-byte aligned, strides multiple of 8");
-  if (a->epi < 0 || a->epi > 4) return fail(STB_ERR_ARG, "unknown epilogue %d", a->epi);
+  if (a->epi < 0 || a->epi > 6) return fail(STB_ERR_ARG, "unknown epilogue %d", a->epi);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int bn = a->tile_bn, mt = a->tile_mt;
   if (bn == 0) {
@@ -400,7 +400,32 @@ int stb_attn_fwd(const stb_attn_fwd_args* a, void* stream) {
   p.O = static_cast<__nv_bfloat16*>(a->o);
   p.o_b = a->o_b; p.o_s = a->o_s; p.o_h = a->o_h;
   p.lse = a->lse;
+  p.bias = static_cast<const __nv_bfloat16*>(a->bias);
+  p.bias_h = a->bias_h; p.bias_q = a->bias_q;
+  p.inv_scale = a->scale != 0.f ? 1.f / a->scale : 0.f;
   dim3 grid((a->Sq + 255) / 256, a->H, a->B);
+  if (a->bias) {   // text-encoder instantiation (additive bias / mask); never taken by the training step
+    if (a->scale == 0.f || a->bias_q < a->Sk) return fail(STB_ERR_ARG, "attn_fwd bias: scale must be non-zero and bias_q >= Sk");
+    if (a->HD == 128) {
+      auto kernel = stb::attn_fwd_kernel<128, true>;
+      static bool configured = false;
+      if (!configured) {
+        if (int r = set_smem(kernel, stb::AttnFwdCfg<128>::SMEM_BYTES)) return r;
+        configured = true;
+      }
+      kernel<<<grid, 384, stb::AttnFwdCfg<128>::SMEM_BYTES, st>>>(maps, p);
+    } else {
+      auto kernel = stb::attn_fwd_kernel<64, true>;
+      static bool configured = false;
+      if (!configured) {
+        if (int r = set_smem(kernel, stb::AttnFwdCfg<64>::SMEM_BYTES)) return r;
+        configured = true;
+      }
+      kernel<<<grid, 384, stb::AttnFwdCfg<64>::SMEM_BYTES, st>>>(maps, p);
+    }
+    STB_LAUNCH_CHECK("attn_fwd_bias");
+    return 0;
+  }
   // opt-in (STB_ATTN_FWD_PAIR=1) until it has been measured faster inside the full step
   static const bool use_pair = [] { const char* e = std::getenv("STB_ATTN_FWD_PAIR"); return e && e[0] == '1'; }();
   if (a->HD == 128 && use_pair) {
@@ -443,7 +468,7 @@ int stb_attn_fwd(const stb_attn_fwd_args* a, void* stream) {
     return 0;
   }
   if (a->HD == 128) {
-    auto kernel = stb::attn_fwd_kernel<128>;
+    auto kernel = stb::attn_fwd_kernel<128, false>;
     static bool configured = false;
     if (!configured) {
       if (int r = set_smem(kernel, stb::AttnFwdCfg<128>::SMEM_BYTES)) return r;
@@ -451,7 +476,7 @@ int stb_attn_fwd(const stb_attn_fwd_args* a, void* stream) {
     }
     kernel<<<grid, 384, stb::AttnFwdCfg<128>::SMEM_BYTES, st>>>(maps, p);
   } else {
-    auto kernel = stb::attn_fwd_kernel<64>;
+    auto kernel = stb::attn_fwd_kernel<64, false>;
     static bool configured = false;
     if (!configured) {
       if (int r = set_smem(kernel, stb::AttnFwdCfg<64>::SMEM_BYTES)) return r;
@@ -750,6 +775,20 @@ int stb_lokr_factor_grads(const void* dW, long long dw_row_stride, const void* w
       static_cast<const __nv_bfloat16*>(dW), dw_row_stride, static_cast<const __nv_bfloat16*>(w1), static_cast<const __nv_bfloat16*>(w2),
       scale, dw1, dw2, a, b, c, d);
   STB_LAUNCH_CHECK("lokr_factor_grads");
+  return 0;
+}
+
+int stb_rmsnorm_fwd(const void* x, long long x_b, long long x_s, const void* w, void* out, long long o_b, long long o_s,
+                    int B, int S, int D, float eps, void* stream) {
+  if (int r = check_device()) return r;
+  if (!x || !w || !out || B < 1 || S < 1 || D < 8 || (D & 7)) return fail(STB_ERR_ARG, "rmsnorm_fwd: bad shape (D multiple of 8)");
+  if (!aligned16(x) || !aligned16(out) || !aligned16(w) || (x_b & 7) || (x_s & 7) || (o_b & 7) || (o_s & 7))
+    return fail(STB_ERR_ARG, "rmsnorm_fwd alignment");
+  const long long rows = (long long)B * S;
+  stb::rmsnorm_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_b, x_s, static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(out), o_b,
+      o_s, B, S, D, eps);
+  STB_LAUNCH_CHECK("rmsnorm_fwd");
   return 0;
 }
 

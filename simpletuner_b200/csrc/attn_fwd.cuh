@@ -27,6 +27,11 @@ struct AttnFwdParams {
   __nv_bfloat16* O;   // [B, Sq, H, HD] via strides
   long long o_b, o_s, o_h;
   float* lse;         // [B, H, Sq] natural-log LSE of the scaled scores
+  // BIAS instantiation only: additive logit bias (T5 relative position bias, CLIP causal mask), shared by the batch:
+  // logit = scale * q.k + bias[h * bias_h + sq * bias_q + sk]   (bf16; -inf masks; bias_h = 0 shares it between heads)
+  const __nv_bfloat16* bias;
+  long long bias_h, bias_q;
+  float inv_scale;
 };
 
 struct AttnFwdMaps {
@@ -42,7 +47,10 @@ struct AttnFwdCfg {
   static constexpr int THREADS = 384;
 };
 
-template <int HD>
+// BIAS = true (text encoders only): the bias tile is added to the raw scores (pre-divided by the softmax scale) in both
+// softmax passes.  Every query row needs at least one finite logit in its FIRST key tile (true for a causal mask and for
+// un-masked relative-position biases).  The BIAS = false instantiation is the training kernel, byte-identical to before.
+template <int HD, bool BIAS = false>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_kernel(const __grid_constant__ AttnFwdMaps maps, const AttnFwdParams p) {
   using Cfg = AttnFwdCfg<HD>;
@@ -215,6 +223,31 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdMaps maps, const AttnFwdParams p)
     const float sl2 = p.scale * 1.4426950408889634f;
     float m_used = -INFINITY;  // raw-score max currently baked into O and l
     float l = 0.f;
+    // BIAS: this thread's bias row (query index clamped for the ragged last Q tile; those rows are never written)
+    const __nv_bfloat16* brow = nullptr;
+    if constexpr (BIAS)
+      brow = p.bias + (long long)h * p.bias_h + (long long)min(q0 + t * 128 + r, p.Sq - 1) * p.bias_q;
+    auto add_bias = [&](uint32_t (&v)[64], int col0, int kv_left) {   // v[i] += bias[col0 + i] / scale for i < kv_left
+      if constexpr (BIAS) {
+        const __nv_bfloat16* bp = brow + col0;
+        if (kv_left >= 64 && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+#pragma unroll
+          for (int q8 = 0; q8 < 8; ++q8) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(bp) + q8);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[q8 * 8 + 2 * e] = __float_as_uint(fmaf(bf16_lo(w[e]), p.inv_scale, __uint_as_float(v[q8 * 8 + 2 * e])));
+              v[q8 * 8 + 2 * e + 1] = __float_as_uint(fmaf(bf16_hi(w[e]), p.inv_scale, __uint_as_float(v[q8 * 8 + 2 * e + 1])));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i < kv_left) v[i] = __float_as_uint(fmaf(__bfloat162float(bp[i]), p.inv_scale, __uint_as_float(v[i])));
+        }
+      }
+    };
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full(t), j & 1, 30);
@@ -228,6 +261,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdMaps maps, const AttnFwdParams p)
         uint32_t v[64];
         tmem_ld_32x32b_x64(s_t + c, v);
         tc_wait_ld();
+        add_bias(v, j * 128 + c, kv_valid - c);
         if (ragged) {
 #pragma unroll
           for (int i = 0; i < 64; ++i)
@@ -273,6 +307,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdMaps maps, const AttnFwdParams p)
         uint32_t v[64];
         tmem_ld_32x32b_x64(s_t + c, v);
         tc_wait_ld();
+        add_bias(v, j * 128 + c, kv_valid - c);
         if (ragged) {
 #pragma unroll
           for (int i = 0; i < 64; ++i)

@@ -683,6 +683,40 @@ gate_mul_kernel(const __nv_bfloat16* __restrict__ x, long long x_b, long long x_
 
 
 // ------------------------------------------------------------------------------------------------
+// T5LayerNorm (text-encoder path): out = w * bf16(x * rsqrt(mean(x^2) + eps)); one warp per row,
+// 16-byte accesses, the row is read twice (second read hits L1 / L2: a T5-XXL row is 8 KB).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_b, long long x_s, const __nv_bfloat16* __restrict__ w,
+                   __nv_bfloat16* __restrict__ out, long long o_b, long long o_s, int B, int S, int D, float eps) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (long long)B * S) return;
+  const int lane = threadIdx.x & 31;
+  const int s = int(row % S), b = int(row / S);
+  const __nv_bfloat16* xr = x + b * x_b + s * x_s;
+  __nv_bfloat16* orow = out + b * o_b + s * o_s;
+  float ss = 0.f;
+  for (int c = lane * 8; c < D; c += 256) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / D + eps);
+  for (int c = lane * 8; c < D; c += 256) {
+    float v[8], wv[8], o8[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c), v);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(w + c)), wv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o8[j] = wv[j] * bf16r(v[j] * rstd);
+    *reinterpret_cast<uint4*>(orow + c) = pack8(o8);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
 // GELU(tanh) outside a GEMM epilogue — only the LoRA-on-MLP paths need it (flux_lora_target = "all+ffs" etc.,
 // reference flux/model.py:1283-1338):  mode 0: y = gelu(pre)  — re-creates the bf16 activation the forward GEMM's
 // EPI_GELU epilogue produced from the saved pre-activation (bit-identical: that epilogue applies gelu to the

@@ -26,7 +26,9 @@ enum GemmEpi : int {
   EPI_GELU = 1,         // D = gelu_tanh(acc + bias); aux (optional) = acc + bias (pre-activation)
   EPI_GATE_RES = 2,     // D = res + gate[b, n] * (acc + bias); optional nan_to_num; aux (optional) = acc + bias
   EPI_MUL_DGELU = 3,    // D = acc * gelu_tanh'(aux)          (dgrad through the activation)
-  EPI_ADD_RES = 4,      // D = acc + bias + res                (gradient accumulation)
+  EPI_ADD_RES = 4,      // D = acc + bias + res                (gradient accumulation; residual add of the text encoders)
+  EPI_MUL = 5,          // D = (acc + bias) * aux              (T5 gated feed-forward: gelu(x wi_0) * (x wi_1))
+  EPI_QUICK_GELU = 6,   // D = y * sigmoid(1.702 y), y = bf16(acc + bias)   (CLIP text model activation)
 };
 
 struct GemmParams {
@@ -93,6 +95,8 @@ struct GemmPairCfg {
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
+
+__device__ __forceinline__ float gemm_bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 __device__ __forceinline__ void gemm_tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
   // grouped rasterisation: bands of 8 m-tiles sweep all n-tiles -> square-ish L2 footprint
@@ -445,6 +449,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                   if (n + j < p.N) f[j] *= gelu_tanh_grad(__bfloat162float(xrow[n + j]));
+              }
+            } else if (p.epi == EPI_MUL) {
+              if (full) {
+                const uint4* xp = reinterpret_cast<const uint4*>(xrow + n);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4 u = xp[q];
+                  f[q * 8 + 0] = gemm_bf16r(f[q * 8 + 0]) * bf16_lo(u.x); f[q * 8 + 1] = gemm_bf16r(f[q * 8 + 1]) * bf16_hi(u.x);
+                  f[q * 8 + 2] = gemm_bf16r(f[q * 8 + 2]) * bf16_lo(u.y); f[q * 8 + 3] = gemm_bf16r(f[q * 8 + 3]) * bf16_hi(u.y);
+                  f[q * 8 + 4] = gemm_bf16r(f[q * 8 + 4]) * bf16_lo(u.z); f[q * 8 + 5] = gemm_bf16r(f[q * 8 + 5]) * bf16_hi(u.z);
+                  f[q * 8 + 6] = gemm_bf16r(f[q * 8 + 6]) * bf16_lo(u.w); f[q * 8 + 7] = gemm_bf16r(f[q * 8 + 7]) * bf16_hi(u.w);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n + j < p.N) f[j] = gemm_bf16r(f[j]) * __bfloat162float(xrow[n + j]);
+              }
+            } else if (p.epi == EPI_QUICK_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float y = gemm_bf16r(f[j]);
+                f[j] = y / (1.f + __expf(-1.702f * y));
               }
             } else if (p.epi == EPI_ADD_RES) {
               if (full) {

@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from ._lib import QkPrep, AttnBwdArgs, AttnFwdArgs, GemmArgs, check
 
-EPI_STORE, EPI_GELU, EPI_GATE_RES, EPI_MUL_DGELU, EPI_ADD_RES = 0, 1, 2, 3, 4
+EPI_STORE, EPI_GELU, EPI_GATE_RES, EPI_MUL_DGELU, EPI_ADD_RES, EPI_MUL, EPI_QUICK_GELU = 0, 1, 2, 3, 4, 5, 6
 
 
 def _stream() -> int:
@@ -104,8 +104,9 @@ def gemm(
     return out.squeeze(0) if (squeeze and out.dim() == 3) else out
 
 
-def attn_fwd(q, k, v, scale: Optional[float] = None, out: Optional[torch.Tensor] = None):
-    """q/k/v: [B, S, H, HD] views (HD contiguous).  Returns (o [B,Sq,H,HD] bf16, lse [B,H,Sq] fp32)."""
+def attn_fwd(q, k, v, scale: Optional[float] = None, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None):
+    """q/k/v: [B, S, H, HD] views (HD contiguous).  Returns (o [B,Sq,H,HD] bf16, lse [B,H,Sq] fp32).
+    bias (forward only): bf16 [H or 1, Sq, Sk] additive logit bias / mask shared by the batch."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _chk(t, n)
     B, Sq, H, HD = q.shape
@@ -124,6 +125,10 @@ def attn_fwd(q, k, v, scale: Optional[float] = None, out: Optional[torch.Tensor]
     a.o = out.data_ptr()
     a.o_b, a.o_s, a.o_h = out.stride(0), out.stride(1), out.stride(2)
     a.lse = lse.data_ptr()
+    if bias is not None:
+        _chk(bias, "bias")
+        assert bias.dim() == 3 and bias.shape[0] in (1, H) and bias.shape[1] == Sq and bias.shape[2] == Sk
+        a.bias, a.bias_h, a.bias_q = bias.data_ptr(), (0 if bias.shape[0] == 1 else bias.stride(0)), bias.stride(1)
     check(_lib.lib().stb_attn_fwd(C.byref(a), _stream()))
     return out, lse
 
@@ -348,6 +353,17 @@ def lokr_factor_grads(dW, w1, w2, scale: float):
     check(_lib.lib().stb_lokr_factor_grads(dW.data_ptr(), dW.stride(0), w1.data_ptr(), w2.data_ptr(), float(scale),
                                            dw1.data_ptr(), dw2.data_ptr(), a, b, c, d, _stream()))
     return dw1, dw2
+
+
+def rmsnorm_fwd(x, w, eps: float, out=None):
+    """T5LayerNorm: out = w * bf16(x * rsqrt(mean(x^2) + eps)) for a [B, S, D] view."""
+    _chk(x, "x"); _chk(w, "w")
+    B, S, D = x.shape
+    if out is None:
+        out = torch.empty((B, S, D), device=x.device, dtype=torch.bfloat16)
+    check(_lib.lib().stb_rmsnorm_fwd(x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), out.data_ptr(), out.stride(0),
+                                     out.stride(1), B, S, D, float(eps), _stream()))
+    return out
 
 
 def gelu_tanh(pre, out=None):
