@@ -639,10 +639,13 @@ int stb_qk_rmsnorm_rope_bwd(const void* dq, const void* dk, long long d_b, long 
   const long long warps = (long long)B * S;  // one warp per token
   const unsigned grid = (unsigned)((warps + 7) / 8);
   auto cast = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
-  if (HD == 128)
-    stb::qk_rmsnorm_rope_bwd_kernel<128><<<grid, 256, 0, st>>>(cast(dq), cast(dk), d_b, d_s, cast(src), src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(dsrc), ds_b, ds_s, B, S, H, eps, dw);
-  else
-    stb::qk_rmsnorm_rope_bwd_kernel<64><<<grid, 256, 0, st>>>(cast(dq), cast(dk), d_b, d_s, cast(src), src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(dsrc), ds_b, ds_s, B, S, H, eps, dw);
+  if (HD == 128) {
+    if (dw) stb::qk_rmsnorm_rope_bwd_kernel<128, true><<<grid, 256, 0, st>>>(cast(dq), cast(dk), d_b, d_s, cast(src), src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(dsrc), ds_b, ds_s, B, S, H, eps, dw);
+    else stb::qk_rmsnorm_rope_bwd_kernel<128, false><<<grid, 256, 0, st>>>(cast(dq), cast(dk), d_b, d_s, cast(src), src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(dsrc), ds_b, ds_s, B, S, H, eps, dw);
+  } else {
+    if (dw) stb::qk_rmsnorm_rope_bwd_kernel<64, true><<<grid, 256, 0, st>>>(cast(dq), cast(dk), d_b, d_s, cast(src), src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(dsrc), ds_b, ds_s, B, S, H, eps, dw);
+    else stb::qk_rmsnorm_rope_bwd_kernel<64, false><<<grid, 256, 0, st>>>(cast(dq), cast(dk), d_b, d_s, cast(src), src_b, src_s, k_off, cast(wq), cast(wk), cast(wq_added), cast(wk_added), s_split, cos_t, sin_t, static_cast<__nv_bfloat16*>(dsrc), ds_b, ds_s, B, S, H, eps, dw);
+  }
   STB_LAUNCH_CHECK("qk_rmsnorm_rope_bwd");
   return 0;
 }

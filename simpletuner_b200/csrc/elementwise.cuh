@@ -299,7 +299,8 @@ qk_rmsnorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ src, long long src_
 // Backward: given dq/dk in post-RoPE space, produce gradient w.r.t. the projection outputs
 // (written into the q / k column ranges of the fused d_qkv buffer).  RMSNorm weights are frozen.
 //   dy = R^T d_out ;  g = dy * w ;  dx = rstd * (g - xhat * mean(g * xhat))
-template <int HD>
+// DW = false (LoRA / frozen norms): no weight-gradient registers, no shared-memory staging — the round-1 footprint.
+template <int HD, bool DW>
 __global__ void __launch_bounds__(256)
 qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bfloat16* __restrict__ dk,
                            long long d_b, long long d_s, const __nv_bfloat16* __restrict__ src,
@@ -313,14 +314,14 @@ qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bflo
   // shared-memory atomics per block and one global atomic per entry per block:  dw[i] += (R^T d_out)[i] * xhat[i]
   constexpr int EPL = HD / 32;
   constexpr int U = 4;
-  __shared__ float dw_s[4 * HD];
-  if (dw) {
+  __shared__ float dw_s[DW ? 4 * HD : 1];
+  if constexpr (DW) {
     for (int i = threadIdx.x; i < 4 * HD; i += blockDim.x) dw_s[i] = 0.f;
     __syncthreads();
   }
   const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const bool active = tok < (long long)B * S;
-  if (!active && !dw) return;
+  if (!active && !DW) return;
   const int lane = threadIdx.x & 31;
   if (active) {
   const int s = int(tok % S);
@@ -370,8 +371,10 @@ qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bflo
         const float dy1 = go[u][i + 1] * cs[i + 1] - go[u][i] * sn[i];
         g[u][i] = dy0 * (which ? wkv[i] : wqv[i]);
         g[u][i + 1] = dy1 * (which ? wkv[i + 1] : wqv[i + 1]);
-        go[u][i] = dy0;        // keep the pre-weight gradient for dw
-        go[u][i + 1] = dy1;
+        if constexpr (DW) {
+          go[u][i] = dy0;        // keep the pre-weight gradient for dw
+          go[u][i + 1] = dy1;
+        }
       }
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
@@ -398,13 +401,13 @@ qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bflo
 #pragma unroll
       for (int i = 0; i < EPL; ++i) o[i] = rstd * (g[u][i] - (x[u][i] * rstd) * m);
       st_row<EPL>(out_tok + (which ? k_off : 0) + hh * HD, o);
-      if (dw) {
+      if constexpr (DW) {
 #pragma unroll
         for (int i = 0; i < EPL; ++i) dwacc[which][i] += go[u][i] * (x[u][i] * rstd);
       }
     }
   }
-  if (dw) {
+  if constexpr (DW) {
     const int base = (txt ? 2 : 0) * HD;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
@@ -413,7 +416,7 @@ qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bflo
     }
   }
   }  // active
-  if (dw) {
+  if constexpr (DW) {
     __syncthreads();
     for (int i = threadIdx.x; i < 4 * HD; i += blockDim.x)
       if (dw_s[i] != 0.f) atomicAdd(dw + i, dw_s[i]);

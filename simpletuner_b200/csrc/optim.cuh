@@ -47,6 +47,7 @@ adamw_bf16_multi_kernel(const long long* __restrict__ ptrs, const long long* __r
   __nv_bfloat16* s = reinterpret_cast<__nv_bfloat16*>(ptrs[4 * T + t]);
   __nv_bfloat16* e = ema ? reinterpret_cast<__nv_bfloat16*>(ema[t]) : nullptr;
   const float dec = decay[t];
+  const uint32_t key0 = hash_u32(seed ^ (uint64_t(uint32_t(t)) << 40)), key1 = hash_u32((seed + 0x632BE59BD9B4E019ull) ^ (uint64_t(uint32_t(t)) << 17));
   const long long roff = rnd_off ? rnd_off[t] : 0;
   // one element of the update, shared by the vector and the scalar path
   auto clampg = [&](float gv) {
@@ -60,8 +61,10 @@ adamw_bf16_multi_kernel(const long long* __restrict__ ptrs, const long long* __r
       r0 = uint32_t(rnd[0 * rnd_plane + roff + i]), r1 = uint32_t(rnd[1 * rnd_plane + roff + i]);
       r2 = uint32_t(rnd[2 * rnd_plane + roff + i]), r3 = uint32_t(rnd[3 * rnd_plane + roff + i]);
     } else {
-      const uint64_t key = (seed ^ (uint64_t(uint32_t(t)) << 40)) + uint64_t(i) * 4ull;
-      const uint32_t h0 = hash_u32(key), h1 = hash_u32(key + 2);
+      // two murmur3 finalisers over a Weyl-sequenced element counter, keyed per (seed, step, tensor): 64 random bits for
+      // ~14 integer instructions (the splitmix64 pair this replaces made the kernel instruction-bound, 3.2 TB/s)
+      const uint32_t c = uint32_t(i) * 0x9E3779B1u + uint32_t(uint64_t(i) >> 32) * 0x7FEB352Du;
+      const uint32_t h0 = mix32(c ^ key0), h1 = mix32(c + key1);
       r0 = h0 & 0xFFFFu, r1 = h0 >> 16, r2 = h1 & 0xFFFFu, r3 = h1 >> 16;
     }
     // exp_avg.mul_(beta1); add_stochastic_(exp_avg, grad, alpha = 1 - beta1)  ->  grad + alpha * exp_avg

@@ -64,5 +64,51 @@ elif which == "gelu":
     pre = torch.randn(4, 4608, 12288, device="cuda").bfloat16()
     for _ in range(3):
         ops.gelu_tanh(pre)
+elif which == "time_tail":
+    # CUDA-event timings (not under a profiler) of the HBM-bound kernels at Flux shapes: ms and algorithmic GB/s
+    import json
+    B, S, H, HD, D = 4, 4608, 24, 128, 3072
+
+    def timeit(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    res = {}
+    qkv = torch.randn(B, S, 3 * D, device="cuda").bfloat16()
+    wq, wk = torch.ones(HD, device="cuda").bfloat16(), torch.ones(HD, device="cuda").bfloat16()
+    cos, sin = torch.rand(S, HD, device="cuda"), torch.rand(S, HD, device="cuda")
+    dq, dk = torch.randn(B, S, H, HD, device="cuda").bfloat16(), torch.randn(B, S, H, HD, device="cuda").bfloat16()
+    dqkv = torch.empty_like(qkv)
+    t = timeit(lambda: ops.qk_rmsnorm_rope_fwd(qkv, D, H, HD, wq, wk, None, None, 0, cos, sin, 1e-6))
+    res["qk_rmsnorm_rope_fwd"] = {"ms": t, "GBps": 4 * B * S * D * 2 / t / 1e6}
+    t = timeit(lambda: ops.qk_rmsnorm_rope_bwd(dq, dk, qkv, D, H, HD, wq, wk, None, None, 0, cos, sin, 1e-6, dsrc=dqkv))
+    res["qk_rmsnorm_rope_bwd"] = {"ms": t, "GBps": 6 * B * S * D * 2 / t / 1e6}
+    h = torch.randn(B, S, D, device="cuda").bfloat16()
+    sh, sc = torch.randn(B, D, device="cuda").bfloat16(), torch.randn(B, D, device="cuda").bfloat16()
+    t = timeit(lambda: ops.ln_modulate_fwd(h, sh, sc, 1e-6))
+    res["ln_modulate_fwd"] = {"ms": t, "GBps": 2 * B * S * D * 2 / t / 1e6}
+    dn = torch.randn(B, S, D, device="cuda").bfloat16()
+    out = torch.empty_like(h)
+    t = timeit(lambda: ops.ln_modulate_bwd(dn, h, sc, add=h, eps=1e-6, out=out))
+    res["ln_modulate_bwd"] = {"ms": t, "GBps": 4 * B * S * D * 2 / t / 1e6}
+    t = timeit(lambda: ops.gate_mul(h, sc))
+    res["gate_mul"] = {"ms": t, "GBps": 2 * B * S * D * 2 / t / 1e6}
+    from simpletuner_b200.training.optim import AdamWBF16
+    ps = [torch.nn.Parameter(torch.randn(3072, 12288, device="cuda").bfloat16()) for _ in range(16)]
+    opt = AdamWBF16(ps, lr=1e-4, seed=0)
+    for p in ps:
+        p.grad = torch.randn_like(p)
+    n_el = sum(p.numel() for p in ps)
+    t = timeit(lambda: opt.step(grad_clamp=2.0), n=5)
+    res["adamw_bf16_multi"] = {"ms": t, "GBps": n_el * 18 / t / 1e6}
+    print(json.dumps(res))
 torch.cuda.synchronize()
 print("done", which)
