@@ -21,6 +21,7 @@ def encode_token_ids(text_encoder, text_encoder_2, clip_input_ids: torch.Tensor,
     S = embeds.shape[1]
     embeds = embeds.repeat(1, num_images_per_prompt, 1).view(B * num_images_per_prompt, S, -1)
     if t5_padding == "zero" and t5_attention_mask is not None:
-        embeds = embeds * t5_attention_mask.to(device=embeds.device).unsqueeze(-1).expand(embeds.shape)
+        m = t5_attention_mask.to(device=embeds.device).repeat_interleave(num_images_per_prompt, dim=0)
+        embeds = embeds * m.unsqueeze(-1).expand(embeds.shape)
     text_ids = torch.zeros(S, 3, device=embeds.device, dtype=embeds.dtype)
     return embeds, pooled, text_ids, t5_attention_mask

@@ -98,6 +98,7 @@ def test_t5_wide_config_and_encode_token_ids_against_the_oracle():
     cos = torch.nn.functional.cosine_similarity
     e = emb.float().cpu()
     assert torch.equal(e[0], e[1]) and float(e[0, 100:].abs().sum()) == 0          # repeat per image; zeroed padding
+    ref = torch.stack([ref[0], ref[1]])
     assert float(cos(e[0::2].flatten(), ref.flatten(), dim=0)) >= 0.9995, float(cos(e[0::2].flatten(), ref.flatten(), dim=0))
     assert float(cos(pooled.float().cpu()[0::2].flatten(), ref_pooled.flatten(), dim=0)) >= 0.9995
 
