@@ -288,6 +288,13 @@ int stb_colsum2(const void* dy, long long dy_b, long long dy_s, const void* z, l
  * ------------------------------------------------------------------------------------------- */
 int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, long long r_b, long long r_s,
                   float* out, int B, int S, int R, int N, float alpha, void* stream);
+/* Run-to-run reproducible variant: every (batch, row-split) CTA writes its partial [R, N] into `workspace` (fp32,
+ * stb_skinny_tn_workspace(B, S, R, N) elements) with plain stores and a second kernel adds the slabs to `out` in index order —
+ * no floating-point atomics.  workspace == NULL is stb_skinny_tn. */
+long long stb_skinny_tn_workspace(int B, int S, int R, int N);
+int stb_skinny_tn_ws(const void* L, long long l_b, long long l_s, const void* Rm, long long r_b, long long r_s,
+                     float* out, int B, int S, int R, int N, float alpha, float* workspace, long long workspace_elems,
+                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * VAE latent encode (diffusers AutoencoderKL.encode as called at reference common.py:2766-2772 from

@@ -935,8 +935,28 @@ int stb_colsum2(const void* dy, long long dy_b, long long dy_s, const void* z, l
   return 0;
 }
 
+static void skinny_split(int B, int S, int N, int& rows, int& spb) {
+  const int n_tiles = (N + 127) / 128;
+  spb = std::max(1, (2 * num_sms()) / std::max(1, n_tiles * B));     // ~2 CTAs' worth of work per SM
+  rows = ((S + spb - 1) / spb + 63) / 64 * 64;
+  spb = (S + rows - 1) / rows;
+}
+
+long long stb_skinny_tn_workspace(int B, int S, int R, int N) {
+  if (B < 1 || S < 1 || R < 1 || N < 1 || check_device()) return 0;
+  int rows, spb;
+  skinny_split(B, S, N, rows, spb);
+  return (long long)spb * B * R * N;
+}
+
 int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, long long r_b, long long r_s,
                   float* out, int B, int S, int R, int N, float alpha, void* stream) {
+  return stb_skinny_tn_ws(L, l_b, l_s, Rm, r_b, r_s, out, B, S, R, N, alpha, nullptr, 0, stream);
+}
+
+int stb_skinny_tn_ws(const void* L, long long l_b, long long l_s, const void* Rm, long long r_b, long long r_s,
+                     float* out, int B, int S, int R, int N, float alpha, float* workspace, long long workspace_elems,
+                     void* stream) {
   if (int r = check_device()) return r;
   if (N & 1) return fail(STB_ERR_ARG, "N must be even");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -960,9 +980,13 @@ int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, l
     p.alpha = alpha;
     p.out = out;
     const int n_tiles = (N + 127) / 128;
-    int spb = std::max(1, (2 * num_sms()) / std::max(1, n_tiles * B));     // ~2 CTAs' worth of work per SM
-    int rows = ((S + spb - 1) / spb + 63) / 64 * 64;
-    spb = (S + rows - 1) / rows;
+    int spb, rows;
+    skinny_split(B, S, N, rows, spb);
+    p.partial = nullptr;
+    if (workspace) {
+      if (workspace_elems < (long long)spb * B * R * N) return fail(STB_ERR_ARG, "skinny_tn workspace too small (stb_skinny_tn_workspace)");
+      p.partial = workspace;
+    }
     p.rows_per_split = rows;
     p.splits_per_batch = spb;
     dim3 grid(n_tiles, spb * B);
@@ -990,8 +1014,15 @@ int stb_skinny_tn(const void* L, long long l_b, long long l_s, const void* Rm, l
     }
 #undef STB_WG
     STB_LAUNCH_CHECK("wgrad_tn");
+    if (workspace) {
+      const long long n = (long long)R * N;
+      stb::wgrad_reduce_slabs_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8), 256, 0, st>>>(
+          workspace, out, spb * B, n, alpha);
+      STB_LAUNCH_CHECK("wgrad_reduce_slabs");
+    }
     return 0;
   }
+  if (workspace) return fail(STB_ERR_UNSUPPORTED, "deterministic skinny_tn needs the tensor-core path (R % 8 == 0, R <= 128, N % 8 == 0, 16-byte aligned operands)");
   const long long M = (long long)B * S;
   const int col_blocks = (N / 2 + 255) / 256;
   // enough row chunks to fill the machine ~4x

@@ -20,6 +20,8 @@ struct WgradParams {
   int splits_per_batch;
   float alpha;
   float* out;           // [R, N] fp32
+  float* partial;       // deterministic mode: [gridDim.y][R][N] slabs written with plain stores (summed in slab order by
+                        // wgrad_reduce_slabs_kernel); nullptr = fp32 atomics straight into `out`
 };
 
 struct WgradMaps {
@@ -157,7 +159,10 @@ wgrad_tn_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
       if (n < p.N) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (c + j < p.R) atomicAdd(p.out + (long long)(c + j) * p.N + n, p.alpha * __uint_as_float(v[j]));
+          if (c + j < p.R) {
+            if (p.partial) p.partial[((long long)blockIdx.y * p.R + (c + j)) * p.N + n] = __uint_as_float(v[j]);
+            else atomicAdd(p.out + (long long)(c + j) * p.N + n, p.alpha * __uint_as_float(v[j]));
+          }
       }
     }
   }
@@ -166,6 +171,16 @@ wgrad_tn_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// out[i] += alpha * sum_y partial[y][i], slabs in index order (run-to-run reproducible LoRA gradients)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_slabs_kernel(const float* __restrict__ partial, float* __restrict__ out, int slabs, long long n, float alpha) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int y = 0; y < slabs; ++y) acc += partial[(long long)y * n + i];
+    out[i] += alpha * acc;
   }
 }
 

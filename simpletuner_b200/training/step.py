@@ -144,6 +144,15 @@ class GraphedTrainStep:
             raise NotImplementedError("GraphedTrainStep supports gradient_accumulation_steps == 1")
         if hasattr(step.model.model, "no_sync"):
             raise NotImplementedError("GraphedTrainStep: wrap with FlatGradSync instead of torch DDP")
+        den = getattr(step.model, "model", None)
+        if float(getattr(den, "_lora_dropout_p", 0.0) or 0.0) > 0.0:
+            # the dropout seed is drawn on the host once per forward: a captured graph would replay ONE mask forever
+            raise NotImplementedError("GraphedTrainStep: lora_dropout > 0 draws a per-step host seed; run the eager TrainStep")
+        if getattr(den, "_lycoris_network", None) is not None:
+            raise NotImplementedError("GraphedTrainStep: LoKr rebuilds the projection layouts between steps; run the eager TrainStep")
+        from .. import ops
+        if ops.DETERMINISTIC:
+            raise NotImplementedError("GraphedTrainStep: deterministic mode keeps a reduction workspace outside the graph pool")
         self.step = step
         self.warmup = warmup
         self._graphs: Dict[Any, Any] = {}

@@ -111,3 +111,34 @@ def test_unsupported_lora_targets_raise():
     w = FP.build_cuda_model(FP.small_config(layers=1, single=1), {k: v for k, v in __import__("oracle.flux_oracle", fromlist=["x"]).init_flux_params(FP.small_config(layers=1, single=1)).items()}, None, 8)
     with pytest.raises(NotImplementedError):
         w._denoiser().add_adapter(rank=8, target_modules=["norm1.linear"])
+
+
+def test_deterministic_mode_gives_bit_identical_lora_gradients():
+    """`ops.set_deterministic(True)` (or STB_DETERMINISTIC=1): the LoRA weight-gradient kernel writes per-split slabs and a
+    second kernel adds them in index order instead of using fp32 atomics — two runs of the same step agree bit for bit, and
+    stay within the parity tolerances."""
+    from simpletuner_b200 import ops
+
+    def grads():
+        from oracle import flux_oracle as O
+        cfg = FP.small_config(layers=1, single=1)
+        P = {k: v.bfloat16().float() for k, v in O.init_flux_params(cfg, seed=0).items()}
+        L = {k: v.bfloat16().float() for k, v in O.init_lora_params(cfg, 16, seed=1, b_std=0.02).items()}
+        w = FP.build_cuda_model(cfg, P, L, 16)
+        batch = FP.make_batch(3, 24, 40, 77, cfg, seed=2)
+        torch.manual_seed(7); torch.cuda.manual_seed(7)
+        prep = w.prepare_batch({k: v.clone() for k, v in batch.items()}, {"global_step": 0})
+        w.loss(prep, w.model_predict(prep)).backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.clone() for n, p in w._denoiser().named_parameters() if p.grad is not None}
+
+    ops.set_deterministic(True)
+    try:
+        a, b = grads(), grads()
+    finally:
+        ops.set_deterministic(False)
+    assert len(a) == 22 and all(torch.equal(a[k], b[k]) for k in a)
+    c = grads()          # default (atomics) path: same values up to fp32 summation order
+    for k in a:
+        assert torch.allclose(a[k].float(), c[k].float(), rtol=2e-2, atol=1e-6 + 2e-2 * float(c[k].float().abs().max())), k
+    _assert(FP.run_parity(cfg=FP.small_config(layers=1, single=1), seed=21))
