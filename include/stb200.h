@@ -57,6 +57,8 @@ typedef struct {
   const void* w;
   long long w_row_stride;
   int K;
+  int w_kn;  /* 0: w is [N, K] row-major (nn.Linear layout); 1: w is [K, N] row-major, i.e. the contraction index is the ROW
+                of w — the dgrad of a Linear reads the forward weight itself (dx = dy W), no transposed copy.  N % 8 == 0. */
 } stb_gemm_seg;
 
 typedef struct {

@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 class GemmSeg(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("a_batch_stride", C.c_longlong), ("a_row_stride", C.c_longlong),
-        ("w", C.c_void_p), ("w_row_stride", C.c_longlong), ("K", C.c_int),
+        ("w", C.c_void_p), ("w_row_stride", C.c_longlong), ("K", C.c_int), ("w_kn", C.c_int),
     ]
 
 

@@ -205,10 +205,18 @@ int launch_gemm(const stb_gemm_args* a, cudaStream_t st) {
     if (a->num_batches == 1) as[1] = as[0] * (unsigned long long)a->rows_per_batch;
     unsigned ab[3] = {64, 128, 1};
     if (int r = make_map(&maps.a[s], g.a, 3, ad, as, ab)) return r;
-    unsigned long long wd[2] = {(unsigned long long)g.K, (unsigned long long)a->N};
-    unsigned long long ws[1] = {(unsigned long long)g.w_row_stride * 2ull};
-    unsigned wb[2] = {64, (unsigned)(PAIR ? BN / 2 : BN)};   // pair: each CTA stages half of the W rows
-    if (int r = make_map(&maps.w[s], g.w, 2, wd, ws, wb)) return r;
+    if (g.w_kn) {   // [K, N] row-major: contraction index = row; staged as 64 x 64 MN-major boxes
+      unsigned long long wd[2] = {(unsigned long long)a->N, (unsigned long long)g.K};
+      unsigned long long ws[1] = {(unsigned long long)g.w_row_stride * 2ull};
+      unsigned wb[2] = {64, 64};
+      if (int r = make_map(&maps.w[s], g.w, 2, wd, ws, wb)) return r;
+    } else {
+      unsigned long long wd[2] = {(unsigned long long)g.K, (unsigned long long)a->N};
+      unsigned long long ws[1] = {(unsigned long long)g.w_row_stride * 2ull};
+      unsigned wb[2] = {64, (unsigned)(PAIR ? BN / 2 : BN)};   // pair: each CTA stages half of the W rows
+      if (int r = make_map(&maps.w[s], g.w, 2, wd, ws, wb)) return r;
+    }
+    p.w_kn[s] = g.w_kn ? 1 : 0;
     p.kblocks[s] = (g.K + 63) / 64;
     int rem = g.K - (p.kblocks[s] - 1) * 64;
     p.kmmas_last[s] = (rem + 15) / 16;

@@ -38,6 +38,8 @@ struct GemmParams {
   int nseg;
   int kblocks[3];  // ceil(K_seg / 64)
   int kmmas_last[3];  // UMMA_K=16 steps needed in the last k-block of the segment (1..4)
+  int w_kn[3];        // 1: the segment's weight is given as [K, N] row-major (contraction index = row): the B operand is
+                      // staged MN-major (64 k-rows x 64 n-columns SWIZZLE_128B boxes) — dgrad reads W itself, no W^T copy
   int epi;
   int nan_to_num;
   __nv_bfloat16* D;
@@ -60,7 +62,7 @@ struct GemmParams {
 
 struct GemmMaps {
   CUtensorMap a[3];  // 3-D (k, s, b), box (64, 128, 1), SWIZZLE_128B
-  CUtensorMap w[3];  // 2-D (k, n),   box (64, BN),      SWIZZLE_128B
+  CUtensorMap w[3];  // 2-D (k, n),   box (64, BN),      SWIZZLE_128B;  w_kn: 2-D (n, k), box (64, 64)
 };
 
 template <int MT, int BN>
@@ -217,7 +219,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 } else {
                   tma_load_3d_pair(sa, &maps.a[seg], full_bar(stage), kb * 64, s0, b);
                 }
-                tma_load_2d_pair(sa + Cfg::A_BYTES, &maps.w[seg], full_bar(stage), kb * 64, n0 + int(rank) * (BN / 2));
+                if (p.w_kn[seg]) {
+#pragma unroll
+                  for (int g = 0; g < BN / 128; ++g)
+                    tma_load_2d_pair(sa + Cfg::A_BYTES + g * 8192, &maps.w[seg], full_bar(stage), n0 + int(rank) * (BN / 2) + g * 64, kb * 64);
+                } else {
+                  tma_load_2d_pair(sa + Cfg::A_BYTES, &maps.w[seg], full_bar(stage), kb * 64, n0 + int(rank) * (BN / 2));
+                }
               } else {
               mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
               if constexpr (CONV) {
@@ -233,7 +241,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 for (int mt = 0; mt < MT; ++mt)
                   tma_load_3d(sa + mt * Cfg::A_BYTES, &maps.a[seg], full_bar(stage), kb * 64, s0 + mt * 128, b);
               }
-              tma_load_2d(sa + MT * Cfg::A_BYTES, &maps.w[seg], full_bar(stage), kb * 64, n0);
+              if (p.w_kn[seg]) {
+#pragma unroll
+                for (int g = 0; g < BN / 64; ++g)
+                  tma_load_2d(sa + MT * Cfg::A_BYTES + g * 8192, &maps.w[seg], full_bar(stage), n0 + g * 64, kb * 64);
+              } else {
+                tma_load_2d(sa + MT * Cfg::A_BYTES, &maps.w[seg], full_bar(stage), kb * 64, n0);
+              }
               }
             }
             __syncwarp();
@@ -248,7 +262,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
   } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     {
-      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN, 0, 0);
+      constexpr uint32_t idesc_k = make_idesc_bf16(PAIR ? 256 : 128, BN, 0, 0);
+      constexpr uint32_t idesc_mn = make_idesc_bf16(PAIR ? 256 : 128, BN, 0, 1);   // B operand MN-major (w_kn segments)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -265,9 +280,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
             const uint32_t sw = sa + MT * Cfg::A_BYTES;
             const int nk = (kb == p.kblocks[seg] - 1) ? p.kmmas_last[seg] : 4;
+            const bool wkn = p.w_kn[seg] != 0;
+            const uint32_t idesc = wkn ? idesc_mn : idesc_k;
             if (elect_one()) {
               for (int kk = 0; kk < nk; ++kk) {
-                const uint64_t bdesc = sdesc_k(sw, kk * 32);
+                const uint64_t bdesc = wkn ? sdesc_mn(sw, kk * 2048, 8192) : sdesc_k(sw, kk * 32);
                 if constexpr (PAIR) {
                   mma_ss2(d_base, sdesc_k(sa, kk * 32), bdesc, idesc, accumulate);
                 } else {

@@ -66,6 +66,16 @@ def _t(w: torch.Tensor) -> torch.Tensor:
     return w.t().contiguous()
 
 
+# STB_DGRAD_WKN=1: dgrad GEMMs read the forward weights themselves as [K, N] operands (ops.WT) — the transposed copies of
+# every projection (a second copy of all base weights: 24 GB for Flux.1-dev) are never built.
+DGRAD_WKN = _os.environ.get("STB_DGRAD_WKN", "0") == "1"
+
+
+def _wt(w: torch.Tensor):
+    """The dgrad operand of a base weight: a zero-copy transposed view (ops.WT) or, without STB_DGRAD_WKN, a real W^T."""
+    return ops.WT(w) if DGRAD_WKN else w.t().contiguous()
+
+
 @dataclass
 class LoraPack:
     """Per-step packed view of the LoRA matrices of one fused projection group.

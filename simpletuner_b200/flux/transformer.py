@@ -31,7 +31,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .blocks import AttnPlan, DoubleBlockFn, LoraDrop, LoraLinearFn, MlpPlan, SingleBlockFn, TailFn, _t
+from . import blocks as _blocks
+from .blocks import AttnPlan, DoubleBlockFn, LoraDrop, LoraLinearFn, MlpPlan, SingleBlockFn, TailFn, _t, _wt
 
 _ATTN = ["to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_out.0", "to_add_out"]
 _FFS = ["ff.net.0.proj", "ff.net.2", "ff_context.net.0.proj", "ff_context.net.2", "proj_mlp", "proj_out"]
@@ -171,21 +172,25 @@ class _FeedForward(nn.Module):
     _lycoris_class_name = "FeedForward"
 
 
-def _fill_weight(lin: Linear, out: torch.Tensor, out_t: torch.Tensor) -> None:
-    """Write `lin`'s effective weight and its transpose into (slices of) a plan's layouts; with a LoKr adapter both come out of
-    one `stb_lokr_rebuild` pass over W."""
+def _fill_weight(lin: Linear, out: torch.Tensor, out_t: Optional[torch.Tensor]) -> None:
+    """Write `lin`'s effective weight and (unless the dgrad reads W itself, STB_DGRAD_WKN) its transpose into (slices of) a
+    plan's layouts; with a LoKr adapter both come out of one `stb_lokr_rebuild` pass over W."""
     if lin.lokr is None:
         out.copy_(lin.weight.detach())
-        out_t.copy_(lin.weight.detach().t())
+        if out_t is not None:
+            out_t.copy_(lin.weight.detach().t())
     else:
         lin.lokr.rebuild_into(out, out_t)
 
 
-def _weight_pair(lin: Linear) -> Tuple[torch.Tensor, torch.Tensor]:
+def _weight_pair(lin: Linear):
     if lin.lokr is None:
         w = lin.weight.detach()
-        return w, _t(w)
+        return w, _wt(w)
     w = torch.empty_like(lin.weight)
+    if _blocks.DGRAD_WKN:
+        _fill_weight(lin, w, None)
+        return w, _wt(w)
     w_t = torch.empty((lin.in_features, lin.out_features), device=w.device, dtype=w.dtype)
     _fill_weight(lin, w, w_t)
     return w, w_t
@@ -195,13 +200,15 @@ def _attn_plan(q: Linear, k: Linear, v: Linear, out: Optional[Linear], nq, nk) -
     b_qkv = torch.cat([q.bias.detach(), k.bias.detach(), v.bias.detach()], 0).contiguous()
     if q.lokr is None and k.lokr is None and v.lokr is None:
         w_qkv = torch.cat([q.weight.detach(), k.weight.detach(), v.weight.detach()], 0).contiguous()
-        w_qkv_t = _t(w_qkv)
+        w_qkv_t = _wt(w_qkv)
     else:
         n, kin = q.out_features, q.in_features
         w_qkv = torch.empty((3 * n, kin), device=q.weight.device, dtype=q.weight.dtype)
-        w_qkv_t = torch.empty((kin, 3 * n), device=q.weight.device, dtype=q.weight.dtype)
+        w_qkv_t = None if _blocks.DGRAD_WKN else torch.empty((kin, 3 * n), device=q.weight.device, dtype=q.weight.dtype)
         for m, lin in enumerate((q, k, v)):
-            _fill_weight(lin, w_qkv[m * n:(m + 1) * n], w_qkv_t[:, m * n:(m + 1) * n])
+            _fill_weight(lin, w_qkv[m * n:(m + 1) * n], None if w_qkv_t is None else w_qkv_t[:, m * n:(m + 1) * n])
+        if w_qkv_t is None:
+            w_qkv_t = _wt(w_qkv)
     p = AttnPlan(w_qkv, b_qkv, w_qkv_t, norm_q=nq.weight.detach(), norm_k=nk.weight.detach())
     if out is not None:
         p.w_out, p.w_out_t = _weight_pair(out)
@@ -305,8 +312,8 @@ class FluxSingleTransformerBlock(nn.Module):
         if "attn" not in pl:
             pl["attn"] = _attn_plan(a.to_q, a.to_k, a.to_v, None, a.norm_q, a.norm_k)
         if "mlp" not in pl:
-            pl["mlp"] = MlpPlan(self.proj_mlp.weight.detach(), self.proj_mlp.bias.detach(), _t(self.proj_mlp.weight.detach()),
-                                self.proj_out.weight.detach(), self.proj_out.bias.detach(), _t(self.proj_out.weight.detach()))
+            pl["mlp"] = MlpPlan(self.proj_mlp.weight.detach(), self.proj_mlp.bias.detach(), _wt(self.proj_mlp.weight.detach()),
+                                self.proj_out.weight.detach(), self.proj_out.bias.detach(), _wt(self.proj_out.weight.detach()))
         return pl
 
     def drop_adapted_plans(self):
@@ -664,7 +671,7 @@ class FluxTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
             h = self._run_block(i, blk, h, silu_temb, cos, sin, scaling)
         if self._tail_plan is None:
             self._tail_plan = {"w_proj": self.proj_out.weight.detach(), "b_proj": self.proj_out.bias.detach(),
-                               "w_proj_t": _t(self.proj_out.weight.detach())}
+                               "w_proj_t": _wt(self.proj_out.weight.detach())}
         mod = self.norm_out.linear(silu_temb)
         pa, pb = self.proj_out.lora_tensors()
         tail_lora = () if pa is None else (pa, pb)

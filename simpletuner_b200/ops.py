@@ -45,6 +45,26 @@ def _chk(t: torch.Tensor, name: str):
         raise ValueError(f"{name} must be contiguous in its last dimension")
 
 
+class WT:
+    """W^T without a copy: stands for the transpose of a forward weight `w` [N, K] wherever a dgrad GEMM wants W^T [K, N]
+    in nn.Linear layout.  `gemm` hands `w` itself to the kernel as a [K_contract, N_out] operand (stb_gemm_seg.w_kn: the B
+    tile is staged MN-major by TMA), so no transposed copy of the weights exists in HBM.  Row slices of the virtual W^T are
+    column slices of w."""
+    __slots__ = ("w",)
+
+    def __init__(self, w: torch.Tensor):
+        self.w = w
+
+    def __getitem__(self, idx):
+        if isinstance(idx, slice):
+            return WT(self.w[:, idx])
+        raise TypeError("WT supports row slices only")
+
+    @property
+    def shape(self):
+        return (self.w.shape[1], self.w.shape[0])
+
+
 def gemm(
     a_list: Sequence[torch.Tensor],
     w_list: Sequence[torch.Tensor],
@@ -57,17 +77,23 @@ def gemm(
     aux: Optional[torch.Tensor] = None,
     nan_to_num: bool = False,
     tile: Tuple[int, int] = (0, 0),
+    w_kn: Optional[Sequence[bool]] = None,
 ) -> torch.Tensor:
     """out[b, s, :] = epi( sum_i a_list[i][b, s, :] @ w_list[i].T + bias ).
 
-    a_list[i]: [B, S, K_i] or [M, K_i];  w_list[i]: [N, K_i] (nn.Linear layout, row stride free).
+    a_list[i]: [B, S, K_i] or [M, K_i];  w_list[i]: [N, K_i] (nn.Linear layout, row stride free) — or, where w_kn[i] is
+    set, [K_i, N] (the contraction index is the row: `a @ w`, e.g. the dgrad of a Linear on its forward weight).
     gate: [B, N];  res / aux / out: same leading shape as a_list[0] with last dim N.
     """
     nseg = len(a_list)
     assert 1 <= nseg <= 3 and len(w_list) == nseg
+    if any(isinstance(w, WT) for w in w_list):
+        w_kn = [isinstance(w, WT) or bool(w_kn[i] if w_kn is not None else False) for i, w in enumerate(w_list)]
+        w_list = [w.w if isinstance(w, WT) else w for w in w_list]
     a0 = _as3d(a_list[0])
     B, S, _ = a0.shape
-    N = w_list[0].shape[0]
+    kn = list(w_kn) if w_kn is not None else [False] * nseg
+    N = w_list[0].shape[1] if kn[0] else w_list[0].shape[0]
     squeeze = a_list[0].dim() == 2
     if out is None:
         out = torch.empty((B, S, N), device=a0.device, dtype=torch.bfloat16)
@@ -79,11 +105,12 @@ def gemm(
         a3 = _as3d(a)
         _chk(a3, f"a[{i}]")
         _chk(w, f"w[{i}]")
-        if a3.shape[0] != B or a3.shape[1] != S or w.shape[0] != N or w.shape[1] != a3.shape[2]:
+        wn, wk = (w.shape[1], w.shape[0]) if kn[i] else (w.shape[0], w.shape[1])
+        if a3.shape[0] != B or a3.shape[1] != S or wn != N or wk != a3.shape[2]:
             raise ValueError(f"segment {i}: shapes {tuple(a3.shape)} x {tuple(w.shape)} do not match")
         sg = args.seg[i]
         sg.a, sg.a_batch_stride, sg.a_row_stride = a3.data_ptr(), a3.stride(0), a3.stride(1)
-        sg.w, sg.w_row_stride, sg.K = w.data_ptr(), w.stride(0), a3.shape[2]
+        sg.w, sg.w_row_stride, sg.K, sg.w_kn = w.data_ptr(), w.stride(0), a3.shape[2], int(bool(kn[i]))
     args.d, args.d_batch_stride, args.d_row_stride = out3.data_ptr(), out3.stride(0), out3.stride(1)
     args.bias = _ptr(bias)
     args.epi = epi

@@ -25,7 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from ..flux.blocks import AttnPlan, DoubleBlockFn, MlpPlan, TailFn, _t
+from ..flux.blocks import AttnPlan, DoubleBlockFn, MlpPlan, TailFn, _t, _wt
 from ..flux.transformer import AttnProcessorAPI, LoraDropoutAPI, Linear, RMSNormWeight, _AdaNorm, _FeedForward, _TimestepEmbedding, _attn_plan, _lora_list, _sinusoid
 
 SD3_LORA_TARGETS = ["to_k", "to_q", "to_v", "to_out.0"]  # SD3.DEFAULT_LORA_TARGET, reference sd3/model.py:122
@@ -59,10 +59,10 @@ class _NoNorm:
 def _plan(q, k, v, out, nq, nk) -> AttnPlan:
     w_qkv = torch.cat([q.weight.detach(), k.weight.detach(), v.weight.detach()], 0).contiguous()
     b_qkv = torch.cat([q.bias.detach(), k.bias.detach(), v.bias.detach()], 0).contiguous()
-    p = AttnPlan(w_qkv, b_qkv, _t(w_qkv), norm_q=None if nq is None else nq.weight.detach(),
+    p = AttnPlan(w_qkv, b_qkv, _wt(w_qkv), norm_q=None if nq is None else nq.weight.detach(),
                  norm_k=None if nk is None else nk.weight.detach())
     if out is not None:
-        p.w_out, p.b_out, p.w_out_t = out.weight.detach(), out.bias.detach(), _t(out.weight.detach())
+        p.w_out, p.b_out, p.w_out_t = out.weight.detach(), out.bias.detach(), _wt(out.weight.detach())
     return p
 
 
@@ -87,8 +87,8 @@ class JointTransformerBlock(nn.Module):
         if self._plans is None:
             a = self.attn
             g = lambda m, n: getattr(m, n, None)
-            mk = lambda ff: MlpPlan(ff.net[0].proj.weight.detach(), ff.net[0].proj.bias.detach(), _t(ff.net[0].proj.weight.detach()),
-                                    ff.net[2].weight.detach(), ff.net[2].bias.detach(), _t(ff.net[2].weight.detach()))
+            mk = lambda ff: MlpPlan(ff.net[0].proj.weight.detach(), ff.net[0].proj.bias.detach(), _wt(ff.net[0].proj.weight.detach()),
+                                    ff.net[2].weight.detach(), ff.net[2].bias.detach(), _wt(ff.net[2].weight.detach()))
             pl = {
                 "img_attn": _plan(a.to_q, a.to_k, a.to_v, a.to_out[0], g(a, "norm_q"), g(a, "norm_k")),
                 "txt_attn": _plan(a.add_q_proj, a.add_k_proj, a.add_v_proj, g(a, "to_add_out"), g(a, "norm_added_q"), g(a, "norm_added_k")),
@@ -354,7 +354,7 @@ class SD3Transformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
             h = self._run_block(blk, h, silu_temb, S_txt, self._lora_scaling)
         if self._tail_plan is None:
             self._tail_plan = {"w_proj": self.proj_out.weight.detach(), "b_proj": self.proj_out.bias.detach(),
-                               "w_proj_t": _t(self.proj_out.weight.detach())}
+                               "w_proj_t": _wt(self.proj_out.weight.detach())}
         mod = self.norm_out.linear(silu_temb)
         if full:
             out = TailFullFn.apply(h, mod, self.proj_out.weight, self.proj_out.bias, S_txt)

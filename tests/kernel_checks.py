@@ -56,8 +56,9 @@ def gelu_tanh(x):
 
 
 def check_gemm(M=256, N=256, K=128, B=1, bias=False, epi=ops.EPI_STORE, tile=(0, 0), segs=None, strided=False,
-               nan_to_num=False, name=None):
-    """segs: list of extra K sizes appended as additional segments."""
+               nan_to_num=False, name=None, w_kn=None):
+    """segs: list of extra K sizes appended as additional segments.  w_kn[i]: hand segment i's weight over as [K, N]
+    (the contraction index is the row — what a dgrad reads from the forward weight) instead of [N, K]."""
     Ks = [K] + list(segs or [])
     S = M
     a_list, w_list = [], []
@@ -98,7 +99,17 @@ def check_gemm(M=256, N=256, K=128, B=1, bias=False, epi=ops.EPI_STORE, tile=(0,
     if strided:
         outfull = torch.zeros(B, S + 2, N + 8, dtype=torch.bfloat16, device=DEV)
         out = outfull[:, 1:S + 1, :N]
-    got = ops.gemm(a_list, w_list, bias_t, out=out, epi=epi, gate=gate, res=res, aux=aux, nan_to_num=nan_to_num, tile=tile)
+    w_pass = list(w_list)
+    if w_kn is not None:
+        for i, flag in enumerate(w_kn):
+            if flag:                      # [K, N] storage; with `strided` a column range of a wider matrix (row stride > N)
+                if strided:
+                    wide = torch.zeros(w_list[i].shape[1], N + 24, dtype=torch.bfloat16, device=DEV)
+                    wide[:, 8:8 + N] = w_list[i].t()
+                    w_pass[i] = wide[:, 8:8 + N]
+                else:
+                    w_pass[i] = w_list[i].t().contiguous()
+    got = ops.gemm(a_list, w_pass, bias_t, out=out, epi=epi, gate=gate, res=res, aux=aux, nan_to_num=nan_to_num, tile=tile, w_kn=w_kn)
     torch.cuda.synchronize()
     scale = float(ref.abs().max().item())
     r = _report(name or f"gemm_M{M}_N{N}_K{Ks}_B{B}_epi{epi}_tile{tile}", got, ref, atol=scale * 6e-3, rtol=1.6e-2)
@@ -665,4 +676,18 @@ CHECKS.update({
     "lokr_factor_grads_tiny": lambda: check_lokr_factor_grads(a=2, b=3, c=2, d=8, strided=False),
     "gelu_tanh": lambda: check_gelu_tanh(),
     "gelu_matches_gemm_epilogue": lambda: check_gelu_matches_gemm_epilogue(),
+})
+
+
+# --------------------------------------------------------------------------------------------- [K, N] weight segments (dgrad on W itself)
+CHECKS.update({
+    "gemm_wkn_basic": lambda: check_gemm(256, 256, 128, w_kn=[True]),
+    "gemm_wkn_bn64_tails": lambda: check_gemm(200, 72, 200, B=2, w_kn=[True], tile=(1, 64)),
+    "gemm_wkn_bn128_ktail": lambda: check_gemm(300, 136, 72, w_kn=[True], tile=(1, 128)),
+    "gemm_wkn_strided_bias": lambda: check_gemm(333, 320, 192, B=2, bias=True, strided=True, w_kn=[True]),
+    "gemm_wkn_pair": lambda: check_gemm(4096, 3072, 512, w_kn=[True], tile=(3, 256)),
+    "gemm_wkn_pair_tails": lambda: check_gemm(700, 328, 456, B=2, w_kn=[True], tile=(3, 256)),
+    "gemm_wkn_mixed_segments": lambda: check_gemm(512, 384, 256, B=2, segs=[48, 128], w_kn=[True, False, True], tile=(3, 256)),
+    "gemm_wkn_dgelu_epilogue": lambda: check_gemm(256, 512, 128, epi=E.EPI_MUL_DGELU, w_kn=[True]),
+    "gemm_wkn_flux_dgrad": lambda: check_gemm(4608, 3072, 9216, w_kn=[True], tile=(3, 256)),
 })
