@@ -1,7 +1,8 @@
 """Generates tests/golden/text_golden.pt by running the REAL `transformers` classes the reference calls
 (T5EncoderModel / CLIPTextModel, simpletuner/helpers/models/flux/pipeline.py:1085, 1127-1130) on tiny random-weight configs.
-The weights are the oracle's own seeded initialisation loaded into the transformers modules (strict), so the fixture only
-needs to hold the seed, the token ids and the outputs.  Run here (transformers is importable in this container):
+The weights are the oracle's own seeded initialisation, rounded to bf16-representable values (the CUDA path stores bf16
+weights; the fp32 reference then sees exactly the same numbers), loaded into the transformers modules (strict), so the fixture
+only needs to hold the seed, the token ids and the outputs.  Run here (transformers is importable in this container):
     python -m oracle.make_golden_text
 """
 from pathlib import Path
@@ -26,7 +27,7 @@ def main():
                   feed_forward_proj="gated-gelu", dropout_rate=0.0, layer_norm_epsilon=1e-6, is_encoder_decoder=False,
                   use_cache=False, tie_word_embeddings=False)
     m = T5EncoderModel(hf).eval()
-    P = TO.init_params(TO.t5_param_shapes(tc), seed=11)
+    P = {k: v.bfloat16().float() for k, v in TO.init_params(TO.t5_param_shapes(tc), seed=11).items()}   # bf16-representable
     sd = dict(P)
     sd["encoder.embed_tokens.weight"] = P["shared.weight"]
     missing, unexpected = m.load_state_dict(sd, strict=False)
@@ -47,7 +48,7 @@ def main():
                             max_position_embeddings=77, hidden_act="quick_gelu", layer_norm_eps=1e-5, eos_token_id=eos,
                             bos_token_id=0, pad_token_id=1, attention_dropout=0.0)
         m = CLIPTextModel(hf).eval()
-        P = TO.init_params(TO.clip_param_shapes(cc), seed=12)
+        P = {k: v.bfloat16().float() for k, v in TO.init_params(TO.clip_param_shapes(cc), seed=12).items()}
         missing, unexpected = m.load_state_dict(P, strict=False)
         assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
         ids = torch.randint(3, 190, (3, 77))

@@ -300,8 +300,8 @@ qk_rmsnorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ src, long long src_
 // (written into the q / k column ranges of the fused d_qkv buffer).  RMSNorm weights are frozen.
 //   dy = R^T d_out ;  g = dy * w ;  dx = rstd * (g - xhat * mean(g * xhat))
 // DW = false (LoRA / frozen norms): no weight-gradient registers, no shared-memory staging — the round-1 footprint.
-template <int HD, bool DW, int U = 4, int MINB = 1>
-__global__ void __launch_bounds__(256, MINB)
+template <int HD, bool DW>
+__global__ void __launch_bounds__(256)
 qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bfloat16* __restrict__ dk,
                            long long d_b, long long d_s, const __nv_bfloat16* __restrict__ src,
                            long long src_b, long long src_s, int k_off,
@@ -313,6 +313,7 @@ qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bflo
   // dw (optional, full fine-tune): fp32 [4][HD] gradients of the RMSNorm weights (wq0, wk0, wq1, wk1), accumulated with
   // shared-memory atomics per block and one global atomic per entry per block:  dw[i] += (R^T d_out)[i] * xhat[i]
   constexpr int EPL = HD / 32;
+  constexpr int U = 4;
   __shared__ float dw_s[DW ? 4 * HD : 1];
   if constexpr (DW) {
     for (int i = threadIdx.x; i < 4 * HD; i += blockDim.x) dw_s[i] = 0.f;
@@ -426,8 +427,11 @@ qk_rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bflo
 // "Flat" variants of the two kernels above for HD = 128 with frozen norm weights (the LoRA / LoKr training path): one
 // thread = one 16-byte chunk (8 elements) of one head row, 16 lanes = one head row, no per-thread loop — the launch
 // exposes B*S*2H*16 independent threads at ~56 registers instead of one warp walking 48 head rows of a token, i.e. the
-// memory-level parallelism of the plain streaming kernels (gate_mul: 5.2 TB/s) instead of 2.7 / 3.9 TB/s.  The token's
-// cos / sin row (1 KB) is re-read per head row and hits L1 (16 head rows of a token share a block).
+// memory-level parallelism of the plain streaming kernels.  Measured at the Flux shape (B = 4, S = 4608, 24 x 128;
+// tools/one_kernel.py time_rope_bwd): backward 169 us = 4.0 TB/s against 254 us for the warp-per-token loop (and 196-586 us
+// for its occupancy / unroll variants) -> the backward uses this kernel; forward 137 us against 114 us -> the forward keeps
+// the loop kernel (its cos / sin registers are amortised over 48 head rows there).  The token's cos / sin row (1 KB) is
+// re-read per head row and hits L1 (16 head rows of a token share a block).
 // ------------------------------------------------------------------------------------------------
 template <bool BWD>
 __global__ void __launch_bounds__(256)
