@@ -835,6 +835,8 @@ def run_b200(args):
             return inner_step(batch)
         step.check_finite = inner_step.check_finite
     nbat = len(dev_batches)
+    if use_graph:      # every bucket shape must be captured BEFORE the timed region
+        args.warmup = max(args.warmup, nbat)
 
     def barrier():
         if world > 1:

@@ -66,14 +66,21 @@ def _t(w: torch.Tensor) -> torch.Tensor:
     return w.t().contiguous()
 
 
-# STB_DGRAD_WKN=1: dgrad GEMMs read the forward weights themselves as [K, N] operands (ops.WT) — the transposed copies of
-# every projection (a second copy of all base weights: 24 GB for Flux.1-dev) are never built.
-DGRAD_WKN = _os.environ.get("STB_DGRAD_WKN", "0") == "1"
+# Dgrad operand policy.  A dgrad GEMM wants W^T in nn.Linear layout; it can get it as a real transposed copy (K-major B
+# operand, the fastest tile path: Flux LoRA step 362 ms of GEMM) or as a zero-copy view of the forward weight (ops.WT: the
+# kernel stages W as an MN-major B operand; +1.7 % GEMM time, but no second copy of the weights — 16 GB less for Flux.1-dev —
+# and, when the weights CHANGE every step, no per-step transposes at all).  STB_DGRAD_WKN = "auto" (default): the view for
+# weights that change per step (full fine-tune, LoKr), the copy for frozen weights; "1" / "0" force either.
+_WKN_MODE = _os.environ.get("STB_DGRAD_WKN", "auto")
 
 
-def _wt(w: torch.Tensor):
-    """The dgrad operand of a base weight: a zero-copy transposed view (ops.WT) or, without STB_DGRAD_WKN, a real W^T."""
-    return ops.WT(w) if DGRAD_WKN else w.t().contiguous()
+def use_wkn(dynamic: bool = False) -> bool:
+    return _WKN_MODE == "1" or (_WKN_MODE == "auto" and dynamic)
+
+
+def _wt(w: torch.Tensor, dynamic: bool = False):
+    """The dgrad operand of a base weight (see the policy above).  dynamic: the weight is rewritten every optimizer step."""
+    return ops.WT(w) if use_wkn(dynamic) else w.t().contiguous()
 
 
 @dataclass

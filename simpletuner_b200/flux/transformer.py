@@ -188,9 +188,9 @@ def _weight_pair(lin: Linear):
         w = lin.weight.detach()
         return w, _wt(w)
     w = torch.empty_like(lin.weight)
-    if _blocks.DGRAD_WKN:
+    if _blocks.use_wkn(True):          # LoKr: the weight is rebuilt every step -> dgrad reads it in place
         _fill_weight(lin, w, None)
-        return w, _wt(w)
+        return w, _wt(w, True)
     w_t = torch.empty((lin.in_features, lin.out_features), device=w.device, dtype=w.dtype)
     _fill_weight(lin, w, w_t)
     return w, w_t
@@ -204,11 +204,11 @@ def _attn_plan(q: Linear, k: Linear, v: Linear, out: Optional[Linear], nq, nk) -
     else:
         n, kin = q.out_features, q.in_features
         w_qkv = torch.empty((3 * n, kin), device=q.weight.device, dtype=q.weight.dtype)
-        w_qkv_t = None if _blocks.DGRAD_WKN else torch.empty((kin, 3 * n), device=q.weight.device, dtype=q.weight.dtype)
+        w_qkv_t = None if _blocks.use_wkn(True) else torch.empty((kin, 3 * n), device=q.weight.device, dtype=q.weight.dtype)
         for m, lin in enumerate((q, k, v)):
             _fill_weight(lin, w_qkv[m * n:(m + 1) * n], None if w_qkv_t is None else w_qkv_t[:, m * n:(m + 1) * n])
         if w_qkv_t is None:
-            w_qkv_t = _wt(w_qkv)
+            w_qkv_t = _wt(w_qkv, True)
     p = AttnPlan(w_qkv, b_qkv, w_qkv_t, norm_q=nq.weight.detach(), norm_k=nk.weight.detach())
     if out is not None:
         p.w_out, p.w_out_t = _weight_pair(out)

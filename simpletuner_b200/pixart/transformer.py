@@ -32,7 +32,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from ..flux.blocks import EPS, MlpPlan, TailFn, _linear_lora_dgrad, _linear_lora_fwd, _lora_grads, _t, pack_lora
+from ..flux.blocks import EPS, MlpPlan, TailFn, _linear_lora_dgrad, _linear_lora_fwd, _lora_grads, _t, _wt, pack_lora
 from ..flux.transformer import AttnProcessorAPI, LoraDropoutAPI, Linear, _FeedForward, _lora_list, _sinusoid, _TimestepEmbedding
 
 PIXART_LORA_TARGETS = ["to_k", "to_q", "to_v", "to_out.0"]  # PixartSigma.DEFAULT_LORA_TARGET, reference pixart/model.py:59
@@ -224,13 +224,13 @@ class PixArtTransformerBlock(nn.Module):
             w_out2 = _pad_cols(a2.to_out[0].weight.detach(), H, hd, hdp)
             ff = self.ff
             self._plans = {
-                "w_qkv1": w_qkv1, "b_qkv1": torch.cat([bq, bk, bv], 0).contiguous(), "w_qkv1_t": _t(w_qkv1),
-                "w_out1": w_out1, "b_out1": a1.to_out[0].bias.detach(), "w_out1_t": _t(w_out1),
-                "w_q2": w_q2, "b_q2": b_q2, "w_q2_t": _t(w_q2),
+                "w_qkv1": w_qkv1, "b_qkv1": torch.cat([bq, bk, bv], 0).contiguous(), "w_qkv1_t": _wt(w_qkv1),
+                "w_out1": w_out1, "b_out1": a1.to_out[0].bias.detach(), "w_out1_t": _wt(w_out1),
+                "w_q2": w_q2, "b_q2": b_q2, "w_q2_t": _wt(w_q2),
                 "w_kv2": torch.cat([wk2, wv2], 0).contiguous(), "b_kv2": torch.cat([bk2, bv2], 0).contiguous(),
-                "w_out2": w_out2, "b_out2": a2.to_out[0].bias.detach(), "w_out2_t": _t(w_out2),
-                "mlp": MlpPlan(ff.net[0].proj.weight.detach(), ff.net[0].proj.bias.detach(), _t(ff.net[0].proj.weight.detach()),
-                               ff.net[2].weight.detach(), ff.net[2].bias.detach(), _t(ff.net[2].weight.detach())),
+                "w_out2": w_out2, "b_out2": a2.to_out[0].bias.detach(), "w_out2_t": _wt(w_out2),
+                "mlp": MlpPlan(ff.net[0].proj.weight.detach(), ff.net[0].proj.bias.detach(), _wt(ff.net[0].proj.weight.detach()),
+                               ff.net[2].weight.detach(), ff.net[2].bias.detach(), _wt(ff.net[2].weight.detach())),
             }
         return self._plans
 
@@ -510,7 +510,7 @@ class PixArtTransformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
             if keep != self.out_channels:   # PixartSigma keeps `.chunk(2, dim=1)[0]` only (pixart/model.py:313): skip the rest
                 sel = (torch.arange(4, device=dev)[:, None] * self.out_channels + torch.arange(keep, device=dev)[None, :]).reshape(-1)
                 w, b = w[sel].contiguous(), b[sel].contiguous()
-            tp = {"w_proj": w, "b_proj": b, "w_proj_t": _t(w)}
+            tp = {"w_proj": w, "b_proj": b, "w_proj_t": _wt(w)}
             self._tail_plan[keep] = tp
         out = TailFn.apply(h, mod, {"S_txt": 0, **tp})          # [B, S, 4 * keep] in (dy, dx, c) order
         if not _packed_output:

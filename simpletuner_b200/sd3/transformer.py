@@ -56,13 +56,13 @@ class _NoNorm:
     weight = None
 
 
-def _plan(q, k, v, out, nq, nk) -> AttnPlan:
+def _plan(q, k, v, out, nq, nk, dyn: bool = False) -> AttnPlan:
     w_qkv = torch.cat([q.weight.detach(), k.weight.detach(), v.weight.detach()], 0).contiguous()
     b_qkv = torch.cat([q.bias.detach(), k.bias.detach(), v.bias.detach()], 0).contiguous()
-    p = AttnPlan(w_qkv, b_qkv, _wt(w_qkv), norm_q=None if nq is None else nq.weight.detach(),
+    p = AttnPlan(w_qkv, b_qkv, _wt(w_qkv, dyn), norm_q=None if nq is None else nq.weight.detach(),
                  norm_k=None if nk is None else nk.weight.detach())
     if out is not None:
-        p.w_out, p.b_out, p.w_out_t = out.weight.detach(), out.bias.detach(), _wt(out.weight.detach())
+        p.w_out, p.b_out, p.w_out_t = out.weight.detach(), out.bias.detach(), _wt(out.weight.detach(), dyn)
     return p
 
 
@@ -87,18 +87,19 @@ class JointTransformerBlock(nn.Module):
         if self._plans is None:
             a = self.attn
             g = lambda m, n: getattr(m, n, None)
-            mk = lambda ff: MlpPlan(ff.net[0].proj.weight.detach(), ff.net[0].proj.bias.detach(), _wt(ff.net[0].proj.weight.detach()),
-                                    ff.net[2].weight.detach(), ff.net[2].bias.detach(), _wt(ff.net[2].weight.detach()))
+            dyn = bool(getattr(self, "_full_ft", False))      # full fine-tune: the weights change every step
+            mk = lambda ff: MlpPlan(ff.net[0].proj.weight.detach(), ff.net[0].proj.bias.detach(), _wt(ff.net[0].proj.weight.detach(), dyn),
+                                    ff.net[2].weight.detach(), ff.net[2].bias.detach(), _wt(ff.net[2].weight.detach(), dyn))
             pl = {
-                "img_attn": _plan(a.to_q, a.to_k, a.to_v, a.to_out[0], g(a, "norm_q"), g(a, "norm_k")),
-                "txt_attn": _plan(a.add_q_proj, a.add_k_proj, a.add_v_proj, g(a, "to_add_out"), g(a, "norm_added_q"), g(a, "norm_added_k")),
+                "img_attn": _plan(a.to_q, a.to_k, a.to_v, a.to_out[0], g(a, "norm_q"), g(a, "norm_k"), dyn),
+                "txt_attn": _plan(a.add_q_proj, a.add_k_proj, a.add_v_proj, g(a, "to_add_out"), g(a, "norm_added_q"), g(a, "norm_added_k"), dyn),
                 "img_mlp": mk(self.ff),
             }
             if not self.context_pre_only:
                 pl["txt_mlp"] = mk(self.ff_context)
             if self.use_dual_attention:
                 b = self.attn2
-                pl["img_attn2"] = _plan(b.to_q, b.to_k, b.to_v, b.to_out[0], g(b, "norm_q"), g(b, "norm_k"))
+                pl["img_attn2"] = _plan(b.to_q, b.to_k, b.to_v, b.to_out[0], g(b, "norm_q"), g(b, "norm_k"), dyn)
             self._plans = pl
         return self._plans
 
@@ -354,7 +355,7 @@ class SD3Transformer2DModel(AttnProcessorAPI, LoraDropoutAPI, nn.Module):
             h = self._run_block(blk, h, silu_temb, S_txt, self._lora_scaling)
         if self._tail_plan is None:
             self._tail_plan = {"w_proj": self.proj_out.weight.detach(), "b_proj": self.proj_out.bias.detach(),
-                               "w_proj_t": _wt(self.proj_out.weight.detach())}
+                               "w_proj_t": _wt(self.proj_out.weight.detach(), bool(getattr(self, "_full_ft", False)))}
         mod = self.norm_out.linear(silu_temb)
         if full:
             out = TailFullFn.apply(h, mod, self.proj_out.weight, self.proj_out.bias, S_txt)
