@@ -837,6 +837,12 @@ def run_b200(args):
     nbat = len(dev_batches)
     if use_graph:      # every bucket shape must be captured BEFORE the timed region
         args.warmup = max(args.warmup, nbat)
+    if (sd3 or pix) and not args.tiny:
+        # every rank must time the SAME multiset of buckets (ranks only start at different offsets): round the step count up so
+        # that the timed micro-batches are whole cycles of the bucket list
+        import math
+        cyc = nbat // math.gcd(nbat, accum)
+        args.steps = ((args.steps + cyc - 1) // cyc) * cyc
 
     def barrier():
         if world > 1:
