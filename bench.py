@@ -789,7 +789,8 @@ def run_b200(args):
     grad_sync = None
     if world > 1 and args.dp == "flat":
         from simpletuner_b200.training.dist import FlatGradSync
-        grad_sync = FlatGradSync(params)
+        # full fine-tune (5 GB of gradients): 8 chunks, the optimizer of chunk i overlaps the all-reduce of chunk i + 1
+        grad_sync = FlatGradSync(params, pipeline_chunks=(int(os.environ.get("STB_GRAD_CHUNKS", "8")) if sd3 else 0))
     accum = 4 if pix else 1      # BASELINE configs[4]: grad-accum = 4 (a "step" of the PixArt line is one optimizer step = 4 micro-batches)
     step = TrainStep(wrapper, opt, max_grad_norm=(0.01 if pix else 2.0), grad_clip_method="value", grad_sync=grad_sync,
                      gradient_accumulation_steps=accum)
@@ -973,7 +974,7 @@ def run_b200(args):
                 "workload": workload, "config_name": args.config,
                 "global_batch": B * world * accum, "per_gpu_batch": B, "grad_accum": accum,
                 "seq_len": (S_IMG + S_TXT) if not (sd3 or pix) else (1024 + SD3_S_TXT if sd3 else "1024..9216 (+300 cross)"),
-                "parallelism": f"dp{world}", "grad_exchange": (None if world == 1 else args.dp), "cuda_graph": bool(use_graph),
+                "parallelism": f"dp{world}", "grad_exchange": (None if world == 1 else (args.dp + ("+pipelined-optimizer" if (sd3 and args.dp == "flat" and int(os.environ.get("STB_GRAD_CHUNKS", "8")) > 0) else ""))), "cuda_graph": bool(use_graph),
                 "activation_recompute": ("every block re-run in backward (--gradient-checkpointing)" if args.gradient_checkpointing else
                                          "none (block-native minimal saves; reference default would recompute every block)"),
                 "host_syncs_in_step": 0, "l2_policy": "inputs larger than L2 (24 GB of weights + 16 MB fresh batch streamed every step)",

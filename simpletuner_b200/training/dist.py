@@ -107,9 +107,13 @@ class FlatGradSync:
     accumulation boundaries only (the reference's `no_sync` on the other micro-steps).  Parameters are broadcast from
     rank 0 at construction, as DDP does."""
 
-    def __init__(self, params, group=None, broadcast: bool = True):
+    def __init__(self, params, group=None, broadcast: bool = True, pipeline_chunks: int = 0):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        # pipeline_chunks > 0 (large gradient sets: full fine-tune): `start_chunks()` issues one asynchronous coalesced
+        # all-reduce per chunk directly on the gradient tensors (no flat copy) and TrainStep runs the optimizer on chunk i
+        # while chunk i + 1 is still on the wire (training/step.py::_optimizer_step)
+        self.pipeline_chunks = int(pipeline_chunks)
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.sizes = [p.numel() for p in self.params]
         if broadcast and self.world > 1 and self.params:
@@ -135,3 +139,45 @@ class FlatGradSync:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
             flat.div_(self.world)
         torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(flat.split(self.sizes), grads)])
+
+    def chunks(self):
+        """Parameters in `pipeline_chunks` groups of roughly equal size (parameter order kept)."""
+        n = max(1, self.pipeline_chunks)
+        total = sum(self.sizes)
+        target = (total + n - 1) // n
+        out, cur, acc = [], [], 0
+        for p, sz in zip(self.params, self.sizes):
+            cur.append(p)
+            acc += sz
+            if acc >= target and len(out) < n - 1:
+                out.append(cur)
+                cur, acc = [], 0
+        if cur:
+            out.append(cur)
+        return out
+
+    @torch.no_grad()
+    def start_chunks(self):
+        """[(work handle or None, parameters of the chunk)]: the mean all-reduce of every chunk's gradients is in flight (NCCL:
+        one coalesced, asynchronous collective per chunk on NCCL's stream) or already done (other backends)."""
+        out = []
+        for chunk in self.chunks():
+            grads = []
+            for p in chunk:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                grads.append(p.grad)
+            if self.world == 1:
+                out.append((None, chunk))
+                continue
+            if dist.get_backend(self.group) == "nccl":
+                with dist._coalescing_manager(group=self.group, async_ops=True) as cm:     # -> one allreduce_coalesced
+                    for g in grads:
+                        dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+                out.append((cm, chunk))
+            else:
+                for g in grads:
+                    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+                    g.div_(self.world)
+                out.append((None, chunk))
+        return out

@@ -80,19 +80,22 @@ class AdamWBF16(Optimizer):
 
     @torch.no_grad()
     def step(self, zero_grad: bool = False, _rnd: Optional[torch.Tensor] = None, *, grad_clamp: Optional[float] = None,
-             ema=None, ema_global_step: Optional[int] = None):
+             ema=None, ema_global_step: Optional[int] = None, only=None, salt: int = 0):
         """Performs a single optimization step.  `_rnd` (tests only): int32 [4, total] random 16-bit integers, tensors
         concatenated in parameter order, replacing the internal generator.
         grad_clamp: fuse `clip_grad_value_(params, grad_clamp)` (the trainer's default clip, trainer.py:7188-7195) into the
         gradient read.  ema (+ ema_global_step): a training.ema.EMAModel whose update (trainer.py:7352-7357) runs inside the
-        same kernel when it tracks exactly this group's tensors; otherwise `ema.step` runs after the launch."""
+        same kernel when it tracks exactly this group's tensors; otherwise `ema.step` runs after the launch.
+        only (+ salt): update just these parameters (a chunk of a pipelined gradient exchange, training/dist.py); `salt`
+        de-correlates the rounding streams of different chunks."""
+        only_ids = None if only is None else {id(p) for p in only}
         if grad_clamp is not None and not grad_clamp > 0:
             grad_clamp = None
         ema_decay = ema.begin_step(ema_global_step) if ema is not None else None
         ema_done = ema is None or ema_decay is None
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
-            ps = [p for p in group["params"] if p.grad is not None]
+            ps = [p for p in group["params"] if p.grad is not None and (only_ids is None or id(p) in only_ids)]
             if not ps:
                 continue
             lr = group["lr"]
@@ -149,7 +152,7 @@ class AdamWBF16(Optimizer):
             if _rnd is not None:
                 assert _rnd.dtype == torch.int32 and _rnd.is_cuda and _rnd.is_contiguous() and _rnd.shape == (4, pl["total"])
                 rnd_ptr, rnd_plane = _rnd.data_ptr(), pl["total"]
-            seed = (self._seed * 0x9E3779B1 + int(stepf) * 0x85EBCA77) & 0xFFFFFFFFFFFFFFFF
+            seed = (self._seed * 0x9E3779B1 + int(stepf) * 0x85EBCA77 + int(salt) * 0xC2B2AE3D27D4EB4F) & 0xFFFFFFFFFFFFFFFF
             check(_lib.lib().stb_adamw_bf16_multi(
                 pl["ptrs"].data_ptr(), pl["sizes"].data_ptr(), pl["decay"].data_ptr(), pl["blk_tensor"].data_ptr(),
                 pl["blk_off"].data_ptr(), pl["num_blocks"], pl["T"], float(beta1), float(beta2), stepf, float(lr),

@@ -64,6 +64,23 @@ class TrainStep:
             raise ValueError(f"unknown grad_clip_method {self.grad_clip_method}")
         return None
 
+    def _pipelined_ok(self) -> bool:
+        gs = self.grad_sync
+        clipping = self.max_grad_norm is not None and self.max_grad_norm > 0
+        return (gs is not None and getattr(gs, "pipeline_chunks", 0) > 0 and self._fused_opt and not self.track_grad_norm
+                and (not clipping or self.grad_clip_method == "value"))
+
+    def _sync_and_step_pipelined(self):
+        """Full fine-tune sized gradient sets: chunk i's optimizer launch (clip fused) overlaps chunk i + 1's all-reduce."""
+        clamp = float(self.max_grad_norm) if (self.max_grad_norm is not None and self.max_grad_norm > 0) else None
+        ema_decay = self.ema.begin_step(self.state["global_step"] + 1) if self.ema is not None else None
+        for i, (work, chunk) in enumerate(self.grad_sync.start_chunks()):
+            if work is not None:
+                work.wait()          # stream-level wait: the compute stream waits for this chunk's collective only
+            self.optimizer.step(grad_clamp=clamp, only=chunk, salt=i)
+        if ema_decay is not None:
+            self.ema.apply(ema_decay)
+
     def _optimizer_step(self):
         """clip -> optimizer.step -> EMA (trainer.py:7138-7239, 7351-7357); one launch for all three with AdamWBF16."""
         clamp = self._clip()
@@ -91,9 +108,12 @@ class TrainStep:
         self._nonfinite = bad if self._nonfinite is None else (self._nonfinite | bad)
         self.state["micro_step"] += 1
         if sync:
-            if self.grad_sync is not None:
-                self.grad_sync()
-            self._optimizer_step()
+            if self._pipelined_ok():
+                self._sync_and_step_pipelined()
+            else:
+                if self.grad_sync is not None:
+                    self.grad_sync()
+                self._optimizer_step()
             self.optimizer.zero_grad(set_to_none=True)
             den = getattr(self.model, "model", None)
             den = getattr(den, "module", den)
@@ -178,9 +198,12 @@ class GraphedTrainStep:
         bad = ~torch.isfinite(ld)
         st._nonfinite = bad if st._nonfinite is None else (st._nonfinite | bad)
         st.state["micro_step"] += 1
-        if st.grad_sync is not None:
-            st.grad_sync()
-        st._optimizer_step()
+        if st._pipelined_ok():
+            st._sync_and_step_pipelined()
+        else:
+            if st.grad_sync is not None:
+                st.grad_sync()
+            st._optimizer_step()
         # NO zero_grad(set_to_none): the captured backward writes the same .grad tensors again on the next replay
         st.state["global_step"] += 1
         return ld

@@ -164,3 +164,45 @@ def test_flat_grad_sync_gloo_matches_ddp_semantics():
     w0 = ref.model.weight.detach().clone()
     l.backward()
     assert torch.allclose(torch.tensor(res[0][2]), (w0 - 0.1 * ref.model.weight.grad).flatten(), atol=1e-6)
+
+
+def _chunk_worker(rank, world_size, init_method, q):
+    try:
+        dist.init_process_group("gloo", init_method=init_method, rank=rank, world_size=world_size, timeout=timedelta(seconds=30))
+        from simpletuner_b200.training.dist import FlatGradSync
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.randn(n)) for n in (5, 300, 7, 64, 1000, 3)]
+        sync = FlatGradSync(ps, pipeline_chunks=3)
+        for i, p in enumerate(ps):
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+        works = sync.start_chunks()
+        seen = []
+        for work, chunk in works:
+            if work is not None:
+                work.wait()
+            seen += [id(p) for p in chunk]
+        ok = seen == [id(p) for p in ps] and 2 <= len(works) <= 3
+        ok = ok and all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(ps))   # mean of ranks 1, 2
+        q.put(("ok" if ok else "bad", rank, [len(c) for _, c in works]))
+    except BaseException:
+        q.put(("error", rank, traceback.format_exc()))
+        raise
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_pipelined_gradient_chunks_cover_every_parameter_once_and_average():
+    """FlatGradSync(pipeline_chunks=n).start_chunks(): the chunked exchange TrainStep overlaps with the optimizer launches
+    (full fine-tune); world size 2 over Gloo."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with tempfile.TemporaryDirectory() as d:
+        init = f"file://{os.path.join(d, 'rdv')}"
+        procs = [ctx.Process(target=_chunk_worker, args=(r, 2, init, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(90)
+        res = [q.get(timeout=5) for _ in range(2)]
+    assert all(r[0] == "ok" for r in res), res
