@@ -794,10 +794,12 @@ def run_b200(args):
     accum = 4 if pix else 1      # BASELINE configs[4]: grad-accum = 4 (a "step" of the PixArt line is one optimizer step = 4 micro-batches)
     step = TrainStep(wrapper, opt, max_grad_norm=(0.01 if pix else 2.0), grad_clip_method="value", grad_sync=grad_sync,
                      gradient_accumulation_steps=accum)
-    use_graph = args.graph == "on" or (args.graph == "auto" and sd3 and args.dp != "ddp")
+    # auto: the two configs whose step is made of many short kernels (SD3.5-medium at 512^2, PixArt-Sigma) replay CUDA graphs
+    use_graph = args.graph == "on" or (args.graph == "auto" and (sd3 or pix) and args.dp != "ddp")
     if use_graph:
         from simpletuner_b200.training.step import GraphedTrainStep
-        step = GraphedTrainStep(step)
+        # PixArt (epsilon family): the reference draws timesteps on the host -> prepare_batch stays eager, the rest is replayed
+        step = GraphedTrainStep(step, capture_prepare=not pix)
     torch.manual_seed(42 + rank)  # seed_for_each_device=True (trainer.py:2554-2556)
     joint = cfg_over["joint_attention_dim"] if cfg_over else 4096
     pooled = cfg_over["pooled_projection_dim"] if cfg_over else 768

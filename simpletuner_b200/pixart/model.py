@@ -131,12 +131,21 @@ class PixartSigma(Flux):
         B, height, width = nl.shape[0], nl.shape[-2], nl.shape[-1]
         resolution = prepared_batch.get("resolution")
         aspect_ratio = prepared_batch.get("aspect_ratio")
+        # (the fall-back constants are cached per latent shape: building a device tensor from a Python list is a pageable
+        # host-to-device copy, which must not happen inside a CUDA-graph capture of this call)
+        cache = self.__dict__.setdefault("_cond_const_cache", {})
         if resolution is None:
-            resolution = torch.tensor([[height, width]], device=dev).expand(B, -1)
+            key = ("res", height, width, str(dev))
+            if key not in cache:
+                cache[key] = torch.tensor([[height, width]], device=dev)
+            resolution = cache[key].expand(B, -1)
         else:
             resolution = resolution.to(device=dev, dtype=self.config.base_weight_dtype)
         if aspect_ratio is None:
-            aspect_ratio = torch.tensor([[float(height / width)]], device=dev).expand(B, -1)
+            key = ("ar", height, width, str(dev))
+            if key not in cache:
+                cache[key] = torch.tensor([[float(height / width)]], device=dev)
+            aspect_ratio = cache[key].expand(B, -1)
         else:
             aspect_ratio = aspect_ratio.to(device=dev, dtype=self.config.base_weight_dtype)
         return {"resolution": resolution, "aspect_ratio": aspect_ratio}

@@ -155,13 +155,18 @@ class GraphedTrainStep:
     Python / launch path, not by the GPU.  A replay issues the same kernels from one `cudaGraphLaunch`.  The reference has
     no equivalent (its loop is eager); numerics are unchanged — the graph contains exactly the eager launches, and torch's
     CUDA generator is capture-aware, so noise / sigmas still advance every replay.
-    Constraints: gradient_accumulation_steps == 1, no torch DDP wrapper (use `FlatGradSync`), one uniform shape per call
-    (aspect buckets -> one graph per bucket shape), gradients stay allocated between steps (their addresses are baked into
-    the graph), the model must not change structure after the first call."""
+    Constraints: no torch DDP wrapper (use `FlatGradSync`), one uniform shape per call (aspect buckets -> one graph per
+    bucket shape), gradients stay allocated between steps (their addresses are baked into the graph), the model must not
+    change structure after the first call.  gradient_accumulation_steps > 1: every bucket graph ACCUMULATES into one shared,
+    persistent set of gradient buffers (autograd's in-place accumulate is part of the capture); the buffers are zeroed at the
+    start of each accumulation window and the loss is scaled by 1 / accum inside the graph, as TrainStep does eagerly."""
 
-    def __init__(self, step: "TrainStep", warmup: int = 2):
-        if step.accum != 1:
-            raise NotImplementedError("GraphedTrainStep supports gradient_accumulation_steps == 1")
+    def __init__(self, step: "TrainStep", warmup: int = 2, capture_prepare: bool = True):
+        self._shared_grads = step.accum > 1
+        # capture_prepare = False: `prepare_batch` runs eagerly every call and only model_predict -> loss -> backward is
+        # replayed.  Needed by the epsilon / v families, whose timestep draw is host-side in the reference (one CPU
+        # `torch.multinomial(...).item()` per segment, helpers/training/custom_schedule.py:18-58) and must not be frozen into a graph.
+        self.capture_prepare = bool(capture_prepare)
         if hasattr(step.model.model, "no_sync"):
             raise NotImplementedError("GraphedTrainStep: wrap with FlatGradSync instead of torch DDP")
         den = getattr(step.model, "model", None)
@@ -187,10 +192,10 @@ class GraphedTrainStep:
 
     def _body(self, batch):
         st = self.step
-        prepared = st.model.prepare_batch(batch, st.state)
+        prepared = st.model.prepare_batch(batch, st.state) if self.capture_prepare else batch
         out = st.model_predict(prepared)
         loss, _ = st.model.loss_with_logs(prepared, out, apply_conditioning_mask=True)
-        loss.backward()
+        (loss / st.accum if st.accum > 1 else loss).backward()
         return loss.detach()
 
     def _finish(self, ld):
@@ -198,6 +203,8 @@ class GraphedTrainStep:
         bad = ~torch.isfinite(ld)
         st._nonfinite = bad if st._nonfinite is None else (st._nonfinite | bad)
         st.state["micro_step"] += 1
+        if st.state["micro_step"] % st.accum != 0:
+            return ld                      # inside an accumulation window: no exchange, no optimizer
         if st._pipelined_ok():
             st._sync_and_step_pipelined()
         else:
@@ -209,19 +216,26 @@ class GraphedTrainStep:
         return ld
 
     def __call__(self, batch: Dict[str, Any]) -> torch.Tensor:
+        if not self.capture_prepare:          # eager prepare (host-side draws stay live); its output is the graph's input
+            batch = self.step.model.prepare_batch(batch, self.step.state)
         key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.items()) if torch.is_tensor(v))
         entry = self._graphs.get(key)
         if entry is None:
             static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
-            for p in self.step._params:
-                p.grad = None
+            shared = self._shared_grads
+            if shared and getattr(self, "_grad_bufs", None) is None:
+                self._grad_bufs = [torch.zeros_like(p) for p in self.step._params]     # outside every graph pool: persistent
+            keep = [g.clone() for g in self._grad_bufs] if shared else None            # a capture may land mid-window
+            for i, p in enumerate(self.step._params):
+                p.grad = self._grad_bufs[i] if shared else None
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(self.warmup):          # lazy initialisation (weight layouts, tensor maps, smem attributes)
                     self._body(dict(static))
-                    for p in self.step._params:
-                        p.grad = None
+                    if not shared:
+                        for p in self.step._params:
+                            p.grad = None
             torch.cuda.current_stream().wait_stream(side)
             den = getattr(self.step.model, "model", None)
             hook = getattr(den, "before_graph_capture", None)
@@ -234,14 +248,18 @@ class GraphedTrainStep:
                 loss = self._body(dict(static))
             if self._pool is None:
                 self._pool = graph.pool()
+            if shared:       # warm-up runs and the capture pass itself added into the shared buffers: restore the window's state
+                torch._foreach_copy_(self._grad_bufs, keep)
             entry = (graph, static, loss, [p.grad for p in self.step._params], ops.launch_count() - n0)
             self._graphs[key] = entry
         graph, static, loss, grads, n_kernels = entry
         for k, v in batch.items():
             if torch.is_tensor(v):
                 static[k].copy_(v, non_blocking=True)
-        for p, g in zip(self.step._params, grads):       # several bucket graphs own different gradient buffers
+        for p, g in zip(self.step._params, grads):       # several bucket graphs own different gradient buffers (accum == 1)
             p.grad = g
+        if self._shared_grads and self.step.state["micro_step"] % self.step.accum == 0:
+            torch._foreach_zero_(self._grad_bufs)        # start of an accumulation window
         graph.replay()
         from .. import ops
         ops.note_graph_replay(n_kernels)
