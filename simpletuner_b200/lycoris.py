@@ -114,14 +114,14 @@ class LycorisNetwork(nn.Module):
 
     @classmethod
     def apply_preset(cls, preset: Dict) -> None:
-        cls._preset = {"target_module": list(preset.get("target_module", cls._preset["target_module"])),
-                       "module_algo_map": dict(preset.get("module_algo_map", {}))}
         for k in preset:
             if k not in ("target_module", "module_algo_map", "enable_conv", "unet_target_module", "unet_target_name",
                          "target_name", "name_algo_map", "use_fnmatch"):
                 raise NotImplementedError(f"LyCORIS preset key {k!r} is not supported by the libstb200 path")
         if preset.get("name_algo_map") or preset.get("target_name") or preset.get("unet_target_name"):
             raise NotImplementedError("LyCORIS name-based targets are not supported by the libstb200 path")
+        cls._preset = {"target_module": list(preset.get("target_module", cls._preset["target_module"])),
+                       "module_algo_map": dict(preset.get("module_algo_map", {}))}
 
     def __init__(self, model: nn.Module, multiplier: float = 1.0, lora_dim: int = 4, alpha: float = 1.0, factor: int = -1,
                  **unused):
