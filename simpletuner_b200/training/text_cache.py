@@ -145,3 +145,47 @@ def encode_and_cache(prompt_records, clip_ids, t5_ids, t5_masks, text_encoder, t
         write_text_embeds(fn, slice_batch_output_for_cache(out, i, B))
         files.append(fn)
     return files
+
+
+def collate_tensors(tensors):
+    """`compute_prompt_embeddings._collate_tensors` (helpers/training/collate.py:409-451): 2-D [seq, dim] and 1-D entries are
+    stacked, 3-D [1, seq, dim] entries (cached with their batch dimension) concatenated, mixed ranks normalised to 3-D."""
+    tensors = [t for t in tensors if t is not None]
+    if not tensors:
+        return None
+    dims = tensors[0].dim()
+    all_same = all(t.dim() == dims for t in tensors)
+    if dims == 2:
+        return torch.stack(tensors)
+    if dims == 3 and all_same:
+        return torch.cat(tensors, dim=0)
+    if dims == 1:
+        return torch.stack(tensors)
+    normalized = []
+    for t in tensors:
+        if t.dim() in (1, 2):
+            normalized.append(t.unsqueeze(0))
+        elif t.dim() == 3:
+            normalized.append(t)
+        else:
+            raise ValueError(f"Unexpected tensor dimension: {t.dim()} with shape {t.shape}")
+    return torch.cat(normalized, dim=0)
+
+
+def collate_prompt_embeds(text_encoder_output) -> Dict[str, Any]:
+    """The default branch of `compute_prompt_embeddings` (collate.py:453-483): per-prompt cache dicts -> the batch the step
+    consumes (`prompt_embeds`, `pooled_prompt_embeds` -> `add_text_embeds` downstream, `attention_masks`, `time_ids`)."""
+    first = text_encoder_output[0]
+    out: Dict[str, Any] = {}
+    if "prompt_embeds" in first:
+        out["prompt_embeds"] = collate_tensors([t["prompt_embeds"] for t in text_encoder_output])
+    if "pooled_prompt_embeds" in first:
+        out["pooled_prompt_embeds"] = collate_tensors([t["pooled_prompt_embeds"] for t in text_encoder_output])
+    for old in ("attention_mask", "prompt_attention_mask", "attention_masks"):       # old styles first, the new key wins
+        if old in first:
+            out["attention_masks"] = collate_tensors([t[old] for t in text_encoder_output])
+    if "time_ids" in first:
+        out["time_ids"] = collate_tensors([t["time_ids"] for t in text_encoder_output])
+    if not out:
+        raise Exception(f"Could not compute text encoder output: {text_encoder_output}")
+    return out

@@ -97,3 +97,18 @@ def test_encode_and_cache_writes_one_reference_format_file_per_prompt(tmp_path):
     assert a["prompt_embeds"].shape == (1, 12, 16) and a["pooled_prompt_embeds"].shape == (8,) and a["time_ids"] is None
     assert torch.equal(b["prompt_embeds"][0, :, 0].float(), t5_ids[1].float().bfloat16().float())      # (no trimming: Flux keys its mask `attention_masks`)
     assert torch.equal(b["attention_masks"], masks[1:2])
+
+
+def test_collate_of_cached_prompt_dicts():
+    """collate.py:409-483: cached [1, seq, dim] embeds are concatenated, [dim] pooled vectors stacked, None time_ids dropped."""
+    g = torch.Generator().manual_seed(3)
+    recs = [{"prompt_embeds": torch.randn(1, 6, 4, generator=g), "pooled_prompt_embeds": torch.randn(5, generator=g), "time_ids": None,
+             "attention_masks": torch.ones(1, 6, dtype=torch.long)} for _ in range(3)]
+    out = TC.collate_prompt_embeds(recs)
+    assert out["prompt_embeds"].shape == (3, 6, 4) and out["pooled_prompt_embeds"].shape == (3, 5) and out["attention_masks"].shape == (3, 6)
+    assert out["time_ids"] is None
+    assert torch.equal(out["prompt_embeds"][1], recs[1]["prompt_embeds"][0])
+    assert TC.collate_tensors([torch.zeros(6, 4), torch.zeros(6, 4)]).shape == (2, 6, 4)                 # 2-D -> stack
+    assert TC.collate_tensors([torch.zeros(1, 6, 4), torch.zeros(6, 4)]).shape == (2, 6, 4)              # mixed ranks
+    with pytest.raises(Exception):
+        TC.collate_prompt_embeds([{"unknown": 1}])
