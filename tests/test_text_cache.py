@@ -105,7 +105,7 @@ def test_collate_of_cached_prompt_dicts():
     recs = [{"prompt_embeds": torch.randn(1, 6, 4, generator=g), "pooled_prompt_embeds": torch.randn(5, generator=g), "time_ids": None,
              "attention_masks": torch.ones(1, 6, dtype=torch.long)} for _ in range(3)]
     out = TC.collate_prompt_embeds(recs)
-    assert out["prompt_embeds"].shape == (3, 6, 4) and out["pooled_prompt_embeds"].shape == (3, 5) and out["attention_masks"].shape == (3, 6)
+    assert out["prompt_embeds"].shape == (3, 6, 4) and out["pooled_prompt_embeds"].shape == (3, 5) and out["attention_masks"].shape == (3, 1, 6)     # [1, seq] masks are 2-D: stacked
     assert out["time_ids"] is None
     assert torch.equal(out["prompt_embeds"][1], recs[1]["prompt_embeds"][0])
     assert TC.collate_tensors([torch.zeros(6, 4), torch.zeros(6, 4)]).shape == (2, 6, 4)                 # 2-D -> stack
