@@ -35,3 +35,14 @@ def test_reference_citations_have_file_and_line():
     """Every C-ABI declaration block cites a reference file:line (include/stb200.h is the boundary document)."""
     header = (ROOT / "include" / "stb200.h").read_text()
     assert len(re.findall(r"[a-z_/]+\.py:\d+", header)) >= 20
+
+
+def test_cited_repo_files_exist():
+    """Every `tests/...py`, `tools/...`, `oracle/...py` and `simpletuner_b200/...` path quoted in the docs is a real file."""
+    missing = []
+    for doc in ("DESIGN.md", "README.md", "INTEGRATION.md", "profiles/r02/README.md"):
+        text = (ROOT / doc).read_text()
+        for m in re.finditer(r"`((?:tests|tools|oracle|simpletuner_b200)/[A-Za-z0-9_./\-]+\.(?:py|cu|cuh|sh|pt))(?:::[A-Za-z0-9_\[\]\-., =]+)?`", text):
+            if not (ROOT / m.group(1)).exists():
+                missing.append((doc, m.group(1)))
+    assert not missing, missing
