@@ -38,6 +38,8 @@ class TrainStep:
         self.ema = ema                # training.ema.EMAModel over the trainable tensors (trainer.py:7351-7357), or None
         from .optim import AdamWBF16
         self._fused_opt = isinstance(optimizer, AdamWBF16)   # clamp + EMA ride inside the one optimizer launch
+        # optimizers whose step() takes `grad_clamp=`, `only=`, `salt=` can run chunk by chunk behind a pipelined exchange
+        self._chunked_opt = self._fused_opt or bool(getattr(optimizer, "supports_chunked_step", False))
 
     def _clip(self):
         """Gradient clip (trainer.py:7138-7217).  Returns the clamp value when the element clamp is left to the optimizer
@@ -67,7 +69,7 @@ class TrainStep:
     def _pipelined_ok(self) -> bool:
         gs = self.grad_sync
         clipping = self.max_grad_norm is not None and self.max_grad_norm > 0
-        return (gs is not None and getattr(gs, "pipeline_chunks", 0) > 0 and self._fused_opt and not self.track_grad_norm
+        return (gs is not None and getattr(gs, "pipeline_chunks", 0) > 0 and self._chunked_opt and not self.track_grad_norm
                 and (not clipping or self.grad_clip_method == "value"))
 
     def _sync_and_step_pipelined(self):

@@ -206,3 +206,67 @@ def test_pipelined_gradient_chunks_cover_every_parameter_once_and_average():
             p.join(90)
         res = [q.get(timeout=5) for _ in range(2)]
     assert all(r[0] == "ok" for r in res), res
+
+
+class _ChunkSGD(torch.optim.SGD):
+    """SGD with the chunked-step surface of AdamWBF16 (`grad_clamp`, `only`, `salt`) so that the pipelined exchange of
+    TrainStep can be exercised on the CPU."""
+    supports_chunked_step = True
+
+    @torch.no_grad()
+    def step(self, grad_clamp=None, only=None, salt=0, **kw):
+        ids = None if only is None else {id(p) for p in only}
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None or (ids is not None and id(p) not in ids):
+                    continue
+                g = p.grad.clamp(-grad_clamp, grad_clamp) if grad_clamp else p.grad
+                p.add_(g, alpha=-group["lr"])
+
+
+class _Toy3(Toy):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(0)
+        self.model = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(), torch.nn.Linear(8, 4), torch.nn.Linear(4, 4))
+
+
+def _pipe_worker(rank, world_size, init_method, q, chunks):
+    try:
+        dist.init_process_group("gloo", init_method=init_method, rank=rank, world_size=world_size, timeout=timedelta(seconds=30))
+        from simpletuner_b200.training.dist import FlatGradSync
+        w = _Toy3()
+        params = list(w.model.parameters())
+        sync = FlatGradSync(params, pipeline_chunks=chunks)
+        step = TrainStep(w, _ChunkSGD(params, lr=0.1), max_grad_norm=0.05, grad_clip_method="value", grad_sync=sync)
+        assert step._pipelined_ok() == (chunks > 0)
+        for i in range(3):
+            step(_batch(10 * i + rank))
+        q.put(("ok", rank, torch.cat([p.detach().flatten() for p in params]).tolist()))
+    except BaseException:
+        q.put(("error", rank, traceback.format_exc()))
+        raise
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_pipelined_exchange_and_chunked_optimizer_equal_the_flat_path():
+    """TrainStep with FlatGradSync(pipeline_chunks=3) (per-chunk all-reduce -> per-chunk clamp + update) ends at exactly the
+    weights of the flat exchange + one optimizer step, on both ranks (Gloo, world size 2)."""
+    ctx = mp.get_context("spawn")
+    res = {}
+    for chunks in (0, 3):
+        q = ctx.Queue()
+        with tempfile.TemporaryDirectory() as d:
+            init = f"file://{os.path.join(d, 'rdv')}"
+            procs = [ctx.Process(target=_pipe_worker, args=(r, 2, init, q, chunks)) for r in range(2)]
+            for p in procs:
+                p.start()
+            for p in procs:
+                p.join(90)
+            out = sorted((q.get(timeout=5) for _ in procs), key=lambda t: t[1])
+        assert [o[0] for o in out] == ["ok", "ok"], out
+        assert out[0][2] == out[1][2]                      # replicas stay identical
+        res[chunks] = torch.tensor(out[0][2])
+    assert torch.allclose(res[0], res[3], rtol=0, atol=1e-7)
