@@ -113,6 +113,22 @@ def format_text_embedding_flux(text_embedding) -> Dict[str, Any]:
             "attention_masks": masks}
 
 
+def format_text_embedding_pooled(text_embedding) -> Dict[str, Any]:
+    """`SD3._format_text_embedding` / `SDXL._format_text_embedding` (sd3/model.py:369-385, sdxl/model.py:117-133)."""
+    prompt_embeds, pooled_prompt_embeds = text_embedding
+    return {"prompt_embeds": prompt_embeds, "pooled_prompt_embeds": pooled_prompt_embeds.squeeze(0)}
+
+
+def format_text_embedding_pixart(text_embedding) -> Dict[str, Any]:
+    """`PixartSigma._format_text_embedding` (pixart/model.py:176-192)."""
+    prompt_embeds, prompt_attention_mask = text_embedding
+    return {"prompt_embeds": prompt_embeds, "attention_mask": prompt_attention_mask.squeeze(0)}
+
+
+FORMATTERS = {"flux": format_text_embedding_flux, "sd3": format_text_embedding_pooled, "sdxl": format_text_embedding_pooled,
+              "pixart_sigma": format_text_embedding_pixart}
+
+
 def write_text_embeds(filename: str, embeddings: Dict[str, Any]) -> None:
     """`save_to_cache` -> `data_backend.torch_save`: one torch.save per prompt."""
     os.makedirs(os.path.dirname(filename) or ".", exist_ok=True)

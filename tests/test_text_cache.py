@@ -112,3 +112,13 @@ def test_collate_of_cached_prompt_dicts():
     assert TC.collate_tensors([torch.zeros(1, 6, 4), torch.zeros(6, 4)]).shape == (2, 6, 4)              # mixed ranks
     with pytest.raises(Exception):
         TC.collate_prompt_embeds([{"unknown": 1}])
+
+
+def test_family_formatters():
+    pe, pooled, mask = torch.zeros(1, 5, 8), torch.zeros(1, 6), torch.ones(1, 5, dtype=torch.long)
+    assert TC.FORMATTERS["sd3"]((pe, pooled))["pooled_prompt_embeds"].shape == (6,)
+    d = TC.FORMATTERS["pixart_sigma"]((pe, mask))
+    assert set(d) == {"prompt_embeds", "attention_mask"} and d["attention_mask"].shape == (5,)
+    # the PixArt dict is what `slice_batch_output_for_cache` trims by its attention mask
+    out = TC.slice_batch_output_for_cache({"prompt_embeds": torch.zeros(2, 5, 8), "attention_mask": torch.tensor([[1, 1, 1, 0, 0], [1] * 5])}, 0, 2)
+    assert out["prompt_embeds"].shape == (1, 3, 8) and out["attention_mask"].shape == (1, 3)
